@@ -1,0 +1,149 @@
+/*
+ * cmpc.h -- C ABI of the batched, B200-native centroidal-MPC condensed-QP solver.
+ *
+ * Drop-in boundary for ONE path of HuNingHe/Cheeta-MPC: the build + solve that
+ * `CentroidalMPC::UpdateMPC` performs per tick (reference CentroidalMPC.cpp:278-370),
+ * restated as the condensed QP of SURVEY.md §8(a) and solved for B independent
+ * instances per call on one B200.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Each entry point cites the reference interface it replaces (file:line, relative to
+ * the reference root).  The C++ shim with the reference's class/method names lives in
+ * cheeta-mpc_b200/include/CentroidalMPC.h; INTEGRATION.md shows the binding.
+ *
+ * Layouts (all fp64, instance-major outer dimension, reference packing inside):
+ *   state      [B][9+3L]     c(3) v(3) Lm(3) p_i(3)...            CentroidalMPC.cpp:284-291
+ *   des_state  [B][9(N+1)]   3 col-major 3x(N+1) blocks pos|vel|am CentroidalMPC.cpp:297-299
+ *   des_inputs [B][L(4N+3)]  per leg: contact(N) | des_foot_pos 3x(N+1) col-major  :316-317
+ *   forces     [B][L][N][3]  per leg 3xN col-major = the reference's `contact_force_i`
+ *                            controller outputs                    CentroidalMPC.cpp:270
+ *   H          [B][p][p], g [B][p]  with p = 3LN and U index 3L*j + 3*i + r (step-major)
+ *   lam        [B][2][N][L][5] multipliers of the lower (0 <= F f) then upper rows
+ *   active     [B][N][L] uint16: bit r (0..4) lower row r active, bit 5+r upper row r
+ *                            active, bit 15 = leg pinned (swing, contact <= 0)
+ */
+#ifndef CMPC_H_
+#define CMPC_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMPC_MAX_LEGS 4
+#define CMPC_NUM_WEIGHTS (9 + 9 * CMPC_MAX_LEGS)
+#define CMPC_MAX_HORIZON 32
+
+/* per-instance status words (replace the reference's exceptions) */
+enum {
+  CMPC_STATUS_OK = 0,            /* KKT point, active set verified by the polish step     */
+  CMPC_STATUS_OK_IPM = 1,        /* interior-point converged to ipm_tol, polish not accepted */
+  CMPC_STATUS_MAX_ITER = 2,      /* iteration cap hit (IPOPT "Maximum_Iterations" analogue) */
+  CMPC_STATUS_INVALID_TABLE = 3, /* a horizon step with no stance leg: the reference throws
+                                    "mpc table invalid", CentroidalMPC.cpp:328-330         */
+  CMPC_STATUS_NUMERICAL = 4      /* non-finite input or factorisation breakdown           */
+};
+
+/* return codes of the entry points */
+enum {
+  CMPC_OK = 0,
+  CMPC_ERR_ARG = -1,     /* bad argument (the reference asserts, CentroidalMPC.cpp:24-25) */
+  CMPC_ERR_CUDA = -2,    /* CUDA runtime error; text via cmpc_last_error                 */
+  CMPC_ERR_STATE = -3,   /* call order (solve before setup) or batch > max_batch         */
+  CMPC_ERR_NO_DEVICE = -4
+};
+
+/* Constructor arguments of the reference class + solver knobs.
+ * Replaces: CentroidalMPC::CentroidalMPC(mass, num_legs, predict_horizon, time_step,
+ * weights, mu, ipopt_solver) CentroidalMPC.h:26-27 / CentroidalMPC.cpp:13-32 and the IPOPT
+ * option block NonlinearMPC.h:84-100 (tol 1e-8 there). */
+typedef struct cmpc_config {
+  double mass;
+  int32_t num_legs;                 /* 1..CMPC_MAX_LEGS */
+  int32_t horizon;                  /* N, 1..CMPC_MAX_HORIZON */
+  double dt;
+  double mu[CMPC_MAX_LEGS];         /* friction coefficient per leg, > 0 */
+  double weights[CMPC_NUM_WEIGHTS]; /* 9+9L used; index map = CentroidalMPC.cpp:208-231 */
+  int32_t disc_mode;                /* 0 explicit Euler (reference :90-92), 1 zero-order hold */
+  int32_t max_iter;                 /* IPM iteration cap (default 50) */
+  double ipm_tol;                   /* scaled residual + gap tolerance (default 1e-9) */
+  int32_t polish;                   /* 1 = active-set polish (default), 0 = IPM only */
+  int32_t reserved;
+} cmpc_config;
+
+typedef struct cmpc_stats {
+  double kernel_ms;      /* CUDA-event time of the device work of the last call */
+  double h2d_ms, d2h_ms; /* copy phases of cmpc_solve_batch (0 for *_device calls) */
+  double mean_iters;     /* IPM iterations (= Cholesky factorisations of H + C'SC) */
+  int32_t max_iters;
+  int32_t n_ok, n_ok_ipm, n_max_iter, n_invalid, n_numerical;
+  double max_kkt;        /* max scaled KKT residual over instances with status <= 1 */
+  int32_t launches;      /* kernels launched by the call */
+  int32_t reserved;
+} cmpc_stats;
+
+typedef struct cmpc_handle cmpc_handle;
+
+/* Fill cfg with the reference ctor arguments and default solver knobs.
+ * weights has 9+9*num_legs entries, mu has num_legs. */
+int cmpc_config_init(cmpc_config* cfg, double mass, int num_legs, int horizon, double dt,
+                     const double* weights, const double* mu);
+
+/* Replaces the constructor (CentroidalMPC.cpp:13-32). Validates like its asserts. */
+int cmpc_create(const cmpc_config* cfg, cmpc_handle** out);
+
+/* Replaces SetupMPC() (CentroidalMPC.cpp:102-276): one-off allocation of device buffers
+ * for up to max_batch instances on CUDA device `device`, upload of constants. No
+ * allocation happens in the solve calls afterwards. */
+int cmpc_setup(cmpc_handle* h, int max_batch, int device);
+
+/* Replaces NonlinearMPC::UpdateWeights (NonlinearMPC.h:103-105). n = 9+9*num_legs. */
+int cmpc_update_weights(cmpc_handle* h, const double* weights, int n);
+
+/* Replaces UpdateMPC(state, des_state, des_inputs) (CentroidalMPC.cpp:278-370) for B
+ * instances with HOST buffers: H2D, fused build+solve kernel, D2H.  Optional outputs
+ * (iters, kkt, lam, active, stats) may be NULL. */
+int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* des_state,
+                     const double* des_inputs, double* forces, int32_t* status,
+                     int32_t* iters, double* kkt, double* lam, uint16_t* active,
+                     cmpc_stats* stats);
+
+/* Same with DEVICE pointers (inputs already resident in HBM, outputs left in HBM);
+ * asynchronous on the handle's stream unless stats != NULL (then it synchronises). */
+int cmpc_solve_batch_device(cmpc_handle* h, int B, const double* d_state,
+                            const double* d_des_state, const double* d_des_inputs,
+                            double* d_forces, int32_t* d_status, int32_t* d_iters,
+                            double* d_kkt, double* d_lam, uint16_t* d_active,
+                            cmpc_stats* stats);
+
+/* The condensed-QP build alone: H = 2(Bqp' L Bqp + K), g, with swing-leg
+ * rows/cols pinned to identity.  Host buffers.  For parity tests of the build stage. */
+int cmpc_build_batch(cmpc_handle* h, int B, const double* state, const double* des_state,
+                     const double* des_inputs, double* H, double* g, int32_t* status);
+
+/* Closed loop (BASELINE config 5): `ticks` MPC ticks on device; after each solve the
+ * first-step forces drive the reference's nonlinear Euler plant (CentroidalMPC.cpp:85-92),
+ * the contact table is rotated by one step (period = horizon) and the reference
+ * trajectory is re-anchored at the new state.  state is updated in place (host buffers).
+ * force_log (optional) [ticks][B][3L] first-step forces; iters_sum (optional) [B]. */
+int cmpc_rollout(cmpc_handle* h, int B, int ticks, int warm_start, double* state,
+                 double* des_state, double* des_inputs, double* force_log,
+                 int32_t* iters_sum, int32_t* status_or, cmpc_stats* stats);
+
+/* Use an externally owned CUDA stream (cudaStream_t as void*) for all device work. */
+int cmpc_set_stream(cmpc_handle* h, void* cuda_stream);
+int cmpc_synchronize(cmpc_handle* h);
+
+/* FP64 DFMA throughput microbenchmark on the handle's device (TFLOP/s): the roofline
+ * denominator the driver's MEASURED_PEAKS.json does not carry. */
+int cmpc_measure_fp64_peak(cmpc_handle* h, double* tflops);
+
+void cmpc_destroy(cmpc_handle* h);
+const char* cmpc_last_error(const cmpc_handle* h);
+const char* cmpc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMPC_H_ */

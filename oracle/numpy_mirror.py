@@ -1,0 +1,293 @@
+"""NumPy mirror of the condensed centroidal-MPC QP  --  TEST INFRASTRUCTURE ONLY.
+
+This file is an independent, dense, slow restatement of the path in SURVEY.md §8(a).
+It exists to cross-check ``oracle/cmpc_oracle.c`` (the C oracle) and to generate /
+validate the golden vectors under ``tests/golden``.  Nothing in the product path
+(``cheeta-mpc_b200/``) may import it.
+
+PARITY UNPINNED: the reference (``/root/reference/CentroidalMPC.cpp``) returns an empty
+vector from ``UpdateMPC`` (:369) and its only driver asserts nothing
+(``CentoidMPCTest.cpp:113-115``); CasADi/IPOPT/HSL are absent, so no reference output
+exists to pin against.  Every term below cites the reference line it restates.
+
+Layouts (reference ``CentroidalMPC.cpp:278-323``):
+  state      [9+3L]      c(3) v(3) Lm(3) p_i(3)...
+  des_state  [9(N+1)]    three column-major 3x(N+1) blocks: com_pos | com_vel | ang_mom
+  des_inputs [L(4N+3)]   per leg: contact_enable (N) | des_foot_pos 3x(N+1) col-major
+Decision vector U in R^{3LN}, step-major: index 3L*j + 3*i + r  (step j, leg i, xyz r).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+GRAV = 9.81  # CentroidalMPC.cpp:71
+FRIC_UB = 5000.0  # CentroidalMPC.cpp:183
+
+
+def skew(r):
+    return np.array([[0.0, -r[2], r[1]], [r[2], 0.0, -r[0]], [-r[1], r[0], 0.0]])
+
+
+def unpack(cfg, state, des_state, des_inputs):
+    """CentroidalMPC.cpp:284-323 memcpy semantics."""
+    N, L = cfg["horizon"], cfg["num_legs"]
+    state = np.asarray(state, float)
+    des_state = np.asarray(des_state, float)
+    des_inputs = np.asarray(des_inputs, float)
+    x0 = state[:9].copy()
+    feet = state[9:9 + 3 * L].reshape(L, 3)
+    dc = des_state[0:3 * (N + 1)].reshape(N + 1, 3)          # node k -> xyz
+    dv = des_state[3 * (N + 1):6 * (N + 1)].reshape(N + 1, 3)
+    dl = des_state[6 * (N + 1):9 * (N + 1)].reshape(N + 1, 3)
+    contact = np.zeros((L, N))
+    dfoot = np.zeros((L, N + 1, 3))
+    for i in range(L):
+        blk = des_inputs[i * (4 * N + 3):(i + 1) * (4 * N + 3)]
+        contact[i] = blk[:N]
+        dfoot[i] = blk[N:].reshape(N + 1, 3)
+    return x0, feet, dc, dv, dl, contact, dfoot
+
+
+def discretize(cfg, contact_j, r_j):
+    """A_d, B_j, d for one interval (CentroidalMPC.cpp:85-92, lever arms frozen).
+
+    disc_mode 0: explicit Euler (the reference).  1: zero-order hold, obtained here
+    generically from the matrix exponential of the augmented continuous system
+    (series terminates: the augmented matrix is nilpotent of index 3).
+    """
+    m, dt, L = cfg["mass"], cfg["dt"], cfg["num_legs"]
+    Ac = np.zeros((9, 9))
+    Ac[0:3, 3:6] = np.eye(3)
+    Bc = np.zeros((9, 3 * L))
+    for i in range(L):
+        c = contact_j[i] if contact_j[i] > 0 else 0.0
+        Bc[3:6, 3 * i:3 * i + 3] = c / m * np.eye(3)
+        Bc[6:9, 3 * i:3 * i + 3] = c * skew(r_j[i])
+    dc_ = np.zeros(9)
+    dc_[5] = -GRAV
+    if cfg.get("disc_mode", 0) == 0:
+        return np.eye(9) + dt * Ac, dt * Bc, dt * dc_
+    nz = 9 + 3 * L + 1
+    M = np.zeros((nz, nz))
+    M[:9, :9] = Ac * dt
+    M[:9, 9:9 + 3 * L] = Bc * dt
+    M[:9, -1] = dc_ * dt
+    E = np.eye(nz) + M + M @ M / 2.0 + M @ M @ M / 6.0
+    return E[:9, :9], E[:9, 9:9 + 3 * L], E[:9, -1]
+
+
+def build_qp(cfg, state, des_state, des_inputs):
+    """Dense H (p x p), g (p), plus pieces.  Returns dict.  SURVEY §8 a2-a7."""
+    N, L, m = cfg["horizon"], cfg["num_legs"], cfg["mass"]
+    w = np.asarray(cfg["weights"], float)
+    nu, p, q = 3 * L, 3 * L * N, 9 * N
+    x0, feet, dc, dv, dl, contact, dfoot = unpack(cfg, state, des_state, des_inputs)
+    colsum = contact.sum(axis=0)
+    invalid = bool(np.any(colsum <= 0))  # CentroidalMPC.cpp:328-330
+    stance = contact > 0
+
+    Aqp = np.zeros((q, 9))
+    Bqp = np.zeros((q, p))
+    dqp = np.zeros(q)
+    Ad = None
+    Bs, ds = [], []
+    for j in range(N):
+        r_j = dfoot[:, j, :] - dc[j][None, :]
+        Ad, Bj, dj = discretize(cfg, contact[:, j], r_j)
+        Bs.append(Bj)
+        ds.append(dj)
+    Apow = [np.eye(9)]
+    for k in range(N):
+        Apow.append(Ad @ Apow[-1])
+    for k in range(N):
+        Aqp[9 * k:9 * k + 9] = Apow[k + 1]
+        acc = np.zeros(9)
+        for j in range(k + 1):
+            Bqp[9 * k:9 * k + 9, nu * j:nu * j + nu] = Apow[k - j] @ Bs[j]
+            acc += Apow[k - j] @ ds[j]
+        dqp[9 * k:9 * k + 9] = acc
+
+    # cost weights, CentroidalMPC.cpp:203-216 (omega_k inside the square)
+    Lw = np.zeros(q)
+    Xref = np.zeros(q)
+    for k in range(N):
+        node = k + 1
+        om = (w[2] / 2.0) * np.exp(-float(node)) + w[2] / 2.0
+        Lw[9 * k:9 * k + 9] = [w[0], w[1], om * om, w[3], w[4], w[5], w[6], w[7], w[8]]
+        Xref[9 * k:9 * k + 9] = np.concatenate([dc[node], dv[node], dl[node]])
+    # force tracking + rate, CentroidalMPC.cpp:223-231
+    wf = np.zeros(p)
+    Uref = np.zeros(p)
+    D = np.zeros((max(N - 1, 0) * nu, p))
+    wr = np.zeros(max(N - 1, 0) * nu)
+    for j in range(N):
+        for i in range(L):
+            for r in range(3):
+                wf[nu * j + 3 * i + r] = w[9 + 3 * L + 3 * i + r]
+            if stance[i, j] and not invalid:
+                Uref[nu * j + 3 * i + 2] = m * GRAV / colsum[j]  # :331-333
+    for j in range(N - 1):
+        for a in range(nu):
+            D[nu * j + a, nu * j + a] = -1.0
+            D[nu * j + a, nu * (j + 1) + a] = 1.0
+            i, r = divmod(a, 3)
+            wr[nu * j + a] = w[9 + 6 * L + 3 * i + r]
+    K = np.diag(wf) + D.T @ (wr[:, None] * D)
+    H = 2.0 * (Bqp.T @ (Lw[:, None] * Bqp) + K)
+    xfree = Aqp @ x0 + dqp
+    g = 2.0 * Bqp.T @ (Lw * (xfree - Xref)) - 2.0 * wf * Uref
+    cost0 = float((xfree - Xref) @ (Lw * (xfree - Xref)) + Uref @ (wf * Uref))
+
+    pinned = np.ones(p, bool)
+    for j in range(N):
+        for i in range(L):
+            if stance[i, j]:
+                pinned[nu * j + 3 * i:nu * j + 3 * i + 3] = False
+    Hm, gm = H.copy(), g.copy()
+    Hm[pinned, :] = 0.0
+    Hm[:, pinned] = 0.0
+    Hm[pinned, pinned] = 1.0
+    gm[pinned] = 0.0
+    return dict(H=Hm, g=gm, H_raw=H, g_raw=g, pinned=pinned, invalid=invalid, Aqp=Aqp,
+                Bqp=Bqp, dqp=dqp, Lw=Lw, Xref=Xref, K=K, Uref=Uref, wf=wf, x0=x0,
+                contact=contact, stance=stance, cost0=cost0)
+
+
+def constraints(cfg, contact):
+    """Dense C (5 rows per stance leg-step), lb, ub over the FULL U layout.
+    CentroidalMPC.cpp:179-200.  Returns C, lb, ub, rows -> (j, i, r)."""
+    N, L, m = cfg["horizon"], cfg["num_legs"], cfg["mass"]
+    nu = 3 * L
+    rowsC, lb, ub, tags = [], [], [], []
+    for j in range(N):
+        for i in range(L):
+            c = contact[i, j]
+            if c <= 0:
+                continue
+            mu = cfg["mu"][i]
+            F = np.array([[-1, 0, mu], [1, 0, mu], [0, -1, mu], [0, 1, mu], [0, 0, 1.0]])
+            ubv = c * np.array([FRIC_UB] * 4 + [m * GRAV * L])
+            for r in range(5):
+                row = np.zeros(nu * N)
+                row[nu * j + 3 * i:nu * j + 3 * i + 3] = F[r]
+                rowsC.append(row)
+                lb.append(0.0)
+                ub.append(ubv[r])
+                tags.append((j, i, r))
+    return np.array(rowsC), np.array(lb), np.array(ub), tags
+
+
+def solve_active_set(cfg, qp, max_iter=2000, tol=1e-11):
+    """Independent solver: primal active-set on the free variables (textbook,
+    Nocedal & Wright alg. 16.3) started from the interior point f=(0,0,fz_ref).
+    Slow; used only to pin the IPM oracle.  Returns U (full layout), lam_l, lam_u, tags."""
+    p = qp["H"].shape[0]
+    free = np.where(~qp["pinned"])[0]
+    H = qp["H"][np.ix_(free, free)]
+    g = qp["g"][free]
+    C, lb, ub, tags = constraints(cfg, qp["contact"])
+    C = C[:, free]
+    mrows = C.shape[0]
+    # feasible start
+    U0 = np.zeros(p)
+    N, L = cfg["horizon"], cfg["num_legs"]
+    for j in range(N):
+        for i in range(L):
+            if qp["stance"][i, j]:
+                c = qp["contact"][i, j]
+                fzmax = c * cfg["mass"] * GRAV * L
+                U0[3 * L * j + 3 * i + 2] = min(0.5 * fzmax, 0.5 * c * FRIC_UB / cfg["mu"][i])
+    u = U0[free]
+    # working set W: list of (row, side) side=+1 lower (C u >= lb), -1 upper
+    W = []
+    for it in range(max_iter):
+        if W:
+            A = np.array([s * C[r] for r, s in W])
+            KKT = np.block([[H, -A.T], [A, np.zeros((len(W), len(W)))]])
+            rhs = np.concatenate([-(H @ u + g), np.zeros(len(W))])
+            sol = np.linalg.lstsq(KKT, rhs, rcond=None)[0]
+            d, lam = sol[:len(u)], sol[len(u):]
+        else:
+            d = np.linalg.solve(H, -(H @ u + g))
+            lam = np.zeros(0)
+        if np.linalg.norm(d, np.inf) < tol * (1 + np.linalg.norm(u, np.inf)):
+            if len(W) == 0 or lam.min() >= -1e-10:
+                break
+            W.pop(int(np.argmin(lam)))
+            continue
+        alpha, blk = 1.0, None
+        Cd, Cu = C @ d, C @ u
+        inW = set(W)
+        for r in range(mrows):
+            if (r, 1) not in inW and Cd[r] < -1e-14:
+                a = (lb[r] - Cu[r]) / Cd[r]
+                if a < alpha:
+                    alpha, blk = max(a, 0.0), (r, 1)
+            if (r, -1) not in inW and Cd[r] > 1e-14:
+                a = (ub[r] - Cu[r]) / Cd[r]
+                if a < alpha:
+                    alpha, blk = max(a, 0.0), (r, -1)
+        u = u + alpha * d
+        if blk is not None:
+            # keep the working set linearly independent
+            A = np.array([s * C[r] for r, s in W] + [blk[1] * C[blk[0]]])
+            if np.linalg.matrix_rank(A, tol=1e-10) == len(W) + 1:
+                W.append(blk)
+    else:
+        raise RuntimeError("active-set did not converge")
+    U = np.zeros(p)
+    U[free] = u
+    lam_l = np.zeros(mrows)
+    lam_u = np.zeros(mrows)
+    for (r, s), l in zip(W, lam):
+        if s > 0:
+            lam_l[r] = l
+        else:
+            lam_u[r] = l
+    return U, lam_l, lam_u, tags
+
+
+def kkt_residual(cfg, qp, U, lam_l, lam_u):
+    """Scaled KKT residual of (U, lam) on the masked QP; definition shared with the C
+    oracle and the CUDA path."""
+    C, lb, ub, _ = constraints(cfg, qp["contact"])
+    H, g = qp["H"], qp["g"]
+    if C.shape[0] == 0:
+        return float(np.abs(H @ U + g).max() / (1 + np.abs(g).max()))
+    r = H @ U + g - C.T @ lam_l + C.T @ lam_u
+    sl, su = C @ U - lb, ub - C @ U
+    gs, us = 1 + np.abs(g).max(), 1 + np.abs(U).max()
+    stat = np.abs(r).max() / gs
+    prim = max(0.0, (-sl).max(), (-su).max()) / us
+    dual = max(0.0, (-lam_l).max(), (-lam_u).max()) / gs
+    comp = max(np.abs(lam_l * sl).max(), np.abs(lam_u * su).max()) / (gs * us)
+    return float(max(stat, prim, dual, comp))
+
+
+def nonlinear_step(cfg, x, feet, contact_j, forces_j):
+    """Reference plant, verbatim Euler (CentroidalMPC.cpp:85-92); feet fixed."""
+    m, dt, L = cfg["mass"], cfg["dt"], cfg["num_legs"]
+    c, v, lm = x[0:3], x[3:6], x[6:9]
+    acc = np.array([0.0, 0.0, -GRAV])
+    ldot = np.zeros(3)
+    for i in range(L):
+        acc = acc + contact_j[i] / m * forces_j[i]
+        ldot = ldot + contact_j[i] * np.cross(feet[i] - c, forces_j[i])
+    return np.concatenate([c + v * dt, v + acc * dt, lm + ldot * dt])
+
+
+def stage_cost(cfg, qp, U):
+    """Cost by rolling the *linear* condensed dynamics forward and summing the
+    reference's stage costs (CentroidalMPC.cpp:208-231) -- build-vs-evaluate test."""
+    X = qp["Aqp"] @ qp["x0"] + qp["Bqp"] @ U + qp["dqp"]
+    e = X - qp["Xref"]
+    N, L = cfg["horizon"], cfg["num_legs"]
+    nu = 3 * L
+    w = np.asarray(cfg["weights"], float)
+    J = float(e @ (qp["Lw"] * e))
+    J += float((U - qp["Uref"]) @ (qp["wf"] * (U - qp["Uref"])))
+    for j in range(N - 1):
+        for a in range(nu):
+            i, r = divmod(a, 3)
+            J += w[9 + 6 * L + 3 * i + r] * (U[nu * (j + 1) + a] - U[nu * j + a]) ** 2
+    return J
