@@ -1,0 +1,508 @@
+// cmpc_api.cu -- C ABI (include/cmpc.h) over the sm_100a kernels in cmpc_device.cuh.
+// Host side of the drop-in boundary: one handle = one CUDA device + one stream; all
+// device buffers are allocated in cmpc_setup, none in the solve calls.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "cmpc_device.cuh"
+
+using namespace cmpc;
+
+struct cmpc_handle {
+  cmpc_config cfg;
+  DevConfig dev;
+  int device = -1;
+  int max_batch = 0;
+  int num_sms = 0;
+  bool ready = false;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // device buffers
+  double *d_state = nullptr, *d_ds = nullptr, *d_di = nullptr, *d_forces = nullptr, *d_kkt = nullptr,
+         *d_lam = nullptr, *d_scratch = nullptr, *d_flog = nullptr;
+  int32_t *d_status = nullptr, *d_iters = nullptr, *d_iters_sum = nullptr, *d_status_or = nullptr;
+  uint16_t* d_active = nullptr;
+  void* d_stats = nullptr;
+  // launch plan
+  int grid = 0, h_in_smem = 0, m_in_smem = 0, mat_doubles = 0;
+  size_t smem_bytes = 0, scratch_per_cta = 0;
+  std::string err;
+};
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr size_t kMaxSmem = 232448;  // 227 KB opt-in per CTA on sm_100
+
+struct DevStats {
+  unsigned long long iters_sum;
+  int max_iters, n_ok, n_ok_ipm, n_max_iter, n_invalid, n_numerical;
+  unsigned long long max_kkt_bits;
+};
+
+__global__ void stats_kernel(const int32_t* status, const int32_t* iters, const double* kkt, int B, DevStats* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const int st = status[i];
+  if (iters) { atomicAdd(&out->iters_sum, (unsigned long long)iters[i]); atomicMax(&out->max_iters, iters[i]); }
+  if (st == CMPC_STATUS_OK) atomicAdd(&out->n_ok, 1);
+  else if (st == CMPC_STATUS_OK_IPM) atomicAdd(&out->n_ok_ipm, 1);
+  else if (st == CMPC_STATUS_MAX_ITER) atomicAdd(&out->n_max_iter, 1);
+  else if (st == CMPC_STATUS_INVALID_TABLE) atomicAdd(&out->n_invalid, 1);
+  else atomicAdd(&out->n_numerical, 1);
+  if (kkt && st <= CMPC_STATUS_OK_IPM) {
+    double k = kkt[i];
+    if (k >= 0.0) atomicMax(&out->max_kkt_bits, (unsigned long long)__double_as_longlong(k));
+  }
+}
+
+// Closed loop, one tick (BASELINE config 5): plant = the reference's nonlinear Euler step
+// (CentroidalMPC.cpp:85-92) with the TRUE lever arm foot - com and the first-step forces;
+// contact table rotated by one step (period N); reference trajectory and desired feet
+// shifted by one node (last node extrapolated at constant velocity / held).
+__global__ void advance_kernel(const DevConfig cfg, int B, double* state, double* des_state, double* des_inputs,
+                               const double* forces, const int32_t* status, double* flog, int32_t* iters_sum,
+                               const int32_t* iters, int32_t* status_or) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int N = cfg.N, L = cfg.L;
+  const int ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = L * (4 * N + 3), nf = 3 * L * N;
+  double* x = state + (size_t)b * ns;
+  double* ds = des_state + (size_t)b * nds;
+  double* di = des_inputs + (size_t)b * ndi;
+  const double* F = forces + (size_t)b * nf;
+  double acc[3] = {0.0, 0.0, -kGrav}, ld[3] = {0.0, 0.0, 0.0};
+  for (int i = 0; i < L; ++i) {
+    const double ce = di[i * (4 * N + 3)];
+    const double* f = F + (size_t)i * 3 * N;  // step 0 of leg i
+    if (flog) for (int q = 0; q < 3; ++q) flog[(size_t)b * 3 * L + 3 * i + q] = f[q];
+    const double r0 = x[9 + 3 * i] - x[0], r1 = x[9 + 3 * i + 1] - x[1], r2 = x[9 + 3 * i + 2] - x[2];
+    for (int q = 0; q < 3; ++q) acc[q] += ce / cfg.mass * f[q];
+    ld[0] += ce * (r1 * f[2] - r2 * f[1]);
+    ld[1] += ce * (r2 * f[0] - r0 * f[2]);
+    ld[2] += ce * (r0 * f[1] - r1 * f[0]);
+  }
+  double xn[9];
+  for (int q = 0; q < 3; ++q) {
+    xn[q] = x[q] + x[3 + q] * cfg.dt;
+    xn[3 + q] = x[3 + q] + acc[q] * cfg.dt;
+    xn[6 + q] = x[6 + q] + ld[q] * cfg.dt;
+  }
+  for (int q = 0; q < 9; ++q) x[q] = xn[q];
+  // rotate the contact table, shift desired feet
+  for (int i = 0; i < L; ++i) {
+    double* blk = di + i * (4 * N + 3);
+    const double c0 = blk[0];
+    for (int j = 0; j + 1 < N; ++j) blk[j] = blk[j + 1];
+    blk[N - 1] = c0;
+    double* fp = blk + N;
+    for (int k = 0; k < N; ++k)
+      for (int q = 0; q < 3; ++q) fp[3 * k + q] = fp[3 * (k + 1) + q];
+  }
+  // shift the reference: pos extrapolated, vel / angular momentum held
+  for (int blkid = 0; blkid < 3; ++blkid) {
+    double* t = ds + blkid * 3 * (N + 1);
+    double last[3], prev[3];
+    for (int q = 0; q < 3; ++q) { last[q] = t[3 * N + q]; prev[q] = t[3 * (N - 1) + q]; }
+    for (int k = 0; k < N; ++k)
+      for (int q = 0; q < 3; ++q) t[3 * k + q] = t[3 * (k + 1) + q];
+    for (int q = 0; q < 3; ++q) t[3 * N + q] = blkid == 0 ? last[q] + (last[q] - prev[q]) : last[q];
+  }
+  if (iters_sum && iters) iters_sum[b] += iters[b];
+  if (status_or) status_or[b] |= (1 << status[b]);
+}
+
+// FP64 throughput probe: 8 independent DFMA chains per thread.
+__global__ void fp64_peak_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1e-9, a2 = a0 + 2e-9, a3 = a0 + 3e-9;
+  double a4 = a0 + 4e-9, a5 = a0 + 5e-9, a6 = a0 + 6e-9, a7 = a0 + 7e-9;
+  const double m = 0.999999, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int fail(cmpc_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+#define CUDA_TRY(h, expr)                                                                      \
+  do {                                                                                         \
+    cudaError_t e_ = (expr);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(h, CMPC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));       \
+  } while (0)
+
+bool valid_config(const cmpc_config* c) {
+  // the reference asserts mass > 0 && num_legs > 0 && horizon > 0 && mu.size() == num_legs
+  if (!(c->mass > 0) || !std::isfinite(c->mass)) return false;
+  if (c->num_legs < 1 || c->num_legs > CMPC_MAX_LEGS) return false;
+  if (c->horizon < 1 || c->horizon > CMPC_MAX_HORIZON) return false;
+  if (!(c->dt > 0) || !std::isfinite(c->dt)) return false;
+  for (int i = 0; i < c->num_legs; ++i)
+    if (!(c->mu[i] > 0) || !std::isfinite(c->mu[i])) return false;
+  for (int i = 0; i < 9 + 9 * c->num_legs; ++i)
+    if (!(c->weights[i] >= 0) || !std::isfinite(c->weights[i])) return false;
+  // strict convexity of the condensed QP needs positive force-tracking weights (K > 0)
+  for (int i = 0; i < 3 * c->num_legs; ++i)
+    if (!(c->weights[9 + 3 * c->num_legs + i] > 0)) return false;
+  if (c->disc_mode != 0 && c->disc_mode != 1) return false;
+  if (c->max_iter < 1 || !(c->ipm_tol > 0)) return false;
+  return true;
+}
+
+void fill_dev(cmpc_handle* h) {
+  const cmpc_config& c = h->cfg;
+  DevConfig& d = h->dev;
+  d.mass = c.mass; d.dt = c.dt; d.L = c.num_legs; d.N = c.horizon; d.zoh = c.disc_mode;
+  d.max_iter = c.max_iter; d.tol = c.ipm_tol; d.polish = c.polish;
+  for (int i = 0; i < CMPC_MAX_LEGS; ++i) d.mu[i] = c.mu[i];
+  for (int i = 0; i < CMPC_NUM_WEIGHTS; ++i) d.w[i] = c.weights[i];
+}
+
+template <int MODE>
+int launch(cmpc_handle* h, const SolveArgs& a) {
+  cmpc_solve_kernel<kThreads, MODE><<<h->grid < a.B ? h->grid : a.B, kThreads, h->smem_bytes, h->stream>>>(h->dev, a);
+  CUDA_TRY(h, cudaGetLastError());
+  return CMPC_OK;
+}
+
+SolveArgs base_args(cmpc_handle* h, int B) {
+  SolveArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.B = B;
+  a.scratch = h->d_scratch;
+  a.scratch_per_cta = h->scratch_per_cta;
+  a.h_in_smem = h->h_in_smem; a.m_in_smem = h->m_in_smem; a.mat_doubles = h->mat_doubles;
+  return a;
+}
+
+int collect_stats(cmpc_handle* h, int B, const int32_t* d_status, const int32_t* d_iters, const double* d_kkt,
+                  cmpc_stats* stats, int launches) {
+  CUDA_TRY(h, cudaMemsetAsync(h->d_stats, 0, sizeof(DevStats), h->stream));
+  stats_kernel<<<(B + 255) / 256, 256, 0, h->stream>>>(d_status, d_iters, d_kkt, B, (DevStats*)h->d_stats);
+  DevStats hs;
+  CUDA_TRY(h, cudaMemcpyAsync(&hs, h->d_stats, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  stats->mean_iters = B ? (double)hs.iters_sum / B : 0.0;
+  stats->max_iters = hs.max_iters;
+  stats->n_ok = hs.n_ok; stats->n_ok_ipm = hs.n_ok_ipm; stats->n_max_iter = hs.n_max_iter;
+  stats->n_invalid = hs.n_invalid; stats->n_numerical = hs.n_numerical;
+  double mk; std::memcpy(&mk, &hs.max_kkt_bits, 8);
+  stats->max_kkt = mk;
+  stats->launches = launches;
+  return CMPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* cmpc_version(void) { return "cmpc_b200 0.1 (sm_100a)"; }
+
+int cmpc_config_init(cmpc_config* cfg, double mass, int num_legs, int horizon, double dt, const double* weights,
+                     const double* mu) {
+  if (!cfg || !weights || !mu || num_legs < 1 || num_legs > CMPC_MAX_LEGS) return CMPC_ERR_ARG;
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->mass = mass; cfg->num_legs = num_legs; cfg->horizon = horizon; cfg->dt = dt;
+  for (int i = 0; i < num_legs; ++i) cfg->mu[i] = mu[i];
+  for (int i = 0; i < 9 + 9 * num_legs; ++i) cfg->weights[i] = weights[i];
+  cfg->disc_mode = 0; cfg->max_iter = 50; cfg->ipm_tol = 1e-9; cfg->polish = 1;
+  return valid_config(cfg) ? CMPC_OK : CMPC_ERR_ARG;
+}
+
+int cmpc_create(const cmpc_config* cfg, cmpc_handle** out) {
+  if (!cfg || !out) return CMPC_ERR_ARG;
+  *out = nullptr;
+  if (!valid_config(cfg)) return CMPC_ERR_ARG;
+  cmpc_handle* h = new (std::nothrow) cmpc_handle();
+  if (!h) return CMPC_ERR_ARG;
+  h->cfg = *cfg;
+  fill_dev(h);
+  *out = h;
+  return CMPC_OK;
+}
+
+int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
+  if (!h || max_batch < 1) return fail(h, CMPC_ERR_ARG, "cmpc_setup: bad arguments");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(h, CMPC_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(h, CMPC_ERR_ARG, "cmpc_setup: device out of range");
+  CUDA_TRY(h, cudaSetDevice(device));
+  if (h->ready) return fail(h, CMPC_ERR_STATE, "cmpc_setup called twice");
+  h->device = device;
+  cudaDeviceProp prop;
+  CUDA_TRY(h, cudaGetDeviceProperties(&prop, device));
+  h->num_sms = prop.multiProcessorCount;
+  if (!h->stream) { CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+  for (auto& e : h->ev) CUDA_TRY(h, cudaEventCreate(&e));
+
+  const int N = h->cfg.horizon, L = h->cfg.num_legs;
+  const size_t ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = (size_t)L * (4 * N + 3), nf = (size_t)3 * L * N;
+  const size_t B = (size_t)max_batch;
+  CUDA_TRY(h, cudaMalloc(&h->d_state, B * ns * 8));
+  CUDA_TRY(h, cudaMalloc(&h->d_ds, B * nds * 8));
+  CUDA_TRY(h, cudaMalloc(&h->d_di, B * ndi * 8));
+  CUDA_TRY(h, cudaMalloc(&h->d_forces, B * nf * 8));
+  CUDA_TRY(h, cudaMalloc(&h->d_kkt, B * 8));
+  CUDA_TRY(h, cudaMalloc(&h->d_lam, B * 10 * L * N * 8));
+  CUDA_TRY(h, cudaMalloc(&h->d_status, B * 4));
+  CUDA_TRY(h, cudaMalloc(&h->d_iters, B * 4));
+  CUDA_TRY(h, cudaMalloc(&h->d_iters_sum, B * 4));
+  CUDA_TRY(h, cudaMalloc(&h->d_status_or, B * 4));
+  CUDA_TRY(h, cudaMalloc(&h->d_active, B * L * N * 2));
+  CUDA_TRY(h, cudaMalloc(&h->d_stats, sizeof(DevStats)));
+
+  // launch plan: keep H and the factor in shared memory when they fit
+  const int nmax = ((3 * L * N + 3) / 4) * 4;
+  h->mat_doubles = bc4_doubles(nmax);
+  h->h_in_smem = 1; h->m_in_smem = 1;
+  SmemPlan p = make_plan(N, L, 1, 1);
+  if ((size_t)p.total * 8 > kMaxSmem) { h->h_in_smem = 0; p = make_plan(N, L, 0, 1); }
+  if ((size_t)p.total * 8 > kMaxSmem) { h->m_in_smem = 0; p = make_plan(N, L, 0, 0); }
+  if ((size_t)p.total * 8 > kMaxSmem) return fail(h, CMPC_ERR_ARG, "horizon too large for shared-memory vectors");
+  h->smem_bytes = (size_t)p.total * 8;
+  CUDA_TRY(h, cudaFuncSetAttribute(cmpc_solve_kernel<kThreads, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  CUDA_TRY(h, cudaFuncSetAttribute(cmpc_solve_kernel<kThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  int occ = 0;
+  CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cmpc_solve_kernel<kThreads, 0>, kThreads, h->smem_bytes));
+  if (occ < 1) return fail(h, CMPC_ERR_CUDA, "kernel does not fit on an SM");
+  h->grid = std::min<long long>((long long)h->num_sms * occ, (long long)max_batch);
+  h->scratch_per_cta = (size_t)h->mat_doubles * ((h->h_in_smem ? 0 : 1) + (h->m_in_smem ? 0 : 1));
+  if (h->scratch_per_cta) CUDA_TRY(h, cudaMalloc(&h->d_scratch, h->scratch_per_cta * 8 * (size_t)h->grid));
+  h->max_batch = max_batch;
+  h->ready = true;
+  return CMPC_OK;
+}
+
+int cmpc_update_weights(cmpc_handle* h, const double* w, int n) {
+  if (!h || !w || n != 9 + 9 * h->cfg.num_legs) return fail(h, CMPC_ERR_ARG, "cmpc_update_weights: need 9+9*num_legs weights");
+  cmpc_config c = h->cfg;
+  for (int i = 0; i < n; ++i) c.weights[i] = w[i];
+  if (!valid_config(&c)) return fail(h, CMPC_ERR_ARG, "cmpc_update_weights: invalid weights");
+  h->cfg = c;
+  fill_dev(h);  // DevConfig travels as a kernel argument: nothing to upload
+  return CMPC_OK;
+}
+
+int cmpc_set_stream(cmpc_handle* h, void* s) {
+  if (!h) return CMPC_ERR_ARG;
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  h->stream = (cudaStream_t)s;
+  h->own_stream = false;
+  return CMPC_OK;
+}
+
+int cmpc_synchronize(cmpc_handle* h) {
+  if (!h || !h->ready) return fail(h, CMPC_ERR_STATE, "not set up");
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return CMPC_OK;
+}
+
+int cmpc_solve_batch_device(cmpc_handle* h, int B, const double* d_state, const double* d_des_state,
+                            const double* d_des_inputs, double* d_forces, int32_t* d_status, int32_t* d_iters,
+                            double* d_kkt, double* d_lam, uint16_t* d_active, cmpc_stats* stats) {
+  if (!h || !h->ready) return fail(h, CMPC_ERR_STATE, "cmpc_solve_batch_device: call cmpc_setup first");
+  if (B < 0 || B > h->max_batch) return fail(h, CMPC_ERR_STATE, "batch exceeds max_batch given to cmpc_setup");
+  if (!d_state || !d_des_state || !d_des_inputs || !d_forces || !d_status) return fail(h, CMPC_ERR_ARG, "null buffer");
+  if (B == 0) { if (stats) std::memset(stats, 0, sizeof(*stats)); return CMPC_OK; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  SolveArgs a = base_args(h, B);
+  a.state = d_state; a.des_state = d_des_state; a.des_inputs = d_des_inputs;
+  a.forces = d_forces; a.status = d_status;
+  a.iters = d_iters ? d_iters : (stats ? h->d_iters : nullptr);
+  a.kkt = d_kkt ? d_kkt : (stats ? h->d_kkt : nullptr);
+  a.lam = d_lam; a.active = d_active;
+  if (stats) CUDA_TRY(h, cudaEventRecord(h->ev[0], h->stream));
+  int rc = launch<0>(h, a);
+  if (rc) return rc;
+  if (stats) {
+    CUDA_TRY(h, cudaEventRecord(h->ev[1], h->stream));
+    std::memset(stats, 0, sizeof(*stats));
+    rc = collect_stats(h, B, d_status, a.iters, a.kkt, stats, 1);
+    if (rc) return rc;
+    float ms = 0;
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    stats->kernel_ms = ms;
+  }
+  return CMPC_OK;
+}
+
+int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* des_state, const double* des_inputs,
+                     double* forces, int32_t* status, int32_t* iters, double* kkt, double* lam, uint16_t* active,
+                     cmpc_stats* stats) {
+  if (!h || !h->ready) return fail(h, CMPC_ERR_STATE, "cmpc_solve_batch: call cmpc_setup first");
+  if (B < 0 || B > h->max_batch) return fail(h, CMPC_ERR_STATE, "batch exceeds max_batch given to cmpc_setup");
+  if (!state || !des_state || !des_inputs || !forces || !status) return fail(h, CMPC_ERR_ARG, "null buffer");
+  if (B == 0) { if (stats) std::memset(stats, 0, sizeof(*stats)); return CMPC_OK; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const int N = h->cfg.horizon, L = h->cfg.num_legs;
+  const size_t ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = (size_t)L * (4 * N + 3), nf = (size_t)3 * L * N;
+  cudaStream_t s = h->stream;
+  CUDA_TRY(h, cudaEventRecord(h->ev[0], s));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_state, state, B * ns * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_ds, des_state, B * nds * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_di, des_inputs, B * ndi * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaEventRecord(h->ev[1], s));
+  SolveArgs a = base_args(h, B);
+  a.state = h->d_state; a.des_state = h->d_ds; a.des_inputs = h->d_di;
+  a.forces = h->d_forces; a.status = h->d_status; a.iters = h->d_iters; a.kkt = h->d_kkt;
+  a.lam = lam ? h->d_lam : nullptr; a.active = active ? h->d_active : nullptr;
+  int rc = launch<0>(h, a);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaEventRecord(h->ev[2], s));
+  CUDA_TRY(h, cudaMemcpyAsync(forces, h->d_forces, B * nf * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaMemcpyAsync(status, h->d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+  if (iters) CUDA_TRY(h, cudaMemcpyAsync(iters, h->d_iters, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+  if (kkt) CUDA_TRY(h, cudaMemcpyAsync(kkt, h->d_kkt, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+  if (lam) CUDA_TRY(h, cudaMemcpyAsync(lam, h->d_lam, (size_t)B * 10 * L * N * 8, cudaMemcpyDeviceToHost, s));
+  if (active) CUDA_TRY(h, cudaMemcpyAsync(active, h->d_active, (size_t)B * L * N * 2, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaEventRecord(h->ev[3], s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    rc = collect_stats(h, B, h->d_status, h->d_iters, h->d_kkt, stats, 1);
+    if (rc) return rc;
+    float t0 = 0, t1 = 0, t2 = 0;
+    CUDA_TRY(h, cudaEventElapsedTime(&t0, h->ev[0], h->ev[1]));
+    CUDA_TRY(h, cudaEventElapsedTime(&t1, h->ev[1], h->ev[2]));
+    CUDA_TRY(h, cudaEventElapsedTime(&t2, h->ev[2], h->ev[3]));
+    stats->h2d_ms = t0; stats->kernel_ms = t1; stats->d2h_ms = t2;
+  }
+  return CMPC_OK;
+}
+
+int cmpc_build_batch(cmpc_handle* h, int B, const double* state, const double* des_state, const double* des_inputs,
+                     double* H, double* g, int32_t* status) {
+  if (!h || !h->ready) return fail(h, CMPC_ERR_STATE, "cmpc_build_batch: call cmpc_setup first");
+  if (B < 0 || B > h->max_batch) return fail(h, CMPC_ERR_STATE, "batch exceeds max_batch given to cmpc_setup");
+  if (!state || !des_state || !des_inputs || !H || !g || !status) return fail(h, CMPC_ERR_ARG, "null buffer");
+  if (B == 0) return CMPC_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const int N = h->cfg.horizon, L = h->cfg.num_legs;
+  const size_t ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = (size_t)L * (4 * N + 3), p = (size_t)3 * L * N;
+  cudaStream_t s = h->stream;
+  double *dH = nullptr, *dg = nullptr;  // test/diagnostic path: temporary buffers are fine here
+  CUDA_TRY(h, cudaMalloc(&dH, (size_t)B * p * p * 8));
+  CUDA_TRY(h, cudaMalloc(&dg, (size_t)B * p * 8));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_state, state, B * ns * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_ds, des_state, B * nds * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_di, des_inputs, B * ndi * 8, cudaMemcpyHostToDevice, s));
+  SolveArgs a = base_args(h, B);
+  a.state = h->d_state; a.des_state = h->d_ds; a.des_inputs = h->d_di;
+  a.status = h->d_status; a.Hout = dH; a.gout = dg; a.forces = h->d_forces;
+  int rc = launch<1>(h, a);
+  if (rc == CMPC_OK) {
+    cudaMemcpyAsync(H, dH, (size_t)B * p * p * 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(g, dg, (size_t)B * p * 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(status, h->d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, s);
+  }
+  cudaError_t e = cudaStreamSynchronize(s);
+  cudaFree(dH); cudaFree(dg);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, cudaGetErrorString(e));
+  return CMPC_OK;
+}
+
+int cmpc_rollout(cmpc_handle* h, int B, int ticks, int warm_start, double* state, double* des_state,
+                 double* des_inputs, double* force_log, int32_t* iters_sum, int32_t* status_or, cmpc_stats* stats) {
+  (void)warm_start;
+  if (!h || !h->ready) return fail(h, CMPC_ERR_STATE, "cmpc_rollout: call cmpc_setup first");
+  if (B < 1 || B > h->max_batch || ticks < 1) return fail(h, CMPC_ERR_ARG, "cmpc_rollout: bad B or ticks");
+  if (!state || !des_state || !des_inputs) return fail(h, CMPC_ERR_ARG, "null buffer");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const int N = h->cfg.horizon, L = h->cfg.num_legs;
+  const size_t ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = (size_t)L * (4 * N + 3);
+  cudaStream_t s = h->stream;
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_state, state, B * ns * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_ds, des_state, B * nds * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_di, des_inputs, B * ndi * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_iters_sum, 0, (size_t)B * 4, s));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_status_or, 0, (size_t)B * 4, s));
+  double* d_flog = nullptr;
+  if (force_log) CUDA_TRY(h, cudaMalloc(&d_flog, (size_t)ticks * B * 3 * L * 8));
+  SolveArgs a = base_args(h, B);
+  a.state = h->d_state; a.des_state = h->d_ds; a.des_inputs = h->d_di;
+  a.forces = h->d_forces; a.status = h->d_status; a.iters = h->d_iters; a.kkt = h->d_kkt;
+  CUDA_TRY(h, cudaEventRecord(h->ev[0], s));
+  int rc = CMPC_OK;
+  for (int t = 0; t < ticks && rc == CMPC_OK; ++t) {
+    rc = launch<0>(h, a);
+    advance_kernel<<<(B + 127) / 128, 128, 0, s>>>(h->dev, B, h->d_state, h->d_ds, h->d_di, h->d_forces, h->d_status,
+                                                    d_flog ? d_flog + (size_t)t * B * 3 * L : nullptr, h->d_iters_sum,
+                                                    h->d_iters, h->d_status_or);
+  }
+  cudaEventRecord(h->ev[1], s);
+  if (rc == CMPC_OK) {
+    cudaMemcpyAsync(state, h->d_state, B * ns * 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(des_state, h->d_ds, B * nds * 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(des_inputs, h->d_di, B * ndi * 8, cudaMemcpyDeviceToHost, s);
+    if (force_log) cudaMemcpyAsync(force_log, d_flog, (size_t)ticks * B * 3 * L * 8, cudaMemcpyDeviceToHost, s);
+    if (iters_sum) cudaMemcpyAsync(iters_sum, h->d_iters_sum, (size_t)B * 4, cudaMemcpyDeviceToHost, s);
+    if (status_or) cudaMemcpyAsync(status_or, h->d_status_or, (size_t)B * 4, cudaMemcpyDeviceToHost, s);
+  }
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (d_flog) cudaFree(d_flog);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, cudaGetErrorString(e));
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    rc = collect_stats(h, B, h->d_status, h->d_iters, h->d_kkt, stats, 2 * ticks);
+    if (rc) return rc;
+    float ms = 0;
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    stats->kernel_ms = ms;
+  }
+  return CMPC_OK;
+}
+
+int cmpc_measure_fp64_peak(cmpc_handle* h, double* tflops) {
+  if (!h || !h->ready || !tflops) return fail(h, CMPC_ERR_STATE, "not set up");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const int blocks = h->num_sms * 8, threads = 256, iters = 4096;
+  double* d = nullptr;
+  CUDA_TRY(h, cudaMalloc(&d, (size_t)blocks * threads * 8));
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(h->ev[0], h->stream);
+    fp64_peak_kernel<<<blocks, threads, 0, h->stream>>>(d, iters);
+    cudaEventRecord(h->ev[1], h->stream);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { cudaFree(d); return fail(h, CMPC_ERR_CUDA, cudaGetErrorString(e)); }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaFree(d);
+  *tflops = best;
+  return CMPC_OK;
+}
+
+void cmpc_destroy(cmpc_handle* h) {
+  if (!h) return;
+  if (h->device >= 0) cudaSetDevice(h->device);
+  cudaFree(h->d_state); cudaFree(h->d_ds); cudaFree(h->d_di); cudaFree(h->d_forces); cudaFree(h->d_kkt);
+  cudaFree(h->d_lam); cudaFree(h->d_scratch); cudaFree(h->d_status); cudaFree(h->d_iters);
+  cudaFree(h->d_iters_sum); cudaFree(h->d_status_or); cudaFree(h->d_active); cudaFree(h->d_stats);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* cmpc_last_error(const cmpc_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+}  // extern "C"

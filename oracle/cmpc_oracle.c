@@ -598,7 +598,7 @@ int cmpc_oracle_solve(const cmpc_config* c, const double* state, const double* d
   for (int a = 0; a < n; ++a) rd[a] += P.g[a];
   double mu0 = maxabs(rd, n); if (mu0 < 1e-2) mu0 = 1e-2;
   for (int t = 0; t < m; ++t) { zl[t] = mu0 / sl[t]; zu[t] = mu0 / su[t]; }
-  int npolish = 0, numerical = 0;
+  int npolish = 0, numerical = 0, ipm_ok = 0;
   for (it = 0; it <= c->max_iter; ++it) {
     symv(P.H, n, u, rd);
     for (int a = 0; a < n; ++a) rd[a] += P.g[a];
@@ -608,15 +608,22 @@ int cmpc_oracle_solve(const cmpc_config* c, const double* state, const double* d
     for (int t = 0; t < m; ++t) gap += sl[t] * zl[t] + su[t] * zu[t];
     double mu = gap / (2.0 * m);
     double us = 1 + maxabs(u, n);
-    int conv = maxabs(rd, n) <= c->ipm_tol * gs && mu <= c->ipm_tol * gs * us;
-    if (conv) {
-      status = CMPC_STATUS_OK_IPM;
-      if (!c->polish || npolish >= 3) break;
+    /* Convergence. The dual residual has a round-off floor ~ eps * cond(H + C'SC) once the
+     * gap is small, so the polish (which verifies the KKT conditions itself) is attempted
+     * as soon as the gap is converged and the residual is merely small. */
+    double rmax = maxabs(rd, n);
+    int conv_mu = mu <= c->ipm_tol * gs * us;
+    int strict = conv_mu && rmax <= c->ipm_tol * gs;
+    int ready = conv_mu && rmax <= 1e4 * c->ipm_tol * gs;
+    ipm_ok = conv_mu && rmax <= 10 * c->ipm_tol * gs;
+    if (c->polish && ready && npolish < 3) {
       ++npolish;
       for (int t = 0; t < m; ++t) { actl[t] = zl[t] * us > sl[t] * gs; actu[t] = zu[t] * us > su[t] * gs; }
       if (polish(&P, gs, us, actl, actu, u, zl, zu)) { status = CMPC_STATUS_OK; break; }
     }
-    if (it == c->max_iter) { if (!conv) status = CMPC_STATUS_MAX_ITER; break; }
+    if (strict && (!c->polish || npolish >= 3)) break;
+    if (mu <= 1e-8 * c->ipm_tol * gs * us) break; /* far past convergence: stop before 0/0 */
+    if (it == c->max_iter) break;
     /* M = H + C' diag(zl/sl + zu/su) C : only the 3x3 diagonal blocks change */
     memcpy(M, P.H, (size_t)n * n * 8);
     for (int b = 0; b < nb; ++b) {
@@ -667,9 +674,10 @@ int cmpc_oracle_solve(const cmpc_config* c, const double* state, const double* d
     if (!all_finite(u, n)) { numerical = 1; break; }
   }
   if (numerical) status = CMPC_STATUS_NUMERICAL;
+  else if (status != CMPC_STATUS_OK) status = ipm_ok ? CMPC_STATUS_OK_IPM : CMPC_STATUS_MAX_ITER;
   if (status <= CMPC_STATUS_MAX_ITER && !numerical) {
     kkt = kkt_scaled(&P, u, zl, zu);
-    if (status == CMPC_STATUS_OK_IPM) {
+    if (status != CMPC_STATUS_OK) {
       double us = 1 + maxabs(u, n);
       for (int t = 0; t < m; ++t) { actl[t] = zl[t] * us > sl[t] * gs; actu[t] = zu[t] * us > su[t] * gs; }
     }
