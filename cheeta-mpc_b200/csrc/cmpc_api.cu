@@ -26,19 +26,24 @@ struct cmpc_handle {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // device buffers
   double *d_state = nullptr, *d_ds = nullptr, *d_di = nullptr, *d_forces = nullptr, *d_kkt = nullptr,
-         *d_lam = nullptr, *d_scratch = nullptr, *d_flog = nullptr;
+         *d_lam = nullptr, *d_flog = nullptr;
   int32_t *d_status = nullptr, *d_iters = nullptr, *d_iters_sum = nullptr, *d_status_or = nullptr;
   uint16_t* d_active = nullptr;
   void* d_stats = nullptr;
-  // launch plan
-  int grid = 0, h_in_smem = 0, m_in_smem = 0, mat_doubles = 0;
-  size_t smem_bytes = 0, scratch_per_cta = 0;
+  // launch plan: one entry per size class (instances bucketed by free-block count)
+  struct ClassPlan {
+    bool used = false;
+    int W = 1, groups = 1, grid = 0, nbmax = 0, n4max = 0, m_in_smem = 1;
+    size_t smem_bytes = 0, scratch_per_group = 0;
+    double* d_scratch = nullptr;
+  } cls[kNumClasses], exp_plan;
+  int4 bounds = {0, 0, 0, 0};
+  int32_t *d_counts = nullptr, *d_perm = nullptr;  // counts[4] then work[4]
   std::string err;
 };
 
 namespace {
 
-constexpr int kThreads = 256;
 constexpr size_t kMaxSmem = 232448;  // 227 KB opt-in per CTA on sm_100
 
 struct DevStats {
@@ -172,21 +177,69 @@ void fill_dev(cmpc_handle* h) {
   for (int i = 0; i < CMPC_NUM_WEIGHTS; ++i) d.w[i] = c.weights[i];
 }
 
+template <int W, int MODE>
+cudaError_t launch_w(cmpc_handle* h, const cmpc_handle::ClassPlan& p, const SolveArgs& a) {
+  cmpc_solve_kernel<W, MODE><<<p.grid, 32 * W * p.groups, p.smem_bytes, h->stream>>>(h->dev, a);
+  return cudaGetLastError();
+}
+
 template <int MODE>
-int launch(cmpc_handle* h, const SolveArgs& a) {
-  cmpc_solve_kernel<kThreads, MODE><<<h->grid < a.B ? h->grid : a.B, kThreads, h->smem_bytes, h->stream>>>(h->dev, a);
-  CUDA_TRY(h, cudaGetLastError());
+int launch_class(cmpc_handle* h, const cmpc_handle::ClassPlan& p, SolveArgs a) {
+  a.scratch = p.d_scratch; a.scratch_per_group = p.scratch_per_group;
+  a.nbmax = p.nbmax; a.n4max = p.n4max; a.m_in_smem = p.m_in_smem; a.groups = p.groups;
+  cudaError_t e = p.W == 1 ? launch_w<1, MODE>(h, p, a) : p.W == 4 ? launch_w<4, MODE>(h, p, a) : launch_w<8, MODE>(h, p, a);
+  if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
   return CMPC_OK;
 }
 
+// classify + one launch per used size class. Returns the number of kernels launched (<0: error).
+int launch_solve(cmpc_handle* h, SolveArgs a, int B) {
+  if (cudaMemsetAsync(h->d_counts, 0, 2 * kNumClasses * sizeof(int32_t), h->stream) != cudaSuccess)
+    return fail(h, CMPC_ERR_CUDA, "memset counts");
+  classify_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(h->dev, B, a.des_inputs, h->bounds, h->d_counts, h->d_perm);
+  int launches = 1;
+  for (int c = 0; c < kNumClasses; ++c) {
+    if (!h->cls[c].used) continue;
+    a.perm = h->d_perm + (size_t)c * B;
+    a.count = h->d_counts + c;
+    a.work = h->d_counts + kNumClasses + c;
+    int rc = launch_class<0>(h, h->cls[c], a);
+    if (rc) return rc;
+    ++launches;
+  }
+  return launches;
+}
+
 SolveArgs base_args(cmpc_handle* h, int B) {
+  (void)h; (void)B;
   SolveArgs a;
   std::memset(&a, 0, sizeof(a));
-  a.B = B;
-  a.scratch = h->d_scratch;
-  a.scratch_per_cta = h->scratch_per_cta;
-  a.h_in_smem = h->h_in_smem; a.m_in_smem = h->m_in_smem; a.mat_doubles = h->mat_doubles;
   return a;
+}
+
+// Fill a class plan: groups per CTA from the shared-memory budget, grid = one CTA per SM.
+int plan_class(cmpc_handle* h, cmpc_handle::ClassPlan& p, int W, int nbmax, int mode) {
+  const int N = h->cfg.horizon, L = h->cfg.num_legs;
+  p.W = W; p.nbmax = nbmax; p.n4max = ((3 * nbmax + 3) / 4) * 4;
+  p.m_in_smem = 1;
+  SmemPlan sp = make_plan(N, L, p.nbmax, p.n4max, 1);
+  if (mode == 1 || (size_t)sp.total * 8 > kMaxSmem) { p.m_in_smem = 0; sp = make_plan(N, L, p.nbmax, p.n4max, 0); }
+  if ((size_t)sp.total * 8 > kMaxSmem) return fail(h, CMPC_ERR_ARG, "horizon too large for the shared-memory vectors");
+  const int gmax = 256 / (32 * W);
+  p.groups = (int)std::min<size_t>((size_t)gmax, kMaxSmem / ((size_t)sp.total * 8));
+  if (p.groups < 1) p.groups = 1;
+  p.smem_bytes = (size_t)sp.total * 8 * p.groups;
+  p.grid = h->num_sms;
+  p.scratch_per_group = (size_t)bc4_doubles(p.n4max) * (p.m_in_smem ? 1 : 2);
+  CUDA_TRY(h, cudaMalloc(&p.d_scratch, p.scratch_per_group * 8 * (size_t)p.grid * p.groups));
+  p.used = true;
+  return CMPC_OK;
+}
+
+template <int W, int MODE>
+int set_smem_attr(cmpc_handle* h, size_t bytes) {
+  CUDA_TRY(h, cudaFuncSetAttribute(cmpc_solve_kernel<W, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return CMPC_OK;
 }
 
 int collect_stats(cmpc_handle* h, int B, const int32_t* d_status, const int32_t* d_iters, const double* d_kkt,
@@ -266,23 +319,39 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
   CUDA_TRY(h, cudaMalloc(&h->d_active, B * L * N * 2));
   CUDA_TRY(h, cudaMalloc(&h->d_stats, sizeof(DevStats)));
 
-  // launch plan: keep H and the factor in shared memory when they fit
-  const int nmax = ((3 * L * N + 3) / 4) * 4;
-  h->mat_doubles = bc4_doubles(nmax);
-  h->h_in_smem = 1; h->m_in_smem = 1;
-  SmemPlan p = make_plan(N, L, 1, 1);
-  if ((size_t)p.total * 8 > kMaxSmem) { h->h_in_smem = 0; p = make_plan(N, L, 0, 1); }
-  if ((size_t)p.total * 8 > kMaxSmem) { h->m_in_smem = 0; p = make_plan(N, L, 0, 0); }
-  if ((size_t)p.total * 8 > kMaxSmem) return fail(h, CMPC_ERR_ARG, "horizon too large for shared-memory vectors");
-  h->smem_bytes = (size_t)p.total * 8;
-  CUDA_TRY(h, cudaFuncSetAttribute(cmpc_solve_kernel<kThreads, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-  CUDA_TRY(h, cudaFuncSetAttribute(cmpc_solve_kernel<kThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-  int occ = 0;
-  CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cmpc_solve_kernel<kThreads, 0>, kThreads, h->smem_bytes));
-  if (occ < 1) return fail(h, CMPC_ERR_CUDA, "kernel does not fit on an SM");
-  h->grid = std::min<long long>((long long)h->num_sms * occ, (long long)max_batch);
-  h->scratch_per_cta = (size_t)h->mat_doubles * ((h->h_in_smem ? 0 : 1) + (h->m_in_smem ? 0 : 1));
-  if (h->scratch_per_cta) CUDA_TRY(h, cudaMalloc(&h->d_scratch, h->scratch_per_cta * 8 * (size_t)h->grid));
+  CUDA_TRY(h, cudaMalloc(&h->d_counts, 2 * kNumClasses * sizeof(int32_t)));
+  CUDA_TRY(h, cudaMalloc(&h->d_perm, (size_t)kNumClasses * B * sizeof(int32_t)));
+  // size classes by number of free 3-blocks: n4 <= 64 -> one warp per instance, n4 <= 128 ->
+  // four warps, larger -> a whole 256-thread CTA; the factor lives in shared memory whenever it fits
+  {
+    const int nbfull = L * N;
+    const int cap[kNumClasses] = {21, 42, 64, nbfull};
+    const int Wc[kNumClasses] = {1, 4, 8, 8};
+    int b[kNumClasses];
+    int lower = 0;
+    for (int c = 0; c < kNumClasses; ++c) {
+      b[c] = std::min(cap[c], nbfull);
+      if (c == kNumClasses - 1) b[c] = nbfull;
+      if (lower < nbfull && b[c] > lower) {
+        int rc = plan_class(h, h->cls[c], Wc[c], b[c], 0);
+        if (rc) return rc;
+      }
+      lower = std::max(lower, b[c]);
+    }
+    h->bounds = make_int4(b[0], b[1], b[2], b[3]);
+    int rc = plan_class(h, h->exp_plan, 8, nbfull, 1);
+    if (rc) return rc;
+    size_t s1 = 0, s4 = 0, s8 = 0;
+    for (int c = 0; c < kNumClasses; ++c) {
+      if (!h->cls[c].used) continue;
+      size_t& sref = h->cls[c].W == 1 ? s1 : h->cls[c].W == 4 ? s4 : s8;
+      sref = std::max(sref, h->cls[c].smem_bytes);
+    }
+    if (s1 && (rc = set_smem_attr<1, 0>(h, s1))) return rc;
+    if (s4 && (rc = set_smem_attr<4, 0>(h, s4))) return rc;
+    if (s8 && (rc = set_smem_attr<8, 0>(h, s8))) return rc;
+    if ((rc = set_smem_attr<8, 1>(h, h->exp_plan.smem_bytes))) return rc;
+  }
   h->max_batch = max_batch;
   h->ready = true;
   return CMPC_OK;
@@ -327,12 +396,13 @@ int cmpc_solve_batch_device(cmpc_handle* h, int B, const double* d_state, const 
   a.kkt = d_kkt ? d_kkt : (stats ? h->d_kkt : nullptr);
   a.lam = d_lam; a.active = d_active;
   if (stats) CUDA_TRY(h, cudaEventRecord(h->ev[0], h->stream));
-  int rc = launch<0>(h, a);
-  if (rc) return rc;
+  int rc = launch_solve(h, a, B);
+  if (rc < 0) return rc;
+  const int launches = rc;
   if (stats) {
     CUDA_TRY(h, cudaEventRecord(h->ev[1], h->stream));
     std::memset(stats, 0, sizeof(*stats));
-    rc = collect_stats(h, B, d_status, a.iters, a.kkt, stats, 1);
+    rc = collect_stats(h, B, d_status, a.iters, a.kkt, stats, launches);
     if (rc) return rc;
     float ms = 0;
     CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
@@ -361,8 +431,9 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
   a.state = h->d_state; a.des_state = h->d_ds; a.des_inputs = h->d_di;
   a.forces = h->d_forces; a.status = h->d_status; a.iters = h->d_iters; a.kkt = h->d_kkt;
   a.lam = lam ? h->d_lam : nullptr; a.active = active ? h->d_active : nullptr;
-  int rc = launch<0>(h, a);
-  if (rc) return rc;
+  int rc = launch_solve(h, a, B);
+  if (rc < 0) return rc;
+  const int launches = rc;
   CUDA_TRY(h, cudaEventRecord(h->ev[2], s));
   CUDA_TRY(h, cudaMemcpyAsync(forces, h->d_forces, B * nf * 8, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(h, cudaMemcpyAsync(status, h->d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
@@ -374,7 +445,7 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
   CUDA_TRY(h, cudaStreamSynchronize(s));
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
-    rc = collect_stats(h, B, h->d_status, h->d_iters, h->d_kkt, stats, 1);
+    rc = collect_stats(h, B, h->d_status, h->d_iters, h->d_kkt, stats, launches);
     if (rc) return rc;
     float t0 = 0, t1 = 0, t2 = 0;
     CUDA_TRY(h, cudaEventElapsedTime(&t0, h->ev[0], h->ev[1]));
@@ -404,7 +475,9 @@ int cmpc_build_batch(cmpc_handle* h, int B, const double* state, const double* d
   SolveArgs a = base_args(h, B);
   a.state = h->d_state; a.des_state = h->d_ds; a.des_inputs = h->d_di;
   a.status = h->d_status; a.Hout = dH; a.gout = dg; a.forces = h->d_forces;
-  int rc = launch<1>(h, a);
+  a.count = nullptr; a.count_imm = B; a.perm = nullptr; a.work = h->d_counts + kNumClasses;
+  cudaMemsetAsync(h->d_counts, 0, 2 * kNumClasses * sizeof(int32_t), s);
+  int rc = launch_class<1>(h, h->exp_plan, a);
   if (rc == CMPC_OK) {
     cudaMemcpyAsync(H, dH, (size_t)B * p * p * 8, cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(g, dg, (size_t)B * p * 8, cudaMemcpyDeviceToHost, s);
@@ -439,8 +512,12 @@ int cmpc_rollout(cmpc_handle* h, int B, int ticks, int warm_start, double* state
   a.forces = h->d_forces; a.status = h->d_status; a.iters = h->d_iters; a.kkt = h->d_kkt;
   CUDA_TRY(h, cudaEventRecord(h->ev[0], s));
   int rc = CMPC_OK;
+  int launches = 0;
   for (int t = 0; t < ticks && rc == CMPC_OK; ++t) {
-    rc = launch<0>(h, a);
+    rc = launch_solve(h, a, B);
+    if (rc < 0) break;
+    launches += rc + 1;
+    rc = CMPC_OK;
     advance_kernel<<<(B + 127) / 128, 128, 0, s>>>(h->dev, B, h->d_state, h->d_ds, h->d_di, h->d_forces, h->d_status,
                                                     d_flog ? d_flog + (size_t)t * B * 3 * L : nullptr, h->d_iters_sum,
                                                     h->d_iters, h->d_status_or);
@@ -460,7 +537,7 @@ int cmpc_rollout(cmpc_handle* h, int B, int ticks, int warm_start, double* state
   if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, cudaGetErrorString(e));
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
-    rc = collect_stats(h, B, h->d_status, h->d_iters, h->d_kkt, stats, 2 * ticks);
+    rc = collect_stats(h, B, h->d_status, h->d_iters, h->d_kkt, stats, launches);
     if (rc) return rc;
     float ms = 0;
     CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
@@ -496,7 +573,9 @@ void cmpc_destroy(cmpc_handle* h) {
   if (!h) return;
   if (h->device >= 0) cudaSetDevice(h->device);
   cudaFree(h->d_state); cudaFree(h->d_ds); cudaFree(h->d_di); cudaFree(h->d_forces); cudaFree(h->d_kkt);
-  cudaFree(h->d_lam); cudaFree(h->d_scratch); cudaFree(h->d_status); cudaFree(h->d_iters);
+  cudaFree(h->d_lam); cudaFree(h->d_counts); cudaFree(h->d_perm); cudaFree(h->exp_plan.d_scratch);
+  for (auto& c : h->cls) cudaFree(c.d_scratch);
+  cudaFree(h->d_status); cudaFree(h->d_iters);
   cudaFree(h->d_iters_sum); cudaFree(h->d_status_or); cudaFree(h->d_active); cudaFree(h->d_stats);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);

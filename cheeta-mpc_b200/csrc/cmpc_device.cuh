@@ -1,7 +1,15 @@
 // cmpc_device.cuh -- sm_100a device code of the batched centroidal-MPC condensed-QP solver.
 //
-// One CTA per MPC instance (persistent loop over the batch).  Everything an instance
-// needs between its 2.3 KB of inputs and its 1 KB of outputs lives on-chip:
+// One *warp group* (W warps, W = 1, 4 or 8) per MPC instance; several groups per CTA, one
+// CTA per SM, persistent over the batch with a device-side work counter.  Groups never use
+// a CTA-wide barrier: W = 1 synchronises with __syncwarp and shuffles only, W > 1 with a
+// named barrier per group.  Instances are bucketed by their number of free (stance-leg)
+// variables so that a trot instance (n = 60 at horizon 10) gets a single warp and ~25 KB
+// of shared memory, and 7-8 instances are resident per SM to hide the Cholesky's
+// dependency chains behind one another.
+//
+// Per instance, everything between its 2.3 KB of inputs and 1 KB of outputs stays on chip
+// or in an L2-resident scratch slab:
 //   * build   : lever arms, A_d^p B_j closed forms ("power stacking" is index arithmetic
 //               for the nilpotent centroidal A_c), H = 2(Bqp' L Bqp + K), g by an adjoint
 //               sum -- SURVEY §8 a2-a7, reference CentroidalMPC.cpp:85-94,179-232,284-335
@@ -23,6 +31,7 @@ namespace cmpc {
 constexpr double kGrav = 9.81;      // CentroidalMPC.cpp:71
 constexpr double kFricUb = 5000.0;  // CentroidalMPC.cpp:183
 constexpr int kMaxLegs = CMPC_MAX_LEGS;
+constexpr int kNumClasses = 4;
 
 struct DevConfig {
   double mass, dt;
@@ -32,6 +41,7 @@ struct DevConfig {
   int L, N, zoh, max_iter, polish;
 };
 
+// One launch = one size class.
 struct SolveArgs {
   const double* state;
   const double* des_state;
@@ -44,11 +54,16 @@ struct SolveArgs {
   uint16_t* active;
   double* Hout;  // build-export mode only
   double* gout;
-  double* scratch;          // global scratch for matrices that do not fit in shared memory
-  size_t scratch_per_cta;   // doubles
-  int B;
-  int h_in_smem, m_in_smem;
-  int mat_doubles;          // BC4 size for the launch's worst-case n
+  double* scratch;           // global (L2-resident) scratch: H per group, and M when it does not fit on chip
+  size_t scratch_per_group;  // doubles
+  const int32_t* perm;       // instance ids of this class (NULL: identity over [0, count))
+  const int32_t* count;      // device pointer to the number of instances of this class (NULL: count_imm)
+  int count_imm;
+  int32_t* work;             // device work counter (zeroed before the launch)
+  int nbmax;                 // most free blocks an instance of this class can have
+  int n4max;                 // padded free dimension bound of the class
+  int m_in_smem;
+  int groups;                // groups per CTA
 };
 
 // ------------------------------------------------------------------ BC4 layout
@@ -58,54 +73,96 @@ __device__ __forceinline__ int blkoff(int bi, int bj, int nblk) {
 __device__ __forceinline__ int midx(int i, int j, int nblk) {  // requires i>>2 >= j>>2
   return (blkoff(i >> 2, j >> 2, nblk) << 4) + ((i & 3) << 2) + (j & 3);
 }
-__host__ __device__ inline int bc4_doubles(int n) {
+__device__ __forceinline__ int sidx(int i, int j, int nblk) {  // symmetric access
+  return ((i >> 2) >= (j >> 2)) ? midx(i, j, nblk) : midx(j, i, nblk);
+}
+__host__ __device__ inline int bc4_tiles(int n) {
   int nblk = (n + 3) >> 2;
-  return ((nblk * (nblk + 1)) >> 1) << 4;
+  return (nblk * (nblk + 1)) >> 1;
 }
+__host__ __device__ inline int bc4_doubles(int n) { return bc4_tiles(n) << 4; }
 
-// ------------------------------------------------------------------ reductions
-template <int NT>
-__device__ __forceinline__ double block_max(double v, double* red) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double r = red[0];
-#pragma unroll
-  for (int k = 1; k < NT / 32; ++k) r = fmax(r, red[k]);
-  return r;
-}
-template <int NT>
-__device__ __forceinline__ double block_sum(double v, double* red) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double r = red[0];
-#pragma unroll
-  for (int k = 1; k < NT / 32; ++k) r += red[k];
-  return r;
-}
-// two maxima and one sum in a single pass (fewer barriers)
-template <int NT>
-__device__ __forceinline__ void block_max2_sum(double& a, double& b, double& s, double* red) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
-    b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o));
-    s += __shfl_xor_sync(0xffffffffu, s, o);
+// ------------------------------------------------------------------ group primitives
+template <int W>
+struct Group {
+  static constexpr int GT = 32 * W;
+  int gtid;     // thread index inside the group
+  int gid;      // group index inside the CTA
+  double* red;  // 3*W doubles of group-private shared scratch (W > 1 only)
+
+  __device__ __forceinline__ void sync() const {
+    if constexpr (W == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "r"(GT) : "memory");
   }
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) {
-    red[threadIdx.x >> 5] = a; red[32 + (threadIdx.x >> 5)] = b; red[64 + (threadIdx.x >> 5)] = s;
+  __device__ __forceinline__ bool all(bool p) const {
+    if constexpr (W == 1) {
+      __syncwarp();  // votes do not order memory; the callers rely on all() as a barrier
+      return __all_sync(0xffffffffu, p);
+    } else {
+      unsigned r;
+      asm volatile(
+          "{ .reg .pred p, q; setp.ne.u32 q, %1, 0; bar.red.and.pred p, %2, %3, q; selp.u32 %0, 1, 0, p; }"
+          : "=r"(r) : "r"((unsigned)p), "r"(gid + 1), "r"(GT) : "memory");
+      return r != 0;
+    }
   }
-  __syncthreads();
-  a = red[0]; b = red[32]; s = red[64];
+  __device__ __forceinline__ double max(double v) const {
+    if constexpr (W == 1) __syncwarp();
 #pragma unroll
-  for (int k = 1; k < NT / 32; ++k) { a = fmax(a, red[k]); b = fmax(b, red[32 + k]); s += red[64 + k]; }
-}
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if constexpr (W > 1) {
+      sync();
+      if ((gtid & 31) == 0) red[gtid >> 5] = v;
+      sync();
+      v = red[0];
+#pragma unroll
+      for (int k = 1; k < W; ++k) v = fmax(v, red[k]);
+    }
+    return v;
+  }
+  __device__ __forceinline__ double sum(double v) const {
+    if constexpr (W == 1) __syncwarp();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if constexpr (W > 1) {
+      sync();
+      if ((gtid & 31) == 0) red[gtid >> 5] = v;
+      sync();
+      v = red[0];
+#pragma unroll
+      for (int k = 1; k < W; ++k) v += red[k];
+    }
+    return v;
+  }
+  __device__ __forceinline__ void max2_sum(double& a, double& b, double& s) const {
+    if constexpr (W == 1) __syncwarp();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
+      b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o));
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+    }
+    if constexpr (W > 1) {
+      sync();
+      if ((gtid & 31) == 0) { red[gtid >> 5] = a; red[W + (gtid >> 5)] = b; red[2 * W + (gtid >> 5)] = s; }
+      sync();
+      a = red[0]; b = red[W]; s = red[2 * W];
+#pragma unroll
+      for (int k = 1; k < W; ++k) { a = fmax(a, red[k]); b = fmax(b, red[W + k]); s += red[2 * W + k]; }
+    }
+  }
+  // broadcast an int from thread 0 of the group
+  __device__ __forceinline__ int bcast0(int v, int* slot) const {
+    if constexpr (W == 1) {
+      return __shfl_sync(0xffffffffu, v, 0);
+    } else {
+      sync();
+      if (gtid == 0) *slot = v;
+      sync();
+      return *slot;
+    }
+  }
+};
 
 // ------------------------------------------------------------------ 4x4 tile kernels
 // Cholesky of a 4x4 SPD tile (row-major, lower part read). Writes l (lower, row-major, upper
@@ -136,23 +193,26 @@ __device__ __forceinline__ bool potrf4(const double* a, double* l, double* dinv)
   return ok;
 }
 
-// Tiled right-looking Cholesky in BC4 layout, in place. All threads must call it.
-// Returns false (uniformly) on a non-positive pivot.
-template <int NT>
-__device__ bool chol_bc4(double* M, int nblk) {
-  const int tid = threadIdx.x;
+// Tiled right-looking Cholesky in BC4 layout, in place; the whole group calls it.
+// tb[t] = bi | bj << 8 for storage tile t (built once per instance).  The factored diagonal
+// tile carries 1/l_ii in its (unused) upper triangle slots [1],[2],[3],[7] -> the solves
+// multiply instead of divide.  Returns false (uniformly) on a non-positive pivot.
+template <int W>
+__device__ bool chol_bc4(const Group<W>& G, double* M, int nblk, const uint16_t* tb) {
+  constexpr int GT = Group<W>::GT;
+  const int gtid = G.gtid;
+  const int ntiles = (nblk * (nblk + 1)) >> 1;
   bool ok = true;
   for (int kb = 0; kb < nblk; ++kb) {
-    // POTRF (redundant in every participating thread) + TRSM of the panel below
-    // (the factored diagonal tile is stored after the barrier: other threads still read A_kk)
+    const int col0 = blkoff(kb, kb, nblk);  // storage index of the diagonal tile of column kb
     const int nrows = nblk - kb;
     double l[16], dinv[4];
-    if (tid < nrows) {
-      const double* Akk = M + ((size_t)blkoff(kb, kb, nblk) << 4);
-      ok = potrf4(Akk, l, dinv) && ok;
-      for (int bi = kb + tid; bi < nblk; bi += NT) {
-        if (bi == kb) continue;
-        double* A = M + ((size_t)blkoff(bi, kb, nblk) << 4);
+    if (gtid < nrows) {
+      // POTRF redundantly in every lane that owns a panel tile (broadcast loads), then TRSM
+      ok = potrf4(M + ((size_t)col0 << 4), l, dinv) && ok;
+      for (int t = gtid; t < nrows; t += GT) {
+        if (t == 0) continue;
+        double* A = M + ((size_t)(col0 + t) << 4);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           double x0 = A[4 * r] * dinv[0];
@@ -163,25 +223,21 @@ __device__ bool chol_bc4(double* M, int nblk) {
         }
       }
     }
-    ok = __syncthreads_and(ok);
+    ok = G.all(ok);   // also the barrier between the panel and the trailing update
     if (!ok) return false;
-    if (tid == 0) {
-      double* Akk = M + ((size_t)blkoff(kb, kb, nblk) << 4);
+    if (gtid == 0) {
+      double* Akk = M + ((size_t)col0 << 4);
+      l[1] = dinv[0]; l[2] = dinv[1]; l[3] = dinv[2]; l[7] = dinv[3];
 #pragma unroll
       for (int q = 0; q < 16; ++q) Akk[q] = l[q];
     }
-    // trailing update: tiles (bi, bj), kb < bj <= bi < nblk
-    const int r = nblk - kb - 1;
-    const int cnt = (r * (r + 1)) >> 1;
-    for (int idx = tid; idx < cnt; idx += NT) {
-      int a = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
-      while (((a + 1) * (a + 2)) >> 1 <= idx) ++a;
-      while ((a * (a + 1)) >> 1 > idx) --a;
-      int c = idx - ((a * (a + 1)) >> 1);
-      const int bi = kb + 1 + a, bj = kb + 1 + c;
-      const double* Li = M + ((size_t)blkoff(bi, kb, nblk) << 4);
-      const double* Lj = M + ((size_t)blkoff(bj, kb, nblk) << 4);
-      double* C = M + ((size_t)blkoff(bi, bj, nblk) << 4);
+    // trailing update: storage tiles of columns kb+1.. are contiguous
+    const int t0 = col0 + nrows;
+    for (int t = t0 + gtid; t < ntiles; t += GT) {
+      const int bi = tb[t] & 0xff, bj = tb[t] >> 8;
+      const double* Li = M + ((size_t)(col0 + bi - kb) << 4);
+      const double* Lj = M + ((size_t)(col0 + bj - kb) << 4);
+      double* C = M + ((size_t)t << 4);
       double li[16], lj[16];
 #pragma unroll
       for (int q = 0; q < 16; ++q) { li[q] = Li[q]; lj[q] = Lj[q]; }
@@ -195,7 +251,7 @@ __device__ bool chol_bc4(double* M, int nblk) {
           C[4 * rr + cc] = s;
         }
     }
-    __syncthreads();
+    G.sync();
   }
   return true;
 }
@@ -204,18 +260,19 @@ __device__ bool chol_bc4(double* M, int nblk) {
 // doubles of scratch).  Forward pass accumulates residuals in x and writes y to tmp; the
 // backward pass accumulates in tmp and writes the solution to x -- no element is read and
 // written by different threads inside one step, so one barrier per block step suffices.
-template <int NT>
-__device__ void chol_solve_bc4(const double* M, int nblk, double* x, double* tmp) {
-  const int tid = threadIdx.x;
+template <int W>
+__device__ void chol_solve_bc4(const Group<W>& G, const double* M, int nblk, double* x, double* tmp) {
+  constexpr int GT = Group<W>::GT;
+  const int gtid = G.gtid;
   for (int kb = 0; kb < nblk; ++kb) {
-    if (tid < nblk - kb) {
+    if (gtid < nblk - kb) {
       const double* l = M + ((size_t)blkoff(kb, kb, nblk) << 4);
       const double b0 = x[4 * kb], b1 = x[4 * kb + 1], b2 = x[4 * kb + 2], b3 = x[4 * kb + 3];
-      const double y0 = b0 / l[0];
-      const double y1 = (b1 - l[4] * y0) / l[5];
-      const double y2 = (b2 - l[8] * y0 - l[9] * y1) / l[10];
-      const double y3 = (b3 - l[12] * y0 - l[13] * y1 - l[14] * y2) / l[15];
-      for (int bi = kb + tid; bi < nblk; bi += NT) {
+      const double y0 = b0 * l[1];
+      const double y1 = (b1 - l[4] * y0) * l[2];
+      const double y2 = (b2 - l[8] * y0 - l[9] * y1) * l[3];
+      const double y3 = (b3 - l[12] * y0 - l[13] * y1 - l[14] * y2) * l[7];
+      for (int bi = kb + gtid; bi < nblk; bi += GT) {
         if (bi == kb) {
           tmp[4 * kb] = y0; tmp[4 * kb + 1] = y1; tmp[4 * kb + 2] = y2; tmp[4 * kb + 3] = y3;
         } else {
@@ -226,17 +283,17 @@ __device__ void chol_solve_bc4(const double* M, int nblk, double* x, double* tmp
         }
       }
     }
-    __syncthreads();
+    G.sync();
   }
   for (int kb = nblk - 1; kb >= 0; --kb) {
-    if (tid <= kb) {
+    if (gtid <= kb) {
       const double* l = M + ((size_t)blkoff(kb, kb, nblk) << 4);
       const double y0 = tmp[4 * kb], y1 = tmp[4 * kb + 1], y2 = tmp[4 * kb + 2], y3 = tmp[4 * kb + 3];
-      const double x3 = y3 / l[15];
-      const double x2 = (y2 - l[14] * x3) / l[10];
-      const double x1 = (y1 - l[9] * x2 - l[13] * x3) / l[5];
-      const double x0 = (y0 - l[4] * x1 - l[8] * x2 - l[12] * x3) / l[0];
-      for (int bj = kb - tid; bj >= 0; bj -= NT) {
+      const double x3 = y3 * l[7];
+      const double x2 = (y2 - l[14] * x3) * l[3];
+      const double x1 = (y1 - l[9] * x2 - l[13] * x3) * l[2];
+      const double x0 = (y0 - l[4] * x1 - l[8] * x2 - l[12] * x3) * l[1];
+      for (int bj = kb - gtid; bj >= 0; bj -= GT) {
         if (bj == kb) {
           x[4 * kb] = x0; x[4 * kb + 1] = x1; x[4 * kb + 2] = x2; x[4 * kb + 3] = x3;
         } else {
@@ -247,20 +304,21 @@ __device__ void chol_solve_bc4(const double* M, int nblk, double* x, double* tmp
         }
       }
     }
-    __syncthreads();
+    G.sync();
   }
 }
 
 // y = H x for symmetric H in BC4 layout (diagonal tiles hold both triangles).
-// tpr lanes cooperate on one row. All threads call; ends with a barrier.
-template <int NT>
-__device__ void symv_bc4(const double* H, int n4, int nblk, const double* x, double* y) {
-  const int tid = threadIdx.x;
+// tpr lanes cooperate on one row.  The whole group calls it; ends with a group barrier.
+template <int W>
+__device__ void symv_bc4(const Group<W>& G, const double* H, int n4, int nblk, const double* x, double* y) {
+  constexpr int GT = Group<W>::GT;
+  const int gtid = G.gtid;
   int tpr = 1;
-  while (tpr * 2 * n4 <= NT && tpr < 8) tpr *= 2;
-  const int rpp = NT / tpr, sub = tid % tpr;
+  while (tpr * 2 * n4 <= GT && tpr < 8) tpr *= 2;
+  const int rpp = GT / tpr, sub = gtid % tpr;
   for (int base = 0; base < n4; base += rpp) {
-    const int row = base + tid / tpr;
+    const int row = base + gtid / tpr;
     double s = 0.0;
     if (row < n4) {
       const int bi = row >> 2, ri = row & 3;
@@ -277,7 +335,15 @@ __device__ void symv_bc4(const double* H, int n4, int nblk, const double* x, dou
     for (int o = tpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (row < n4 && sub == 0) y[row] = s;
   }
-  __syncthreads();
+  G.sync();
+}
+
+// Copy a BC4 matrix (global scratch -> shared), 16 bytes per access.
+template <int W>
+__device__ __forceinline__ void copy_mat(const Group<W>& G, double* dst, const double* src, int ndoubles) {
+  const double2* s2 = reinterpret_cast<const double2*>(src);
+  double2* d2 = reinterpret_cast<double2*>(dst);
+  for (int t = G.gtid; t < (ndoubles >> 1); t += Group<W>::GT) d2[t] = __ldcg(s2 + t);
 }
 
 // ------------------------------------------------------------------ friction pyramid rows
@@ -297,7 +363,7 @@ __device__ __forceinline__ void ctmul5(double mu, const double* w, double* o) {
 }
 
 // Null space of the active rows of one leg-step block (Gram-Schmidt). Returns rank.
-__device__ int block_nullspace(int k, const double (*A)[3], const double* b, double* f0, double (*Z)[3], bool* ok) {
+__device__ __noinline__ int block_nullspace(int k, const double (*A)[3], const double* b, double* f0, double (*Z)[3], bool* ok) {
   double Q[3][3];
   int r = 0;
   *ok = true;
@@ -344,7 +410,7 @@ __device__ int block_nullspace(int k, const double (*A)[3], const double* b, dou
 }
 
 // least squares S' lam = rb for k (<=3) independent normals via normal equations
-__device__ double small_lsq(int k, const double (*S)[3], const double* rb, double* lam) {
+__device__ __noinline__ double small_lsq(int k, const double (*S)[3], const double* rb, double* lam) {
   double G[3][3], y[3];
   for (int a = 0; a < k; ++a) {
     y[a] = S[a][0] * rb[0] + S[a][1] * rb[1] + S[a][2] * rb[2];
@@ -379,7 +445,7 @@ __device__ double small_lsq(int k, const double (*S)[3], const double* rb, doubl
 }
 
 // lam >= 0 with sum lam_t Nrm_t = rb; enumerates independent subsets (degenerate apex).
-__device__ bool block_multipliers(int k, const double (*Nrm)[3], const double* rb, double tol, double* lam) {
+__device__ __noinline__ bool block_multipliers(int k, const double (*Nrm)[3], const double* rb, double tol, double* lam) {
   for (int t = 0; t < k; ++t) lam[t] = 0.0;
   if (k == 0) return fmax(fabs(rb[0]), fmax(fabs(rb[1]), fabs(rb[2]))) <= tol;
   double Q[3][3];
@@ -416,117 +482,146 @@ __device__ bool block_multipliers(int k, const double (*Nrm)[3], const double* r
   return false;
 }
 
-// ------------------------------------------------------------------ shared-memory plan
+// ------------------------------------------------------------------ shared-memory plan (per group)
 struct SmemPlan {
-  // offsets in doubles from the start of dynamic shared memory
-  int in_state, in_ds, in_di, eq, qz, mu_b, ubxy, ubz, g, u, rd, rhs, du, f0, up, tv;
-  int sl, su, zl, zu, cdu, dzl, dzu, Zt, red, Hm, Mm;
-  int ints;  // start of int region (in doubles)
-  int total; // doubles
+  // offsets in doubles from the start of the group's slab
+  int eq, qz, ce, fzref, arm, g, u, rd, rhs, du, tv, up;
+  int sl, su, zl, zu, cdu, dzl, dzu, Zt, red, ints, Mm;
+  int total;  // doubles, multiple of 16
 };
-__host__ __device__ inline SmemPlan make_plan(int N, int L, int h_in_smem, int m_in_smem) {
+__host__ __device__ inline SmemPlan make_plan(int N, int L, int nbmax, int n4max, int m_in_smem) {
   SmemPlan p;
-  const int ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = L * (4 * N + 3);
-  const int nbmax = L * N, nmax = ((3 * nbmax + 3) >> 2) << 2, mmax = 5 * nbmax;
+  const int mmax = 5 * nbmax;
   int o = 0;
   auto take = [&](int cnt) { int r = o; o += (cnt + 1) & ~1; return r; };
-  p.in_state = take(ns); p.in_ds = take(nds); p.in_di = take(ndi);
   p.eq = take(9 * N); p.qz = take(N);
-  p.mu_b = take(nbmax); p.ubxy = take(nbmax); p.ubz = take(nbmax);
-  p.g = take(nmax); p.u = take(nmax); p.rd = take(nmax); p.rhs = take(nmax); p.du = take(nmax);
-  p.f0 = take(nmax); p.up = take(nmax); p.tv = take(nmax);
+  p.ce = take(nbmax); p.fzref = take(nbmax); p.arm = take(3 * nbmax);
+  p.g = take(n4max); p.u = take(n4max); p.rd = take(n4max); p.rhs = take(n4max); p.du = take(n4max);
+  p.tv = take(n4max); p.up = take(n4max);
   p.sl = take(mmax); p.su = take(mmax); p.zl = take(mmax); p.zu = take(mmax);
   p.cdu = take(mmax); p.dzl = take(mmax); p.dzu = take(mmax);
   p.Zt = take(9 * nbmax);
-  p.red = take(96);
-  // int region: blk_j, blk_i, blk_of[N*L], rk, off (ints) + act flags (bytes)
-  p.ints = take((5 * nbmax + 2 * mmax / 4 + 16) / 2 + 8);
-  const int mat = bc4_doubles(nmax);
+  p.red = take(24);
+  // ints: blk_j, blk_i, rk, off [nbmax each], blk_of [N*L], misc[8]; bytes: actl, actu [mmax each];
+  // uint16 tile table [tiles]
+  const int nints = 4 * nbmax + N * L + 8;
+  const int nbytes = 2 * mmax + 2 + 2 * bc4_tiles(n4max);
+  p.ints = take((nints * 4 + nbytes + 15) / 8);
   o = (o + 15) & ~15;  // 128-byte align tiles
-  p.Hm = o; if (h_in_smem) o += mat;
-  p.Mm = o; if (m_in_smem) o += mat;
-  p.total = o;
+  p.Mm = o;
+  if (m_in_smem) o += bc4_doubles(n4max);
+  p.total = (o + 15) & ~15;
   return p;
+}
+
+// ------------------------------------------------------------------ classification
+// One thread per instance: number of free blocks -> size class -> permutation slot.
+// bounds = largest nb of classes 0..2 (ascending); class 3 takes the rest.
+__global__ void classify_kernel(const DevConfig cfg, int B, const double* des_inputs, int4 bounds,
+                                int32_t* counts, int32_t* perm) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int N = cfg.N, L = cfg.L;
+  const double* di = des_inputs + (size_t)b * L * (4 * N + 3);
+  int nb = 0;
+  for (int i = 0; i < L; ++i)
+    for (int j = 0; j < N; ++j) nb += di[i * (4 * N + 3) + j] > 0.0 ? 1 : 0;
+  int c = 3;
+  if (nb <= bounds.x) c = 0;
+  else if (nb <= bounds.y) c = 1;
+  else if (nb <= bounds.z) c = 2;
+  const int slot = atomicAdd(&counts[c], 1);
+  perm[(size_t)c * B + slot] = b;
 }
 
 // ------------------------------------------------------------------ the fused kernel
 // MODE 0: solve.  MODE 1: build-export (H, g in the full 3LN layout to global memory).
-template <int NT, int MODE>
-__global__ void __launch_bounds__(NT) cmpc_solve_kernel(const DevConfig cfg, const SolveArgs args) {
+template <int W, int MODE>
+__global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, const SolveArgs args) {
   extern __shared__ __align__(128) double smem[];
-  const int tid = threadIdx.x;
+  constexpr int GT = Group<W>::GT;
   const int N = cfg.N, L = cfg.L, nu = 3 * L;
   const int ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = L * (4 * N + 3), nf = 3 * L * N;
-  const int nbmax = L * N, mmax = 5 * nbmax;
-  const SmemPlan P = make_plan(N, L, args.h_in_smem, args.m_in_smem);
-  double* s_state = smem + P.in_state;
-  double* s_ds = smem + P.in_ds;
-  double* s_di = smem + P.in_di;
-  double* s_eq = smem + P.eq;
-  double* s_qz = smem + P.qz;
-  double* s_mu = smem + P.mu_b;
-  double* s_ubxy = smem + P.ubxy;
-  double* s_ubz = smem + P.ubz;
-  double* s_g = smem + P.g;
-  double* s_u = smem + P.u;
-  double* s_rd = smem + P.rd;
-  double* s_rhs = smem + P.rhs;
-  double* s_du = smem + P.du;
-  double* s_f0 = smem + P.f0;
-  double* s_up = smem + P.up;
-  double* s_tv = smem + P.tv;
-  double* s_sl = smem + P.sl;
-  double* s_su = smem + P.su;
-  double* s_zl = smem + P.zl;
-  double* s_zu = smem + P.zu;
-  double* s_cdu = smem + P.cdu;
-  double* s_dzl = smem + P.dzl;
-  double* s_dzu = smem + P.dzu;
-  double* s_Zt = smem + P.Zt;
-  double* s_red = smem + P.red;
-  int* s_blk_j = reinterpret_cast<int*>(smem + P.ints);
+  const int nbfull = L * N, mfull = 5 * nbfull;
+  const int nbmax = args.nbmax, mmax = 5 * nbmax;
+  const SmemPlan P = make_plan(N, L, nbmax, args.n4max, args.m_in_smem);
+  Group<W> G;
+  G.gtid = threadIdx.x % GT;
+  G.gid = threadIdx.x / GT;
+  const int gtid = G.gtid;
+  double* base = smem + (size_t)G.gid * P.total;
+  G.red = base + P.red;
+  double* s_eq = base + P.eq;
+  double* s_qz = base + P.qz;
+  double* s_ce = base + P.ce;
+  double* s_fz = base + P.fzref;
+  double* s_arm = base + P.arm;
+  double* s_g = base + P.g;
+  double* s_u = base + P.u;
+  double* s_rd = base + P.rd;
+  double* s_f0 = s_rd;  // polish only; rd is recomputed after a rejected polish
+  double* s_rhs = base + P.rhs;
+  double* s_du = base + P.du;
+  double* s_tv = base + P.tv;
+  double* s_up = base + P.up;
+  double* s_sl = base + P.sl;
+  double* s_su = base + P.su;
+  double* s_zl = base + P.zl;
+  double* s_zu = base + P.zu;
+  double* s_cdu = base + P.cdu;
+  double* s_dzl = base + P.dzl;
+  double* s_dzu = base + P.dzu;
+  double* s_Zt = base + P.Zt;
+  int* s_blk_j = reinterpret_cast<int*>(base + P.ints);
   int* s_blk_i = s_blk_j + nbmax;
-  int* s_blk_of = s_blk_i + nbmax;  // [N*L] free block index or -1
-  int* s_rk = s_blk_of + nbmax;
+  int* s_rk = s_blk_i + nbmax;
   int* s_off = s_rk + nbmax;
-  int* s_misc = s_off + nbmax;      // [0]=nb, [1]=invalid, [2]=flag, [3]=nr
+  int* s_blk_of = s_off + nbmax;    // [N*L] free block index or -1
+  int* s_misc = s_blk_of + nbfull;  // [0]=nb, [1]=invalid, [2]=work slot, [3]=nr
   unsigned char* s_actl = reinterpret_cast<unsigned char*>(s_misc + 8);
   unsigned char* s_actu = s_actl + mmax;
-  double* Hm = args.h_in_smem ? smem + P.Hm : args.scratch + (size_t)blockIdx.x * args.scratch_per_cta;
-  double* Mm = args.m_in_smem ? smem + P.Mm
-                              : args.scratch + (size_t)blockIdx.x * args.scratch_per_cta + (args.h_in_smem ? 0 : args.mat_doubles);
+  uint16_t* s_tb = reinterpret_cast<uint16_t*>(s_actu + mmax);  // 2*mmax bytes past an int: even
+  const int group_global = blockIdx.x * args.groups + G.gid;
+  double* Hm = args.scratch + (size_t)group_global * args.scratch_per_group;
+  double* Mm = args.m_in_smem ? base + P.Mm : Hm + bc4_doubles(args.n4max);
 
-  const double* s_dpos = s_ds;
-  const double* s_dvel = s_ds + 3 * (N + 1);
-  const double* s_dam = s_ds + 6 * (N + 1);
   const double dt = cfg.dt, mass = cfg.mass;
   const double zeta = cfg.zoh ? 0.5 : 0.0;
+  const int count = args.count ? *args.count : args.count_imm;
 
-  for (int inst = blockIdx.x; inst < args.B; inst += gridDim.x) {
-    __syncthreads();
-    // ---- stage inputs (coalesced), CentroidalMPC.cpp:284-317
+  while (true) {
+    int slot = 0;
+    if (gtid == 0) slot = atomicAdd(args.work, 1);
+    slot = G.bcast0(slot, s_misc + 2);
+    if (slot >= count) break;
+    const int inst = args.perm ? args.perm[slot] : slot;
+    const double* g_state = args.state + (size_t)inst * ns;
+    const double* g_ds = args.des_state + (size_t)inst * nds;
+    const double* g_di = args.des_inputs + (size_t)inst * ndi;
+    const double* g_dpos = g_ds;
+    const double* g_dvel = g_ds + 3 * (N + 1);
+    const double* g_dam = g_ds + 6 * (N + 1);
+
+    // ---- scan inputs for non-finite values (CentroidalMPC.cpp:284-317 copies them blindly)
     bool finite = true;
-    for (int t = tid; t < ns; t += NT) { double v = args.state[(size_t)inst * ns + t]; s_state[t] = v; finite = finite && isfinite(v); }
-    for (int t = tid; t < nds; t += NT) { double v = args.des_state[(size_t)inst * nds + t]; s_ds[t] = v; finite = finite && isfinite(v); }
-    for (int t = tid; t < ndi; t += NT) { double v = args.des_inputs[(size_t)inst * ndi + t]; s_di[t] = v; finite = finite && isfinite(v); }
-    finite = __syncthreads_and(finite);
+    for (int t = gtid; t < ns; t += GT) finite = finite && isfinite(g_state[t]);
+    for (int t = gtid; t < nds; t += GT) finite = finite && isfinite(g_ds[t]);
+    for (int t = gtid; t < ndi; t += GT) finite = finite && isfinite(g_di[t]);
+    finite = G.all(finite);
 
     // ---- contact table -> free blocks; validity (CentroidalMPC.cpp:328-330)
-    if (tid == 0) {
+    if (gtid == 0) {
       int nb = 0, invalid = 0;
       for (int j = 0; j < N; ++j) {
         double colsum = 0.0;
-        for (int i = 0; i < L; ++i) colsum += s_di[i * (4 * N + 3) + j];
+        for (int i = 0; i < L; ++i) colsum += g_di[i * (4 * N + 3) + j];
         if (!(colsum > 0.0)) invalid = 1;
         for (int i = 0; i < L; ++i) {
-          double ce = s_di[i * (4 * N + 3) + j];
-          if (ce > 0.0) {
+          const double ce = g_di[i * (4 * N + 3) + j];
+          if (ce > 0.0 && nb < nbmax) {
             s_blk_j[nb] = j; s_blk_i[nb] = i; s_blk_of[j * L + i] = nb;
-            s_mu[nb] = cfg.mu[i];
-            s_ubxy[nb] = kFricUb * ce;                     // :183,199
-            s_ubz[nb] = mass * kGrav * (double)L * ce;
-            // desired normal force m g / #stance (:331-333), kept in s_up until g is built
-            s_up[nb] = (colsum > 0.0) ? mass * kGrav / colsum : 0.0;
+            s_ce[nb] = ce;
+            s_fz[nb] = (colsum > 0.0) ? mass * kGrav / colsum : 0.0;  // desired fz, :331-333
             ++nb;
           } else {
             s_blk_of[j * L + i] = -1;
@@ -534,97 +629,103 @@ __global__ void __launch_bounds__(NT) cmpc_solve_kernel(const DevConfig cfg, con
         }
       }
       s_misc[0] = nb; s_misc[1] = invalid;
-      // zero-input rollout x_{k+1} = A x_k + d and weighted error e = Q (x - x_ref), nodes 1..N
-      double c[3] = {s_state[0], s_state[1], s_state[2]};
-      double v[3] = {s_state[3], s_state[4], s_state[5]};
-      double gz = -kGrav;
-      for (int k = 0; k < N; ++k) {
-        const int node = k + 1;
-        for (int a = 0; a < 3; ++a) c[a] += dt * v[a];
-        if (cfg.zoh) c[2] += 0.5 * dt * dt * gz;
-        v[2] += dt * gz;
-        double om = (cfg.w[2] * 0.5) * exp(-(double)node) + cfg.w[2] * 0.5;  // :205
-        double qz = om * om;                                                  // :210 (inside the square)
-        s_qz[k] = qz;
-        s_eq[9 * k + 0] = cfg.w[0] * (c[0] - s_dpos[3 * node + 0]);
-        s_eq[9 * k + 1] = cfg.w[1] * (c[1] - s_dpos[3 * node + 1]);
-        s_eq[9 * k + 2] = qz * (c[2] - s_dpos[3 * node + 2]);
-        for (int a = 0; a < 3; ++a) {
-          s_eq[9 * k + 3 + a] = cfg.w[3 + a] * (v[a] - s_dvel[3 * node + a]);
-          s_eq[9 * k + 6 + a] = cfg.w[6 + a] * (s_state[6 + a] - s_dam[3 * node + a]);
-        }
+    }
+    // zero-input rollout (closed form of x_k = A^k x0 + sum A^p d) and e = Q (x - x_ref), nodes 1..N
+    for (int k = gtid; k < N; k += GT) {
+      const int node = k + 1;
+      const double kk = (double)node;
+      const double gpos = cfg.zoh ? 0.5 * kk * kk : 0.5 * kk * (kk - 1.0);
+      double c[3], v[3];
+      for (int a = 0; a < 3; ++a) { c[a] = g_state[a] + kk * dt * g_state[3 + a]; v[a] = g_state[3 + a]; }
+      c[2] += gpos * dt * dt * (-kGrav);
+      v[2] += kk * dt * (-kGrav);
+      const double om = (cfg.w[2] * 0.5) * exp(-kk) + cfg.w[2] * 0.5;  // :205
+      const double qz = om * om;                                        // :210 (inside the square)
+      s_qz[k] = qz;
+      s_eq[9 * k + 0] = cfg.w[0] * (c[0] - g_dpos[3 * node + 0]);
+      s_eq[9 * k + 1] = cfg.w[1] * (c[1] - g_dpos[3 * node + 1]);
+      s_eq[9 * k + 2] = qz * (c[2] - g_dpos[3 * node + 2]);
+      for (int a = 0; a < 3; ++a) {
+        s_eq[9 * k + 3 + a] = cfg.w[3 + a] * (v[a] - g_dvel[3 * node + a]);
+        s_eq[9 * k + 6 + a] = cfg.w[6 + a] * (g_state[6 + a] - g_dam[3 * node + a]);
       }
     }
-    __syncthreads();
+    G.sync();
     const int nb = s_misc[0];
     const int n = 3 * nb, nblk = (n + 3) >> 2, n4 = nblk << 2, m = 5 * nb;
+    const int ntiles = (nblk * (nblk + 1)) >> 1;
     const bool invalid = s_misc[1] != 0;
 
-    if (!finite || invalid) {
-      if (MODE == 0) {
-        for (int t = tid; t < nf; t += NT) args.forces[(size_t)inst * nf + t] = 0.0;
-        if (args.lam) for (int t = tid; t < 2 * mmax; t += NT) args.lam[(size_t)inst * 2 * mmax + t] = 0.0;
-        if (args.active) for (int t = tid; t < nbmax; t += NT) args.active[(size_t)inst * nbmax + t] = 0;
-        if (tid == 0) {
-          args.status[inst] = !finite ? CMPC_STATUS_NUMERICAL : CMPC_STATUS_INVALID_TABLE;
-          if (args.iters) args.iters[inst] = 0;
-          if (args.kkt) args.kkt[inst] = 0.0;
-        }
-        continue;
+    if (MODE == 0 && (!finite || invalid)) {
+      for (int t = gtid; t < nf; t += GT) args.forces[(size_t)inst * nf + t] = 0.0;
+      if (args.lam) for (int t = gtid; t < 2 * mfull; t += GT) args.lam[(size_t)inst * 2 * mfull + t] = 0.0;
+      if (args.active) for (int t = gtid; t < nbfull; t += GT) args.active[(size_t)inst * nbfull + t] = 0;
+      if (gtid == 0) {
+        args.status[inst] = !finite ? CMPC_STATUS_NUMERICAL : CMPC_STATUS_INVALID_TABLE;
+        if (args.iters) args.iters[inst] = 0;
+        if (args.kkt) args.kkt[inst] = 0.0;
       }
+      G.sync();
+      continue;
     }
 
+    // lever arms r = des_foot_pos[:, j] - des_com_pos[:, j] (frozen), tile table
+    for (int b = gtid; b < nb; b += GT) {
+      const int j = s_blk_j[b], i = s_blk_i[b];
+      for (int q = 0; q < 3; ++q) s_arm[3 * b + q] = g_di[i * (4 * N + 3) + N + 3 * j + q] - g_dpos[3 * j + q];
+    }
+    for (int bj = gtid; bj < nblk; bj += GT) {
+      const int o = blkoff(bj, bj, nblk);
+      for (int bi = bj; bi < nblk; ++bi) s_tb[o + bi - bj] = (uint16_t)(bi | (bj << 8));
+    }
     // ---- H = 2 (Bqp' L Bqp + K) on the free variables, one thread per block pair (b >= b2).
     // Column (j,i) of Bqp at row block k >= j is A_d^{k-j} B_j =
     //   [ dt^2 (k-j+zeta) (c/m) I ; dt (c/m) I ; dt c [r]x ]   (a2/a3; Euler zeta=0, ZOH 1/2)
     {
-      const int mat = bc4_doubles(n4);
-      for (int t = tid; t < mat; t += NT) Hm[t] = 0.0;
-      __syncthreads();
+      const int mat = ntiles << 4;
+      for (int t = gtid; t < mat; t += GT) Hm[t] = 0.0;
+      G.sync();
       const int npairs = (nb * (nb + 1)) >> 1;
-      for (int idx = tid; idx < npairs; idx += NT) {
+      const double dt2 = dt * dt, dt4 = dt2 * dt2;
+      for (int idx = gtid; idx < npairs; idx += GT) {
         int a = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
         while (((a + 1) * (a + 2)) >> 1 <= idx) ++a;
         while ((a * (a + 1)) >> 1 > idx) --a;
         const int b2 = idx - ((a * (a + 1)) >> 1), b = a;  // b >= b2  => j >= j2
         const int j = s_blk_j[b], i = s_blk_i[b], j2 = s_blk_j[b2], i2 = s_blk_i[b2];
-        const double ce = s_di[i * (4 * N + 3) + j], ce2 = s_di[i2 * (4 * N + 3) + j2];
-        double r[3], r2[3];
-        for (int q = 0; q < 3; ++q) {
-          r[q] = s_di[i * (4 * N + 3) + N + 3 * j + q] - s_dpos[3 * j + q];
-          r2[q] = s_di[i2 * (4 * N + 3) + N + 3 * j2 + q] - s_dpos[3 * j2 + q];
-        }
+        const double ce = s_ce[b], ce2 = s_ce[b2];
+        const double r0 = s_arm[3 * b], r1 = s_arm[3 * b + 1], r2 = s_arm[3 * b + 2];
+        const double p0 = s_arm[3 * b2], p1 = s_arm[3 * b2 + 1], p2 = s_arm[3 * b2 + 2];
         const double cm = ce / mass, cm2 = ce2 / mass;
         // position rows: sum_k alpha_{k-j} alpha_{k-j2} Qp_k ; only the z weight depends on k
         double s0 = 0.0, sz = 0.0;
         for (int k = j; k < N; ++k) {
-          double aa = ((double)(k - j) + zeta) * ((double)(k - j2) + zeta);
+          const double aa = ((double)(k - j) + zeta) * ((double)(k - j2) + zeta);
           s0 += aa; sz += aa * s_qz[k];
         }
-        const double dt2 = dt * dt, dt4 = dt2 * dt2;
         const double cnt = (double)(N - j);
+        // angular rows: dt^2 c c2 [r]x' diag(ql) [r2]x summed over the N-j row blocks below;
+        // [r]x = [[0,-rz,ry],[rz,0,-rx],[-ry,rx,0]]
+        const double q0 = cfg.w[6], q1 = cfg.w[7], q2 = cfg.w[8];
+        const double sc = cnt * dt2 * ce * ce2;
         double blk[3][3];
-        // angular rows: dt^2 c c2 [r]x' diag(ql) [r2]x  summed over N-j row blocks
-        const double ql0 = cfg.w[6], ql1 = cfg.w[7], ql2 = cfg.w[8];
-        // [r]x = [[0,-rz,ry],[rz,0,-rx],[-ry,rx,0]];  ([r]x' Q [r2]x)_{ab} = sum_q [r]x_{qa} ql_q [r2]x_{qb}
-        double X[3][3] = {{0.0, -r[2], r[1]}, {r[2], 0.0, -r[0]}, {-r[1], r[0], 0.0}};
-        double Y[3][3] = {{0.0, -r2[2], r2[1]}, {r2[2], 0.0, -r2[0]}, {-r2[1], r2[0], 0.0}};
-        const double ql[3] = {ql0, ql1, ql2};
-        for (int aa = 0; aa < 3; ++aa)
-          for (int bb = 0; bb < 3; ++bb) {
-            double s = 0.0;
-            for (int q = 0; q < 3; ++q) s += X[q][aa] * ql[q] * Y[q][bb];
-            blk[aa][bb] = cnt * dt2 * ce * ce2 * s;
-          }
+        blk[0][0] = sc * (r2 * q1 * p2 + r1 * q2 * p1);
+        blk[0][1] = sc * (-r1 * q2 * p0);
+        blk[0][2] = sc * (-r2 * q1 * p0);
+        blk[1][0] = sc * (-r0 * q2 * p1);
+        blk[1][1] = sc * (r2 * q0 * p2 + r0 * q2 * p0);
+        blk[1][2] = sc * (-r2 * q0 * p1);
+        blk[2][0] = sc * (-r0 * q1 * p2);
+        blk[2][1] = sc * (-r1 * q0 * p2);
+        blk[2][2] = sc * (r1 * q0 * p1 + r0 * q1 * p0);
         const double pos[3] = {cfg.w[0] * s0, cfg.w[1] * s0, sz};
-        for (int aa = 0; aa < 3; ++aa)
-          blk[aa][aa] += cm * cm2 * (dt4 * pos[aa] + cnt * dt2 * cfg.w[3 + aa]);
+        for (int aa = 0; aa < 3; ++aa) blk[aa][aa] += cm * cm2 * (dt4 * pos[aa] + cnt * dt2 * cfg.w[3 + aa]);
         // K = W_f + D' W_r D (CentroidalMPC.cpp:223-231): same leg, same component
         if (i == i2) {
           for (int aa = 0; aa < 3; ++aa) {
             const double wr = cfg.w[9 + 6 * L + 3 * i + aa];
             if (j == j2) {
-              double nn = (j > 0 ? 1.0 : 0.0) + (j + 1 < N ? 1.0 : 0.0);
+              const double nn = (j > 0 ? 1.0 : 0.0) + (j + 1 < N ? 1.0 : 0.0);
               blk[aa][aa] += cfg.w[9 + 3 * L + 3 * i + aa] + nn * wr;
             } else if (j == j2 + 1) {
               blk[aa][aa] -= wr;
@@ -636,8 +737,7 @@ __global__ void __launch_bounds__(NT) cmpc_solve_kernel(const DevConfig cfg, con
             const int gi = 3 * b + aa, gj = 3 * b2 + bb;
             const double v = 2.0 * blk[aa][bb];
             if (b != b2) {
-              if ((gi >> 2) >= (gj >> 2)) Hm[midx(gi, gj, nblk)] = v;
-              else Hm[midx(gj, gi, nblk)] = v;
+              Hm[midx(gi, gj, nblk)] = v;                              // gi > gj always here
               if ((gi >> 2) == (gj >> 2)) Hm[midx(gj, gi, nblk)] = v;  // same diagonal tile: mirror
             } else if ((gi >> 2) >= (gj >> 2)) {
               // diagonal 3x3 block: all 9 (aa,bb) are visited, so both triangles of a
@@ -646,14 +746,12 @@ __global__ void __launch_bounds__(NT) cmpc_solve_kernel(const DevConfig cfg, con
             }
           }
       }
-      // padding rows (n..n4): identity
-      if (tid < n4 - n) Hm[midx(n + tid, n + tid, nblk)] = 1.0;
+      if (gtid < n4 - n) Hm[midx(n + gtid, n + gtid, nblk)] = 1.0;  // padding rows: identity
       // ---- g = 2 Bqp' L (Aqp x0 + dqp - Xref) - 2 W_f Uref, one thread per block (adjoint sum)
-      for (int b = tid; b < nb; b += NT) {
+      for (int b = gtid; b < nb; b += GT) {
         const int j = s_blk_j[b], i = s_blk_i[b];
-        const double ce = s_di[i * (4 * N + 3) + j];
-        double r[3];
-        for (int q = 0; q < 3; ++q) r[q] = s_di[i * (4 * N + 3) + N + 3 * j + q] - s_dpos[3 * j + q];
+        const double ce = s_ce[b];
+        const double r[3] = {s_arm[3 * b], s_arm[3 * b + 1], s_arm[3 * b + 2]};
         double sp[3] = {0, 0, 0}, sv[3] = {0, 0, 0}, sl3[3] = {0, 0, 0};
         for (int k = j; k < N; ++k) {
           const double al = (double)(k - j) + zeta;
@@ -663,16 +761,16 @@ __global__ void __launch_bounds__(NT) cmpc_solve_kernel(const DevConfig cfg, con
         }
         const double cm = ce / mass;
         // [r]x' v = v x r
-        double cr[3] = {sl3[1] * r[2] - sl3[2] * r[1], sl3[2] * r[0] - sl3[0] * r[2], sl3[0] * r[1] - sl3[1] * r[0]};
-        const double fzref = s_up[b];
+        const double cr[3] = {sl3[1] * r[2] - sl3[2] * r[1], sl3[2] * r[0] - sl3[0] * r[2], sl3[0] * r[1] - sl3[1] * r[0]};
         for (int q = 0; q < 3; ++q) {
           double gq = 2.0 * (cm * (dt * dt * sp[q] + dt * sv[q]) + dt * ce * cr[q]);
-          if (q == 2) gq -= 2.0 * cfg.w[9 + 3 * L + 3 * i + 2] * fzref;
+          if (q == 2) gq -= 2.0 * cfg.w[9 + 3 * L + 3 * i + 2] * s_fz[b];
           s_g[3 * b + q] = gq;
         }
       }
-      if (tid < n4 - n) s_g[n + tid] = 0.0;
-      __syncthreads();
+      if (gtid < n4 - n) s_g[n + gtid] = 0.0;
+      __threadfence_block();
+      G.sync();
     }
 
     if (MODE == 1) {
@@ -680,73 +778,76 @@ __global__ void __launch_bounds__(NT) cmpc_solve_kernel(const DevConfig cfg, con
       const int p = nf;
       double* Ho = args.Hout + (size_t)inst * p * p;
       double* go = args.gout + (size_t)inst * p;
-      for (int t = tid; t < p * p; t += NT) {
+      for (int t = gtid; t < p * p; t += GT) {
         const int a = t / p, c = t % p;
         const int ba = s_blk_of[(a / nu) * L + (a % nu) / 3], bc = s_blk_of[(c / nu) * L + (c % nu) / 3];
         double v;
         if (ba < 0 || bc < 0) v = (a == c) ? 1.0 : 0.0;
-        else {
-          const int gi = 3 * ba + a % 3, gj = 3 * bc + c % 3;
-          v = ((gi >> 2) >= (gj >> 2)) ? Hm[midx(gi, gj, nblk)] : Hm[midx(gj, gi, nblk)];
-        }
+        else v = __ldcg(Hm + sidx(3 * ba + a % 3, 3 * bc + c % 3, nblk));
         Ho[t] = v;
       }
-      for (int t = tid; t < p; t += NT) {
+      for (int t = gtid; t < p; t += GT) {
         const int ba = s_blk_of[(t / nu) * L + (t % nu) / 3];
         go[t] = ba < 0 ? 0.0 : s_g[3 * ba + t % 3];
       }
-      if (tid == 0) args.status[inst] = !finite ? CMPC_STATUS_NUMERICAL : (invalid ? CMPC_STATUS_INVALID_TABLE : CMPC_STATUS_OK);
+      if (gtid == 0) args.status[inst] = !finite ? CMPC_STATUS_NUMERICAL : (invalid ? CMPC_STATUS_INVALID_TABLE : CMPC_STATUS_OK);
+      G.sync();
       continue;
     }
 
     // ---- strictly feasible start f = (0, 0, fz0); centred duals
-    for (int b = tid; b < nb; b += NT) {
-      double fz = s_up[b];
-      fz = fmin(fz, 0.5 * s_ubz[b]);
-      fz = fmin(fz, 0.5 * s_ubxy[b] / s_mu[b]);
+    for (int b = gtid; b < nb; b += GT) {
+      const double mub = cfg.mu[s_blk_i[b]];
+      double fz = s_fz[b];
+      fz = fmin(fz, 0.5 * mass * kGrav * (double)L * s_ce[b]);
+      fz = fmin(fz, 0.5 * kFricUb * s_ce[b] / mub);
       s_u[3 * b] = 0.0; s_u[3 * b + 1] = 0.0; s_u[3 * b + 2] = fz;
     }
-    if (tid < n4 - n) { s_u[n + tid] = 0.0; s_rhs[n + tid] = 0.0; s_du[n + tid] = 0.0; s_f0[n + tid] = 0.0; s_tv[n + tid] = 0.0; }
-    __syncthreads();
-    symv_bc4<NT>(Hm, n4, nblk, s_u, s_rd);
+    if (gtid < n4 - n) { s_u[n + gtid] = 0.0; s_rhs[n + gtid] = 0.0; s_du[n + gtid] = 0.0; s_rd[n + gtid] = 0.0; s_tv[n + gtid] = 0.0; s_up[n + gtid] = 0.0; }
+    copy_mat<W>(G, Mm, Hm, ntiles << 4);
+    G.sync();
+    symv_bc4<W>(G, Mm, n4, nblk, s_u, s_rd);
     double gmax = 0.0, r0max = 0.0;
-    for (int t = tid; t < n; t += NT) { gmax = fmax(gmax, fabs(s_g[t])); r0max = fmax(r0max, fabs(s_rd[t] + s_g[t])); }
-    gmax = block_max<NT>(gmax, s_red);
-    r0max = block_max<NT>(r0max, s_red);
+    for (int t = gtid; t < n; t += GT) { gmax = fmax(gmax, fabs(s_g[t])); r0max = fmax(r0max, fabs(s_rd[t] + s_g[t])); }
+    gmax = G.max(gmax);
+    r0max = G.max(r0max);
     const double gs = 1.0 + gmax;
     const double mu0 = fmax(1e-2, r0max);
-    for (int b = tid; b < nb; b += NT) {
+    for (int b = gtid; b < nb; b += GT) {
+      const double mub = cfg.mu[s_blk_i[b]];
+      const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];  // :183,199
       double y[5];
-      cmul5(s_mu[b], s_u + 3 * b, y);
+      cmul5(mub, s_u + 3 * b, y);
       for (int q = 0; q < 5; ++q) {
-        const double ub = q < 4 ? s_ubxy[b] : s_ubz[b];
+        const double ub = q < 4 ? ubxy : ubz;
         s_sl[5 * b + q] = y[q]; s_su[5 * b + q] = ub - y[q];
         s_zl[5 * b + q] = mu0 / y[q]; s_zu[5 * b + q] = mu0 / (ub - y[q]);
       }
     }
-    __syncthreads();
+    G.sync();
 
     int status = CMPC_STATUS_MAX_ITER, it = 0, npolish = 0;
-    bool numerical = false, ipm_ok = false;
+    bool numerical = false, ipm_ok = false, m_is_h = true;
     double us = 1.0;
     for (it = 0; it <= cfg.max_iter; ++it) {
-      // ---- residuals
-      symv_bc4<NT>(Hm, n4, nblk, s_u, s_rd);
+      // ---- residuals (M holds a fresh copy of H here)
+      if (!m_is_h) { copy_mat<W>(G, Mm, Hm, ntiles << 4); G.sync(); m_is_h = true; }
+      symv_bc4<W>(G, Mm, n4, nblk, s_u, s_rd);
       double rmax = 0.0, umax = 0.0, gap = 0.0;
-      for (int b = tid; b < nb; b += NT) {
+      for (int b = gtid; b < nb; b += GT) {
         double w[5], o[3];
         for (int q = 0; q < 5; ++q) {
           w[q] = s_zl[5 * b + q] - s_zu[5 * b + q];
           gap += s_sl[5 * b + q] * s_zl[5 * b + q] + s_su[5 * b + q] * s_zu[5 * b + q];
         }
-        ctmul5(s_mu[b], w, o);
+        ctmul5(cfg.mu[s_blk_i[b]], w, o);
         for (int q = 0; q < 3; ++q) {
           const double rr = s_rd[3 * b + q] + s_g[3 * b + q] - o[q];
           s_rd[3 * b + q] = rr;
           rmax = fmax(rmax, fabs(rr)); umax = fmax(umax, fabs(s_u[3 * b + q]));
         }
       }
-      block_max2_sum<NT>(rmax, umax, gap, s_red);
+      G.max2_sum(rmax, umax, gap);
       const double mu = gap / (2.0 * (double)m);
       us = 1.0 + umax;
       // Convergence. The dual residual has a round-off floor ~ eps * cond(H + C'SC) once the
@@ -758,57 +859,73 @@ __global__ void __launch_bounds__(NT) cmpc_solve_kernel(const DevConfig cfg, con
       ipm_ok = conv_mu && rmax <= 10.0 * cfg.tol * gs;
       if (cfg.polish && ready && npolish < 3) {
         ++npolish;
-        for (int t = tid; t < m; t += NT) {
-          s_actl[t] = s_zl[t] * us > s_sl[t] * gs;
-          s_actu[t] = s_zu[t] * us > s_su[t] * gs;
+        bool any_act = false;
+        for (int t = gtid; t < m; t += GT) {
+          const bool al = s_zl[t] * us > s_sl[t] * gs, au = s_zu[t] * us > s_su[t] * gs;
+          s_actl[t] = al; s_actu[t] = au;
+          any_act = any_act || al || au;
         }
-        __syncthreads();
+        bool none_active = G.all(!any_act);
         // ---- active-set polish with correction passes
         bool accepted = false;
         for (int pass = 0; pass < 6 && !accepted; ++pass) {
-          bool ok_all = true;
-          for (int b = tid; b < nb; b += NT) {
-            double A[10][3], rhsb[10], Z[3][3], f0[3];
-            int k = 0;
-            for (int q = 0; q < 5; ++q) if (s_actl[5 * b + q]) { row_vec(s_mu[b], q, A[k]); rhsb[k++] = 0.0; }
-            for (int q = 0; q < 5; ++q) if (s_actu[5 * b + q]) { row_vec(s_mu[b], q, A[k]); rhsb[k++] = q < 4 ? s_ubxy[b] : s_ubz[b]; }
-            bool okb;
-            const int rk = block_nullspace(k, A, rhsb, f0, Z, &okb);
-            ok_all = ok_all && okb;
-            s_rk[b] = rk;
-            for (int q = 0; q < 3; ++q) s_f0[3 * b + q] = f0[q];
-            for (int cc = 0; cc < 3 - rk; ++cc)
-              for (int q = 0; q < 3; ++q) s_Zt[9 * b + 3 * cc + q] = Z[cc][q];
-          }
-          ok_all = __syncthreads_and(ok_all);
-          if (!ok_all) break;
-          if (tid == 0) {
-            int o = 0;
-            for (int b = 0; b < nb; ++b) { s_off[b] = o; o += 3 - s_rk[b]; }
-            s_misc[3] = o;
-          }
-          __syncthreads();
-          const int nr = s_misc[3];
-          const int nblk_r = (nr + 3) >> 2, nr4 = nblk_r << 2;
-          // r = H f0 + g
-          symv_bc4<NT>(Hm, n4, nblk, s_f0, s_rhs);
-          for (int t = tid; t < n; t += NT) s_rhs[t] += s_g[t];
-          {
-            const int matr = bc4_doubles(nr4);
-            for (int t = tid; t < matr; t += NT) Mm[t] = 0.0;
-          }
-          __syncthreads();
-          // reduced system Z'HZ t = -Z'(H f0 + g)
-          for (int b = tid; b < nb; b += NT) {
-            for (int cc = 0; cc < 3 - s_rk[b]; ++cc) {
-              const double* z = s_Zt + 9 * b + 3 * cc;
-              s_tv[s_off[b] + cc] = -(z[0] * s_rhs[3 * b] + z[1] * s_rhs[3 * b + 1] + z[2] * s_rhs[3 * b + 2]);
+          int nr, nblk_r;
+          if (none_active) {
+            // no active row: Z = I, f0 = 0, the reduced system is (H, -g) itself
+            nr = n; nblk_r = nblk;
+            for (int b = gtid; b < nb; b += GT) { s_rk[b] = 0; s_off[b] = 3 * b; }
+            for (int t = gtid; t < n4; t += GT) { s_f0[t] = 0.0; s_tv[t] = t < n ? -s_g[t] : 0.0; }
+            if (!m_is_h) copy_mat<W>(G, Mm, Hm, ntiles << 4);
+            G.sync();
+          } else {
+            bool ok_all = true;
+            for (int b = gtid; b < nb; b += GT) {
+              const double mub = cfg.mu[s_blk_i[b]];
+              const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
+              double A[10][3], rhsb[10], Z[3][3], f0[3];
+              int k = 0;
+              for (int q = 0; q < 5; ++q) if (s_actl[5 * b + q]) { row_vec(mub, q, A[k]); rhsb[k++] = 0.0; }
+              for (int q = 0; q < 5; ++q) if (s_actu[5 * b + q]) { row_vec(mub, q, A[k]); rhsb[k++] = q < 4 ? ubxy : ubz; }
+              bool okb;
+              const int rk = block_nullspace(k, A, rhsb, f0, Z, &okb);
+              ok_all = ok_all && okb;
+              s_rk[b] = rk;
+              for (int q = 0; q < 3; ++q) s_f0[3 * b + q] = f0[q];
+              for (int cc = 0; cc < 3 - rk; ++cc)
+                for (int q = 0; q < 3; ++q) s_Zt[9 * b + 3 * cc + q] = Z[cc][q];
             }
-          }
-          if (tid < nr4 - nr) { s_tv[nr + tid] = 0.0; Mm[midx(nr + tid, nr + tid, nblk_r)] = 1.0; }
-          {
+            if (gtid < n4 - n) s_f0[n + gtid] = 0.0;
+            ok_all = G.all(ok_all);
+            if (!ok_all) break;
+            if (gtid == 0) {
+              int o = 0;
+              for (int b = 0; b < nb; ++b) { s_off[b] = o; o += 3 - s_rk[b]; }
+              s_misc[3] = o;
+            }
+            if (!m_is_h) copy_mat<W>(G, Mm, Hm, ntiles << 4);
+            G.sync();
+            nr = s_misc[3];
+            nblk_r = (nr + 3) >> 2;
+            const int nr4 = nblk_r << 2;
+            // r = H f0 + g   (H read from the shared copy)
+            symv_bc4<W>(G, Mm, n4, nblk, s_f0, s_rhs);
+            for (int t = gtid; t < n; t += GT) s_rhs[t] += s_g[t];
+            G.sync();
+            // reduced system Z'HZ t = -Z'(H f0 + g); H is read from the global copy, the
+            // reduced matrix is assembled in M
+            {
+              const int matr = bc4_doubles(nr4);
+              for (int t = gtid; t < matr; t += GT) Mm[t] = 0.0;
+            }
+            for (int b = gtid; b < nb; b += GT)
+              for (int cc = 0; cc < 3 - s_rk[b]; ++cc) {
+                const double* z = s_Zt + 9 * b + 3 * cc;
+                s_tv[s_off[b] + cc] = -(z[0] * s_rhs[3 * b] + z[1] * s_rhs[3 * b + 1] + z[2] * s_rhs[3 * b + 2]);
+              }
+            G.sync();
+            if (gtid < nr4 - nr) { s_tv[nr + gtid] = 0.0; Mm[midx(nr + gtid, nr + gtid, nblk_r)] = 1.0; }
             const int npairs = (nb * (nb + 1)) >> 1;
-            for (int idx = tid; idx < npairs; idx += NT) {
+            for (int idx = gtid; idx < npairs; idx += GT) {
               int a = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
               while (((a + 1) * (a + 2)) >> 1 <= idx) ++a;
               while ((a * (a + 1)) >> 1 > idx) --a;
@@ -817,116 +934,148 @@ __global__ void __launch_bounds__(NT) cmpc_solve_kernel(const DevConfig cfg, con
               if (d1 == 0 || d2 == 0) continue;
               double Hb[3][3];
               for (int aa = 0; aa < 3; ++aa)
-                for (int bb = 0; bb < 3; ++bb) {
-                  const int gi = 3 * b + aa, gj = 3 * b2 + bb;
-                  Hb[aa][bb] = ((gi >> 2) >= (gj >> 2)) ? Hm[midx(gi, gj, nblk)] : Hm[midx(gj, gi, nblk)];
-                }
+                for (int bb = 0; bb < 3; ++bb) Hb[aa][bb] = __ldcg(Hm + sidx(3 * b + aa, 3 * b2 + bb, nblk));
               for (int cc = 0; cc < d1; ++cc)
                 for (int c2 = 0; c2 < d2; ++c2) {
+                  if (b == b2 && c2 > cc) continue;  // lower part of the diagonal block; mirrored below
                   const double* z = s_Zt + 9 * b + 3 * cc;
                   const double* z2 = s_Zt + 9 * b2 + 3 * c2;
                   double s = 0.0;
                   for (int aa = 0; aa < 3; ++aa)
                     for (int bb = 0; bb < 3; ++bb) s += z[aa] * Hb[aa][bb] * z2[bb];
-                  const int gi = s_off[b] + cc, gj = s_off[b2] + c2;
-                  if (b == b2 && c2 > cc) continue;  // lower part of the diagonal block; mirrored below
-                  if ((gi >> 2) >= (gj >> 2)) Mm[midx(gi, gj, nblk_r)] = s;
-                  else Mm[midx(gj, gi, nblk_r)] = s;
+                  const int gi = s_off[b] + cc, gj = s_off[b2] + c2;  // gi >= gj
+                  Mm[midx(gi, gj, nblk_r)] = s;
                   if ((gi >> 2) == (gj >> 2)) Mm[midx(gj, gi, nblk_r)] = s;
                 }
             }
+            G.sync();
+            if (nr > 0) {
+              for (int bj = gtid; bj < nblk_r; bj += GT) {
+                const int o = blkoff(bj, bj, nblk_r);
+                for (int bi = bj; bi < nblk_r; ++bi) s_tb[o + bi - bj] = (uint16_t)(bi | (bj << 8));
+              }
+              G.sync();
+            }
           }
-          __syncthreads();
+          m_is_h = false;
           bool fact_ok = true;
           if (nr > 0) {
-            fact_ok = chol_bc4<NT>(Mm, nblk_r);
-            if (fact_ok) chol_solve_bc4<NT>(Mm, nblk_r, s_tv, s_du);
+            fact_ok = chol_bc4<W>(G, Mm, nblk_r, s_tb);
+            if (fact_ok) chol_solve_bc4<W>(G, Mm, nblk_r, s_tv, s_du);
+          }
+          if (!none_active && nr > 0) {  // restore the tile table of the full system
+            for (int bj = gtid; bj < nblk; bj += GT) {
+              const int o = blkoff(bj, bj, nblk);
+              for (int bi = bj; bi < nblk; ++bi) s_tb[o + bi - bj] = (uint16_t)(bi | (bj << 8));
+            }
           }
           if (!fact_ok) break;
-          for (int b = tid; b < nb; b += NT) {
+          for (int b = gtid; b < nb; b += GT) {
             double f[3] = {s_f0[3 * b], s_f0[3 * b + 1], s_f0[3 * b + 2]};
-            for (int cc = 0; cc < 3 - s_rk[b]; ++cc) {
-              const double tv = s_tv[s_off[b] + cc];
-              for (int q = 0; q < 3; ++q) f[q] += s_Zt[9 * b + 3 * cc + q] * tv;
+            if (none_active) {
+              for (int q = 0; q < 3; ++q) f[q] = s_tv[3 * b + q];
+            } else {
+              for (int cc = 0; cc < 3 - s_rk[b]; ++cc) {
+                const double tv = s_tv[s_off[b] + cc];
+                for (int q = 0; q < 3; ++q) f[q] += s_Zt[9 * b + 3 * cc + q] * tv;
+              }
             }
             for (int q = 0; q < 3; ++q) s_up[3 * b + q] = f[q];
           }
-          if (tid < n4 - n) s_up[n + tid] = 0.0;
-          __syncthreads();
-          symv_bc4<NT>(Hm, n4, nblk, s_up, s_rhs);
+          if (gtid < n4 - n) s_up[n + gtid] = 0.0;
+          copy_mat<W>(G, Mm, Hm, ntiles << 4);
+          m_is_h = true;
+          G.sync();
+          symv_bc4<W>(G, Mm, n4, nblk, s_up, s_rhs);
           // multipliers, verification, correction
-          bool okm = true, changed = false;
-          for (int b = tid; b < nb; b += NT) {
-            double Nrm[10][3], lam[10], rb[3], y[5];
-            int idx[10], k = 0;
-            for (int q = 0; q < 5; ++q) if (s_actl[5 * b + q]) { row_vec(s_mu[b], q, Nrm[k]); idx[k++] = q; }
-            for (int q = 0; q < 5; ++q) if (s_actu[5 * b + q]) {
-              row_vec(s_mu[b], q, Nrm[k]);
-              Nrm[k][0] = -Nrm[k][0]; Nrm[k][1] = -Nrm[k][1]; Nrm[k][2] = -Nrm[k][2];
-              idx[k++] = 5 + q;
-            }
+          bool okm = true, changed = false, any_act2 = false;
+          for (int b = gtid; b < nb; b += GT) {
+            const double mub = cfg.mu[s_blk_i[b]];
+            const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
+            double rb[3], y[5], ll[5] = {0, 0, 0, 0, 0}, lu[5] = {0, 0, 0, 0, 0};
             for (int q = 0; q < 3; ++q) rb[q] = s_rhs[3 * b + q] + s_g[3 * b + q];
-            okm = block_multipliers(k, Nrm, rb, 1e-9 * gs, lam) && okm;
-            double ll[5] = {0, 0, 0, 0, 0}, lu[5] = {0, 0, 0, 0, 0};
-            for (int s = 0; s < k; ++s) { if (idx[s] < 5) ll[idx[s]] = lam[s]; else lu[idx[s] - 5] = lam[s]; }
-            cmul5(s_mu[b], s_up + 3 * b, y);
+            if (none_active) {
+              okm = okm && fmax(fabs(rb[0]), fmax(fabs(rb[1]), fabs(rb[2]))) <= 1e-9 * gs;
+            } else {
+              double Nrm[10][3], lam[10];
+              int idx[10], k = 0;
+              for (int q = 0; q < 5; ++q) if (s_actl[5 * b + q]) { row_vec(mub, q, Nrm[k]); idx[k++] = q; }
+              for (int q = 0; q < 5; ++q) if (s_actu[5 * b + q]) {
+                row_vec(mub, q, Nrm[k]);
+                Nrm[k][0] = -Nrm[k][0]; Nrm[k][1] = -Nrm[k][1]; Nrm[k][2] = -Nrm[k][2];
+                idx[k++] = 5 + q;
+              }
+              okm = block_multipliers(k, Nrm, rb, 1e-9 * gs, lam) && okm;
+              for (int s = 0; s < k; ++s) { if (idx[s] < 5) ll[idx[s]] = lam[s]; else lu[idx[s] - 5] = lam[s]; }
+            }
+            cmul5(mub, s_up + 3 * b, y);
             for (int q = 0; q < 5; ++q) {
-              const double ub = q < 4 ? s_ubxy[b] : s_ubz[b];
+              const double ub = q < 4 ? ubxy : ubz;
               const double sl = y[q], su = ub - y[q];
               const bool vl = sl < -1e-9 * us, vu = su < -1e-9 * us;
               const bool nl = ll[q] < -1e-9 * gs, nuu = lu[q] < -1e-9 * gs;
               if (vl || vu || nl || nuu) changed = true;
-              s_actl[5 * b + q] = (s_actl[5 * b + q] || vl) && !nl;
-              s_actu[5 * b + q] = (s_actu[5 * b + q] || vu) && !nuu;
+              const bool al = (s_actl[5 * b + q] || vl) && !nl, au = (s_actu[5 * b + q] || vu) && !nuu;
+              s_actl[5 * b + q] = al; s_actu[5 * b + q] = au;
+              any_act2 = any_act2 || al || au;
               s_cdu[5 * b + q] = sl;   // candidate slacks / multipliers, committed on accept
               s_dzl[5 * b + q] = ll[q]; s_dzu[5 * b + q] = lu[q];
             }
           }
-          const bool good = __syncthreads_and(okm && !changed);
+          const bool good = G.all(okm && !changed);
+          none_active = G.all(!any_act2);
           if (good) accepted = true;
         }
         if (accepted) {
-          for (int t = tid; t < n; t += NT) s_u[t] = s_up[t];
-          for (int b = tid; b < nb; b += NT)
+          for (int t = gtid; t < n; t += GT) s_u[t] = s_up[t];
+          for (int b = gtid; b < nb; b += GT) {
+            const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
             for (int q = 0; q < 5; ++q) {
-              const double ub = q < 4 ? s_ubxy[b] : s_ubz[b];
+              const double ub = q < 4 ? ubxy : ubz;
               s_sl[5 * b + q] = s_cdu[5 * b + q]; s_su[5 * b + q] = ub - s_cdu[5 * b + q];
               s_zl[5 * b + q] = s_dzl[5 * b + q]; s_zu[5 * b + q] = s_dzu[5 * b + q];
             }
-          __syncthreads();
+          }
+          G.sync();
           status = CMPC_STATUS_OK;
           break;
         }
-        __syncthreads();
+        G.sync();
+        // polish not accepted: rd was used as f0 scratch -> recompute the residual
+        if (!m_is_h) { copy_mat<W>(G, Mm, Hm, ntiles << 4); G.sync(); m_is_h = true; }
+        symv_bc4<W>(G, Mm, n4, nblk, s_u, s_rd);
+        for (int b = gtid; b < nb; b += GT) {
+          double w[5], o[3];
+          for (int q = 0; q < 5; ++q) w[q] = s_zl[5 * b + q] - s_zu[5 * b + q];
+          ctmul5(cfg.mu[s_blk_i[b]], w, o);
+          for (int q = 0; q < 3; ++q) s_rd[3 * b + q] += s_g[3 * b + q] - o[q];
+        }
+        G.sync();
       }
       if (strict && (!cfg.polish || npolish >= 3)) break;
       if (mu <= 1e-8 * cfg.tol * gs * us) break;  // far past convergence: stop before 0/0
       if (it == cfg.max_iter) break;
 
       // ---- M = H + C' diag(zl/sl + zu/su) C  (only the 3x3 diagonal blocks change)
-      {
-        const int mat = bc4_doubles(n4);
-        for (int t = tid; t < mat; t += NT) Mm[t] = Hm[t];
-        __syncthreads();
-        for (int b = tid; b < nb; b += NT) {
-          double sg[5];
-          for (int q = 0; q < 5; ++q) sg[q] = s_zl[5 * b + q] / s_sl[5 * b + q] + s_zu[5 * b + q] / s_su[5 * b + q];
-          const double mb = s_mu[b], sx = sg[0] + sg[1], sy = sg[2] + sg[3];
-          const int g0 = 3 * b, g1 = g0 + 1, g2 = g0 + 2;
-          Mm[midx(g0, g0, nblk)] += sx;
-          Mm[midx(g1, g1, nblk)] += sy;
-          Mm[midx(g2, g2, nblk)] += mb * mb * (sx + sy) + sg[4];
-          Mm[midx(g2, g0, nblk)] += mb * (sg[1] - sg[0]);
-          Mm[midx(g2, g1, nblk)] += mb * (sg[3] - sg[2]);
-        }
-        __syncthreads();
+      for (int b = gtid; b < nb; b += GT) {
+        double sg[5];
+        for (int q = 0; q < 5; ++q) sg[q] = s_zl[5 * b + q] / s_sl[5 * b + q] + s_zu[5 * b + q] / s_su[5 * b + q];
+        const double mb = cfg.mu[s_blk_i[b]], sx = sg[0] + sg[1], sy = sg[2] + sg[3];
+        const int g0 = 3 * b, g1 = g0 + 1, g2 = g0 + 2;
+        Mm[midx(g0, g0, nblk)] += sx;
+        Mm[midx(g1, g1, nblk)] += sy;
+        Mm[midx(g2, g2, nblk)] += mb * mb * (sx + sy) + sg[4];
+        Mm[midx(g2, g0, nblk)] += mb * (sg[1] - sg[0]);
+        Mm[midx(g2, g1, nblk)] += mb * (sg[3] - sg[2]);
       }
-      if (!chol_bc4<NT>(Mm, nblk)) { numerical = true; break; }
+      m_is_h = false;
+      G.sync();
+      if (!chol_bc4<W>(G, Mm, nblk, s_tb)) { numerical = true; break; }
 
       double alpha = 1.0, sigma = 0.0;
       for (int phase = 0; phase < 2; ++phase) {
         // phase 0: affine predictor; phase 1: centred corrector (Mehrotra)
-        for (int b = tid; b < nb; b += NT) {
+        for (int b = gtid; b < nb; b += GT) {
           double tq[5], o[3];
           for (int q = 0; q < 5; ++q) {
             const int t = 5 * b + q;
@@ -934,15 +1083,15 @@ __global__ void __launch_bounds__(NT) cmpc_solve_kernel(const DevConfig cfg, con
             if (phase) { rcl += sigma * mu - s_cdu[t] * s_dzl[t]; rcu += sigma * mu + s_cdu[t] * s_dzu[t]; }
             tq[q] = rcl / s_sl[t] - rcu / s_su[t];
           }
-          ctmul5(s_mu[b], tq, o);
+          ctmul5(cfg.mu[s_blk_i[b]], tq, o);
           for (int q = 0; q < 3; ++q) s_du[3 * b + q] = -s_rd[3 * b + q] + o[q];
         }
-        __syncthreads();
-        chol_solve_bc4<NT>(Mm, nblk, s_du, s_rhs);
+        G.sync();
+        chol_solve_bc4<W>(G, Mm, nblk, s_du, s_rhs);
         double amin = 1.0, ga = 0.0;
-        for (int b = tid; b < nb; b += NT) {
+        for (int b = gtid; b < nb; b += GT) {
           double y[5];
-          cmul5(s_mu[b], s_du + 3 * b, y);
+          cmul5(cfg.mu[s_blk_i[b]], s_du + 3 * b, y);
           for (int q = 0; q < 5; ++q) {
             const int t = 5 * b + q;
             double rcl = -s_sl[t] * s_zl[t], rcu = -s_su[t] * s_zu[t];
@@ -957,31 +1106,33 @@ __global__ void __launch_bounds__(NT) cmpc_solve_kernel(const DevConfig cfg, con
             s_cdu[t] = cd; s_dzl[t] = dl; s_dzu[t] = du_;
           }
         }
-        alpha = -block_max<NT>(-amin, s_red);
+        alpha = -G.max(-amin);
         if (!phase) {
-          for (int t = tid; t < m; t += NT)
+          G.sync();
+          for (int t = gtid; t < m; t += GT)
             ga += (s_sl[t] + alpha * s_cdu[t]) * (s_zl[t] + alpha * s_dzl[t]) +
                   (s_su[t] - alpha * s_cdu[t]) * (s_zu[t] + alpha * s_dzu[t]);
-          ga = block_sum<NT>(ga, s_red);
+          ga = G.sum(ga);
           const double ratio = ga / gap;
           sigma = ratio * ratio * ratio;
         }
       }
       alpha = fmin(1.0, 0.995 * alpha);
       bool fin = true;
-      for (int t = tid; t < n; t += NT) { const double v = s_u[t] + alpha * s_du[t]; s_u[t] = v; fin = fin && isfinite(v); }
-      __syncthreads();
-      for (int b = tid; b < nb; b += NT) {
+      for (int t = gtid; t < n; t += GT) { const double v = s_u[t] + alpha * s_du[t]; s_u[t] = v; fin = fin && isfinite(v); }
+      G.sync();
+      for (int b = gtid; b < nb; b += GT) {
+        const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
         double y[5];
-        cmul5(s_mu[b], s_u + 3 * b, y);
+        cmul5(cfg.mu[s_blk_i[b]], s_u + 3 * b, y);
         for (int q = 0; q < 5; ++q) {
           const int t = 5 * b + q;
-          const double ub = q < 4 ? s_ubxy[b] : s_ubz[b];
+          const double ub = q < 4 ? ubxy : ubz;
           s_zl[t] += alpha * s_dzl[t]; s_zu[t] += alpha * s_dzu[t];
           s_sl[t] = y[q]; s_su[t] = ub - y[q];
         }
       }
-      fin = __syncthreads_and(fin);
+      fin = G.all(fin);
       if (!fin) { numerical = true; break; }
     }
     if (numerical) status = CMPC_STATUS_NUMERICAL;
@@ -990,78 +1141,82 @@ __global__ void __launch_bounds__(NT) cmpc_solve_kernel(const DevConfig cfg, con
     // ---- outputs
     if (!numerical) {
       // scaled KKT residual (same definition as the oracle)
-      symv_bc4<NT>(Hm, n4, nblk, s_u, s_rhs);
+      if (!m_is_h) { copy_mat<W>(G, Mm, Hm, ntiles << 4); G.sync(); m_is_h = true; }
+      symv_bc4<W>(G, Mm, n4, nblk, s_u, s_rhs);
       double stat = 0.0, umax = 0.0, prim = 0.0, dual = 0.0, comp = 0.0;
-      for (int b = tid; b < nb; b += NT) {
+      for (int b = gtid; b < nb; b += GT) {
+        const double mub = cfg.mu[s_blk_i[b]];
+        const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
         double w[5], o[3], y[5];
         for (int q = 0; q < 5; ++q) w[q] = s_zl[5 * b + q] - s_zu[5 * b + q];
-        ctmul5(s_mu[b], w, o);
-        cmul5(s_mu[b], s_u + 3 * b, y);
+        ctmul5(mub, w, o);
+        cmul5(mub, s_u + 3 * b, y);
         for (int q = 0; q < 3; ++q) {
           stat = fmax(stat, fabs(s_rhs[3 * b + q] + s_g[3 * b + q] - o[q]));
           umax = fmax(umax, fabs(s_u[3 * b + q]));
         }
         for (int q = 0; q < 5; ++q) {
-          const double ub = q < 4 ? s_ubxy[b] : s_ubz[b];
+          const double ub = q < 4 ? ubxy : ubz;
           const double sl = y[q], su = ub - y[q], zl = s_zl[5 * b + q], zu = s_zu[5 * b + q];
           prim = fmax(prim, fmax(-sl, -su));
           dual = fmax(dual, fmax(-zl, -zu));
           comp = fmax(comp, fmax(fabs(zl * sl), fabs(zu * su)));
         }
       }
-      stat = block_max<NT>(stat, s_red);
-      umax = block_max<NT>(umax, s_red);
-      prim = block_max<NT>(prim, s_red);
-      dual = block_max<NT>(dual, s_red);
-      comp = block_max<NT>(comp, s_red);
+      stat = G.max(stat);
+      umax = G.max(umax);
+      prim = G.max(prim);
+      dual = G.max(dual);
+      comp = G.max(comp);
       const double usf = 1.0 + umax;
       const double kkt = fmax(fmax(stat / gs, prim / usf), fmax(dual / gs, comp / (gs * usf)));
       if (status != CMPC_STATUS_OK) {
-        for (int t = tid; t < m; t += NT) {
+        for (int t = gtid; t < m; t += GT) {
           s_actl[t] = s_zl[t] * usf > s_sl[t] * gs;
           s_actu[t] = s_zu[t] * usf > s_su[t] * gs;
         }
       }
-      __syncthreads();
+      G.sync();
       // forces in the reference's per-leg order [L][N][3] (CentroidalMPC.cpp:270)
-      for (int t = tid; t < nf; t += NT) {
+      for (int t = gtid; t < nf; t += GT) {
         const int i = t / (3 * N), j = (t % (3 * N)) / 3, q = t % 3;
         const int b = s_blk_of[j * L + i];
         args.forces[(size_t)inst * nf + t] = b < 0 ? 0.0 : s_u[3 * b + q];
       }
       if (args.lam) {
-        for (int t = tid; t < 2 * mmax; t += NT) {
-          const int side = t / mmax, rem = t % mmax, ji = rem / 5, q = rem % 5;
+        for (int t = gtid; t < 2 * mfull; t += GT) {
+          const int side = t / mfull, rem = t % mfull, ji = rem / 5, q = rem % 5;
           const int b = s_blk_of[ji];
-          args.lam[(size_t)inst * 2 * mmax + t] = b < 0 ? 0.0 : (side ? s_zu[5 * b + q] : s_zl[5 * b + q]);
+          args.lam[(size_t)inst * 2 * mfull + t] = b < 0 ? 0.0 : (side ? s_zu[5 * b + q] : s_zl[5 * b + q]);
         }
       }
       if (args.active) {
-        for (int t = tid; t < nbmax; t += NT) {
+        for (int t = gtid; t < nbfull; t += GT) {
           const int b = s_blk_of[t];
           uint16_t a = 0x8000;
           if (b >= 0) {
             a = 0;
             for (int q = 0; q < 5; ++q) a |= (uint16_t)((s_actl[5 * b + q] ? 1 : 0) << q | (s_actu[5 * b + q] ? 1 : 0) << (5 + q));
           }
-          args.active[(size_t)inst * nbmax + t] = a;
+          args.active[(size_t)inst * nbfull + t] = a;
         }
       }
-      if (tid == 0) {
+      if (gtid == 0) {
         args.status[inst] = status;
         if (args.iters) args.iters[inst] = it;
         if (args.kkt) args.kkt[inst] = kkt;
       }
     } else {
-      for (int t = tid; t < nf; t += NT) args.forces[(size_t)inst * nf + t] = 0.0;
-      if (args.lam) for (int t = tid; t < 2 * mmax; t += NT) args.lam[(size_t)inst * 2 * mmax + t] = 0.0;
-      if (args.active) for (int t = tid; t < nbmax; t += NT) args.active[(size_t)inst * nbmax + t] = 0;
-      if (tid == 0) {
+      for (int t = gtid; t < nf; t += GT) args.forces[(size_t)inst * nf + t] = 0.0;
+      if (args.lam) for (int t = gtid; t < 2 * mfull; t += GT) args.lam[(size_t)inst * 2 * mfull + t] = 0.0;
+      if (args.active) for (int t = gtid; t < nbfull; t += GT) args.active[(size_t)inst * nbfull + t] = 0;
+      if (gtid == 0) {
         args.status[inst] = status;
         if (args.iters) args.iters[inst] = it;
         if (args.kkt) args.kkt[inst] = 0.0;
       }
     }
+    G.sync();
   }
 }
 
