@@ -222,8 +222,8 @@ int plan_class(cmpc_handle* h, cmpc_handle::ClassPlan& p, int W, int nbmax, int 
   const int N = h->cfg.horizon, L = h->cfg.num_legs;
   p.W = W; p.nbmax = nbmax; p.n4max = ((3 * nbmax + 3) / 4) * 4;
   p.m_in_smem = 1;
-  SmemPlan sp = make_plan(N, L, p.nbmax, p.n4max, 1);
-  if (mode == 1 || (size_t)sp.total * 8 > kMaxSmem) { p.m_in_smem = 0; sp = make_plan(N, L, p.nbmax, p.n4max, 0); }
+  SmemPlan sp = make_plan(N, L, W, p.nbmax, p.n4max, 1);
+  if (mode == 1 || (size_t)sp.total * 8 > kMaxSmem) { p.m_in_smem = 0; sp = make_plan(N, L, W, p.nbmax, p.n4max, 0); }
   if ((size_t)sp.total * 8 > kMaxSmem) return fail(h, CMPC_ERR_ARG, "horizon too large for the shared-memory vectors");
   const int gmax = 256 / (32 * W);
   p.groups = (int)std::min<size_t>((size_t)gmax, kMaxSmem / ((size_t)sp.total * 8));
@@ -325,7 +325,7 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
   // four warps, larger -> a whole 256-thread CTA; the factor lives in shared memory whenever it fits
   {
     const int nbfull = L * N;
-    const int cap[kNumClasses] = {21, 42, 64, nbfull};
+    const int cap[kNumClasses] = {20, 42, 64, nbfull};
     const int Wc[kNumClasses] = {1, 4, 8, 8};
     int b[kNumClasses];
     int lower = 0;

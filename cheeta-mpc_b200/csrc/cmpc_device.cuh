@@ -67,11 +67,15 @@ struct SolveArgs {
 };
 
 // ------------------------------------------------------------------ BC4 layout
+// Tiles are 16 doubles padded to kTS = 18 (144 B): lanes that walk consecutive tiles with
+// 128-bit accesses then fall into distinct 16-byte bank groups (9 t mod 8 = t mod 8), where
+// the natural 128 B stride would put all 32 lanes on the same banks.
+constexpr int kTS = 18;
 __device__ __forceinline__ int blkoff(int bi, int bj, int nblk) {
   return bj * nblk - ((bj * (bj - 1)) >> 1) + (bi - bj);
 }
 __device__ __forceinline__ int midx(int i, int j, int nblk) {  // requires i>>2 >= j>>2
-  return (blkoff(i >> 2, j >> 2, nblk) << 4) + ((i & 3) << 2) + (j & 3);
+  return blkoff(i >> 2, j >> 2, nblk) * kTS + ((i & 3) << 2) + (j & 3);
 }
 __device__ __forceinline__ int sidx(int i, int j, int nblk) {  // symmetric access
   return ((i >> 2) >= (j >> 2)) ? midx(i, j, nblk) : midx(j, i, nblk);
@@ -80,7 +84,7 @@ __host__ __device__ inline int bc4_tiles(int n) {
   int nblk = (n + 3) >> 2;
   return (nblk * (nblk + 1)) >> 1;
 }
-__host__ __device__ inline int bc4_doubles(int n) { return bc4_tiles(n) << 4; }
+__host__ __device__ inline int bc4_doubles(int n) { return bc4_tiles(n) * 18; }
 
 // ------------------------------------------------------------------ group primitives
 template <int W>
@@ -165,185 +169,288 @@ struct Group {
 };
 
 // ------------------------------------------------------------------ 4x4 tile kernels
-// Cholesky of a 4x4 SPD tile (row-major, lower part read). Writes l (lower, row-major, upper
-// zeroed) and the inverse diagonal. Returns false if a pivot is not positive.
-__device__ __forceinline__ bool potrf4(const double* a, double* l, double* dinv) {
-  double a00 = a[0], a10 = a[4], a11 = a[5], a20 = a[8], a21 = a[9], a22 = a[10];
-  double a30 = a[12], a31 = a[13], a32 = a[14], a33 = a[15];
+__device__ __forceinline__ void ld_tile(const double* p, double* r) {
+  const double2* p2 = reinterpret_cast<const double2*>(p);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { const double2 v = p2[q]; r[2 * q] = v.x; r[2 * q + 1] = v.y; }
+}
+__device__ __forceinline__ void st_tile(double* p, const double* r) {
+  double2* p2 = reinterpret_cast<double2*>(p);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) p2[q] = make_double2(r[2 * q], r[2 * q + 1]);
+}
+// 1/x to full double precision (not correctly rounded): MUFU seed + two Newton steps.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
+// Cholesky of a 4x4 SPD tile (row-major, lower part read) in "solve form" d[16]:
+//   strict lower  : L
+//   diagonal      : 1 / l_ii
+//   strict upper  : strict lower of L^-1, transposed  (d[4c + r] = Linv(r, c), r > c... see below)
+// so that  L^-1 b  and  L^-T b  are four independent short dot products (no substitution
+// chain) in the TRSM and in both triangular solves.  d[4*r + c] for r < c holds Linv(c, r).
+// Returns false if a pivot is not positive.
+__device__ __forceinline__ bool potrf4(const double* a, double* d) {
+  const double a00 = a[0], a10 = a[4], a11 = a[5], a20 = a[8], a21 = a[9], a22 = a[10];
+  const double a30 = a[12], a31 = a[13], a32 = a[14], a33 = a[15];
   bool ok = a00 > 0.0;
-  double i0 = rsqrt(a00);
-  double l00 = a00 * i0, l10 = a10 * i0, l20 = a20 * i0, l30 = a30 * i0;
-  double d1 = a11 - l10 * l10;
+  const double i0 = rsqrt(a00);
+  const double l10 = a10 * i0, l20 = a20 * i0, l30 = a30 * i0;
+  const double d1 = a11 - l10 * l10;
   ok = ok && d1 > 0.0;
-  double i1 = rsqrt(d1);
-  double l11 = d1 * i1, l21 = (a21 - l20 * l10) * i1, l31 = (a31 - l30 * l10) * i1;
-  double d2 = a22 - l20 * l20 - l21 * l21;
+  const double i1 = rsqrt(d1);
+  const double l21 = (a21 - l20 * l10) * i1, l31 = (a31 - l30 * l10) * i1;
+  const double d2 = a22 - l20 * l20 - l21 * l21;
   ok = ok && d2 > 0.0;
-  double i2 = rsqrt(d2);
-  double l22 = d2 * i2, l32 = (a32 - l30 * l20 - l31 * l21) * i2;
-  double d3 = a33 - l30 * l30 - l31 * l31 - l32 * l32;
+  const double i2 = rsqrt(d2);
+  const double l32 = (a32 - l30 * l20 - l31 * l21) * i2;
+  const double d3 = a33 - l30 * l30 - l31 * l31 - l32 * l32;
   ok = ok && d3 > 0.0;
-  double i3 = rsqrt(d3);
-  double l33 = d3 * i3;
-  l[0] = l00; l[1] = 0; l[2] = 0; l[3] = 0;
-  l[4] = l10; l[5] = l11; l[6] = 0; l[7] = 0;
-  l[8] = l20; l[9] = l21; l[10] = l22; l[11] = 0;
-  l[12] = l30; l[13] = l31; l[14] = l32; l[15] = l33;
-  dinv[0] = i0; dinv[1] = i1; dinv[2] = i2; dinv[3] = i3;
+  const double i3 = rsqrt(d3);
+  // inverse of the unit... of L: Linv(r,c), r > c
+  const double v10 = -l10 * i0 * i1;
+  const double v21 = -l21 * i1 * i2;
+  const double v32 = -l32 * i2 * i3;
+  const double v20 = -(l20 * i0 + l21 * v10) * i2;
+  const double v31 = -(l31 * i1 + l32 * v21) * i3;
+  const double v30 = -(l30 * i0 + l31 * v10 + l32 * v20) * i3;
+  d[0] = i0;   d[1] = v10;  d[2] = v20;  d[3] = v30;
+  d[4] = l10;  d[5] = i1;   d[6] = v21;  d[7] = v31;
+  d[8] = l20;  d[9] = l21;  d[10] = i2;  d[11] = v32;
+  d[12] = l30; d[13] = l31; d[14] = l32; d[15] = i3;
   return ok;
+}
+// y = L^-1 b for a solve-form diagonal tile d
+__device__ __forceinline__ void linv4(const double* d, double b0, double b1, double b2, double b3,
+                                      double& y0, double& y1, double& y2, double& y3) {
+  y0 = d[0] * b0;
+  y1 = d[1] * b0 + d[5] * b1;
+  y2 = d[2] * b0 + d[6] * b1 + d[10] * b2;
+  y3 = d[3] * b0 + d[7] * b1 + d[11] * b2 + d[15] * b3;
+}
+// x = L^-T y
+__device__ __forceinline__ void linvt4(const double* d, double y0, double y1, double y2, double y3,
+                                       double& x0, double& x1, double& x2, double& x3) {
+  x3 = d[15] * y3;
+  x2 = d[10] * y2 + d[11] * y3;
+  x1 = d[5] * y1 + d[6] * y2 + d[7] * y3;
+  x0 = d[0] * y0 + d[1] * y1 + d[2] * y2 + d[3] * y3;
+}
+
+// Rows of a vector are owned by threads: row r = gtid + s * GT, s = 0, 1 (n4 <= 2 GT).
+// Fetch the four pivot values x[4kb .. 4kb+3] from their owners' registers.
+template <int W>
+__device__ __forceinline__ void pivot4(const Group<W>& G, const double (&xr)[2], int kb, double* exch,
+                                       double& b0, double& b1, double& b2, double& b3) {
+  constexpr int GT = Group<W>::GT;
+  const int r0 = 4 * kb;
+  if constexpr (W == 1) {
+    const double v = (r0 >= GT) ? xr[1] : xr[0];
+    const int l0 = r0 & 31;
+    b0 = __shfl_sync(0xffffffffu, v, l0);
+    b1 = __shfl_sync(0xffffffffu, v, l0 + 1);
+    b2 = __shfl_sync(0xffffffffu, v, l0 + 2);
+    b3 = __shfl_sync(0xffffffffu, v, l0 + 3);
+  } else {
+    double* buf = exch + ((kb & 1) << 2);  // double-buffered: one barrier per step
+    const int q0 = G.gtid - (r0 % GT);
+    if (q0 >= 0 && q0 < 4) buf[q0] = (r0 >= GT) ? xr[1] : xr[0];
+    G.sync();
+    b0 = buf[0]; b1 = buf[1]; b2 = buf[2]; b3 = buf[3];
+  }
 }
 
 // Tiled right-looking Cholesky in BC4 layout, in place; the whole group calls it.
-// tb[t] = bi | bj << 8 for storage tile t (built once per instance).  The factored diagonal
-// tile carries 1/l_ii in its (unused) upper triangle slots [1],[2],[3],[7] -> the solves
-// multiply instead of divide.  Returns false (uniformly) on a non-positive pivot.
+// tb[t] = bi | bj << 8 for storage tile t.  Diagonal tiles end up in solve form (potrf4).
+// If rhs != nullptr the forward substitution  y = L^-1 rhs  is fused into the sweep (rows
+// live in registers, the update of step kb rides along with the trailing update) and y
+// overwrites rhs.  Returns false (uniformly) on a non-positive pivot.
 template <int W>
-__device__ bool chol_bc4(const Group<W>& G, double* M, int nblk, const uint16_t* tb) {
+__device__ bool chol_bc4(const Group<W>& G, double* M, int nblk, const uint16_t* tb, double* rhs, double* exch) {
   constexpr int GT = Group<W>::GT;
   const int gtid = G.gtid;
   const int ntiles = (nblk * (nblk + 1)) >> 1;
+  const int n4 = nblk << 2;
+  double xr[2] = {0.0, 0.0};
+  if (rhs) {
+    if (gtid < n4) xr[0] = rhs[gtid];
+    if (gtid + GT < n4) xr[1] = rhs[gtid + GT];
+  }
   bool ok = true;
   for (int kb = 0; kb < nblk; ++kb) {
     const int col0 = blkoff(kb, kb, nblk);  // storage index of the diagonal tile of column kb
     const int nrows = nblk - kb;
-    double l[16], dinv[4];
-    if (gtid < nrows) {
-      // POTRF redundantly in every lane that owns a panel tile (broadcast loads), then TRSM
-      ok = potrf4(M + ((size_t)col0 << 4), l, dinv) && ok;
-      for (int t = gtid; t < nrows; t += GT) {
-        if (t == 0) continue;
-        double* A = M + ((size_t)(col0 + t) << 4);
+    double d[16], a[16];
+    ld_tile(M + (size_t)col0 * kTS, a);     // broadcast loads: every lane factors the same tile
+    ok = potrf4(a, d) && ok;
+    // TRSM: X = A L^-T, one panel tile per lane
+    for (int t = 1 + gtid; t < nrows; t += GT) {
+      double* A = M + (size_t)(col0 + t) * kTS;
+      double x[16];
+      ld_tile(A, a);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          double x0 = A[4 * r] * dinv[0];
-          double x1 = (A[4 * r + 1] - x0 * l[4]) * dinv[1];
-          double x2 = (A[4 * r + 2] - x0 * l[8] - x1 * l[9]) * dinv[2];
-          double x3 = (A[4 * r + 3] - x0 * l[12] - x1 * l[13] - x2 * l[14]) * dinv[3];
-          A[4 * r] = x0; A[4 * r + 1] = x1; A[4 * r + 2] = x2; A[4 * r + 3] = x3;
+      for (int r = 0; r < 4; ++r) linv4(d, a[4 * r], a[4 * r + 1], a[4 * r + 2], a[4 * r + 3], x[4 * r], x[4 * r + 1], x[4 * r + 2], x[4 * r + 3]);
+      st_tile(A, x);
+    }
+    double y0 = 0, y1 = 0, y2 = 0, y3 = 0;
+    if (rhs) {
+      double b0, b1, b2, b3;
+      pivot4<W>(G, xr, kb, exch, b0, b1, b2, b3);
+      linv4(d, b0, b1, b2, b3, y0, y1, y2, y3);
+    }
+    ok = G.all(ok);  // also the barrier between the panel and the trailing update
+    if (!ok) return false;
+    if (gtid == 0) st_tile(M + (size_t)col0 * kTS, d);
+    if (rhs) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int r = gtid + s * GT;
+        const int q = r - 4 * kb;
+        if (q >= 0 && q < 4) xr[s] = q == 0 ? y0 : (q == 1 ? y1 : (q == 2 ? y2 : y3));
+        else if (q >= 4 && r < n4) {
+          const double2* A2 = reinterpret_cast<const double2*>(M + (size_t)(col0 + (r >> 2) - kb) * kTS + ((r & 3) << 2));
+          const double2 u = A2[0], v = A2[1];
+          xr[s] -= u.x * y0 + u.y * y1 + v.x * y2 + v.y * y3;
         }
       }
-    }
-    ok = G.all(ok);   // also the barrier between the panel and the trailing update
-    if (!ok) return false;
-    if (gtid == 0) {
-      double* Akk = M + ((size_t)col0 << 4);
-      l[1] = dinv[0]; l[2] = dinv[1]; l[3] = dinv[2]; l[7] = dinv[3];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) Akk[q] = l[q];
     }
     // trailing update: storage tiles of columns kb+1.. are contiguous
     const int t0 = col0 + nrows;
     for (int t = t0 + gtid; t < ntiles; t += GT) {
       const int bi = tb[t] & 0xff, bj = tb[t] >> 8;
-      const double* Li = M + ((size_t)(col0 + bi - kb) << 4);
-      const double* Lj = M + ((size_t)(col0 + bj - kb) << 4);
-      double* C = M + ((size_t)t << 4);
-      double li[16], lj[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) { li[q] = Li[q]; lj[q] = Lj[q]; }
+      double li[16], lj[16], c[16];
+      double* C = M + (size_t)t * kTS;
+      ld_tile(M + (size_t)(col0 + bi - kb) * kTS, li);
+      ld_tile(M + (size_t)(col0 + bj - kb) * kTS, lj);
+      ld_tile(C, c);
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-          double s = C[4 * rr + cc];
+          double sacc = c[4 * rr + cc];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) s -= li[4 * rr + k] * lj[4 * cc + k];
-          C[4 * rr + cc] = s;
+          for (int k = 0; k < 4; ++k) sacc -= li[4 * rr + k] * lj[4 * cc + k];
+          c[4 * rr + cc] = sacc;
         }
+      st_tile(C, c);
     }
+    G.sync();
+  }
+  if (rhs) {
+    if (gtid < n4) rhs[gtid] = xr[0];
+    if (gtid + GT < n4) rhs[gtid + GT] = xr[1];
     G.sync();
   }
   return true;
 }
 
-// Solve L L' x = b (x: n4 doubles in shared memory, overwritten by the solution; tmp: n4
-// doubles of scratch).  Forward pass accumulates residuals in x and writes y to tmp; the
-// backward pass accumulates in tmp and writes the solution to x -- no element is read and
-// written by different threads inside one step, so one barrier per block step suffices.
+// Forward substitution y = L^-1 x (in place in shared memory), rows in registers.
 template <int W>
-__device__ void chol_solve_bc4(const Group<W>& G, const double* M, int nblk, double* x, double* tmp) {
+__device__ void chol_fwd_bc4(const Group<W>& G, const double* M, int nblk, double* x, double* exch) {
   constexpr int GT = Group<W>::GT;
-  const int gtid = G.gtid;
+  const int gtid = G.gtid, n4 = nblk << 2;
+  double xr[2] = {0.0, 0.0};
+  if (gtid < n4) xr[0] = x[gtid];
+  if (gtid + GT < n4) xr[1] = x[gtid + GT];
   for (int kb = 0; kb < nblk; ++kb) {
-    if (gtid < nblk - kb) {
-      const double* l = M + ((size_t)blkoff(kb, kb, nblk) << 4);
-      const double b0 = x[4 * kb], b1 = x[4 * kb + 1], b2 = x[4 * kb + 2], b3 = x[4 * kb + 3];
-      const double y0 = b0 * l[1];
-      const double y1 = (b1 - l[4] * y0) * l[2];
-      const double y2 = (b2 - l[8] * y0 - l[9] * y1) * l[3];
-      const double y3 = (b3 - l[12] * y0 - l[13] * y1 - l[14] * y2) * l[7];
-      for (int bi = kb + gtid; bi < nblk; bi += GT) {
-        if (bi == kb) {
-          tmp[4 * kb] = y0; tmp[4 * kb + 1] = y1; tmp[4 * kb + 2] = y2; tmp[4 * kb + 3] = y3;
-        } else {
-          const double* A = M + ((size_t)blkoff(bi, kb, nblk) << 4);
+    const int col0 = blkoff(kb, kb, nblk);
+    double d[16], b0, b1, b2, b3, y0, y1, y2, y3;
+    ld_tile(M + (size_t)col0 * kTS, d);
+    pivot4<W>(G, xr, kb, exch, b0, b1, b2, b3);
+    linv4(d, b0, b1, b2, b3, y0, y1, y2, y3);
 #pragma unroll
-          for (int r = 0; r < 4; ++r)
-            x[4 * bi + r] -= A[4 * r] * y0 + A[4 * r + 1] * y1 + A[4 * r + 2] * y2 + A[4 * r + 3] * y3;
-        }
+    for (int s = 0; s < 2; ++s) {
+      const int r = gtid + s * GT;
+      const int q = r - 4 * kb;
+      if (q >= 0 && q < 4) xr[s] = q == 0 ? y0 : (q == 1 ? y1 : (q == 2 ? y2 : y3));
+      else if (q >= 4 && r < n4) {
+        const double2* A2 = reinterpret_cast<const double2*>(M + (size_t)(col0 + (r >> 2) - kb) * kTS + ((r & 3) << 2));
+        const double2 u = A2[0], v = A2[1];
+        xr[s] -= u.x * y0 + u.y * y1 + v.x * y2 + v.y * y3;
       }
     }
-    G.sync();
   }
-  for (int kb = nblk - 1; kb >= 0; --kb) {
-    if (gtid <= kb) {
-      const double* l = M + ((size_t)blkoff(kb, kb, nblk) << 4);
-      const double y0 = tmp[4 * kb], y1 = tmp[4 * kb + 1], y2 = tmp[4 * kb + 2], y3 = tmp[4 * kb + 3];
-      const double x3 = y3 * l[7];
-      const double x2 = (y2 - l[14] * x3) * l[3];
-      const double x1 = (y1 - l[9] * x2 - l[13] * x3) * l[2];
-      const double x0 = (y0 - l[4] * x1 - l[8] * x2 - l[12] * x3) * l[1];
-      for (int bj = kb - gtid; bj >= 0; bj -= GT) {
-        if (bj == kb) {
-          x[4 * kb] = x0; x[4 * kb + 1] = x1; x[4 * kb + 2] = x2; x[4 * kb + 3] = x3;
-        } else {
-          const double* A = M + ((size_t)blkoff(kb, bj, nblk) << 4);  // L_kj
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            tmp[4 * bj + c] -= A[c] * x0 + A[4 + c] * x1 + A[8 + c] * x2 + A[12 + c] * x3;
-        }
-      }
-    }
-    G.sync();
-  }
+  if (gtid < n4) x[gtid] = xr[0];
+  if (gtid + GT < n4) x[gtid + GT] = xr[1];
+  G.sync();
 }
 
-// y = H x for symmetric H in BC4 layout (diagonal tiles hold both triangles).
-// tpr lanes cooperate on one row.  The whole group calls it; ends with a group barrier.
+// Backward substitution x = L^-T y (in place in shared memory), rows in registers.
+template <int W>
+__device__ void chol_bwd_bc4(const Group<W>& G, const double* M, int nblk, double* x, double* exch) {
+  constexpr int GT = Group<W>::GT;
+  const int gtid = G.gtid, n4 = nblk << 2;
+  double xr[2] = {0.0, 0.0};
+  if (gtid < n4) xr[0] = x[gtid];
+  if (gtid + GT < n4) xr[1] = x[gtid + GT];
+  for (int kb = nblk - 1; kb >= 0; --kb) {
+    double d[16], b0, b1, b2, b3, x0, x1, x2, x3;
+    ld_tile(M + (size_t)blkoff(kb, kb, nblk) * kTS, d);
+    pivot4<W>(G, xr, kb, exch, b0, b1, b2, b3);
+    linvt4(d, b0, b1, b2, b3, x0, x1, x2, x3);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int r = gtid + s * GT;
+      const int q = r - 4 * kb;
+      if (q >= 0 && q < 4) xr[s] = q == 0 ? x0 : (q == 1 ? x1 : (q == 2 ? x2 : x3));
+      else if (q < 0) {
+        const double* A = M + (size_t)blkoff(kb, r >> 2, nblk) * kTS + (r & 3);  // column r&3 of L(kb, r>>2)
+        xr[s] -= A[0] * x0 + A[4] * x1 + A[8] * x2 + A[12] * x3;
+      }
+    }
+  }
+  if (gtid < n4) x[gtid] = xr[0];
+  if (gtid + GT < n4) x[gtid + GT] = xr[1];
+  G.sync();
+}
+
+// y = H x for symmetric H in BC4 layout (diagonal tiles hold both triangles), one row per
+// thread (two passes when n4 > GT).  The whole group calls it; ends with a group barrier.
 template <int W>
 __device__ void symv_bc4(const Group<W>& G, const double* H, int n4, int nblk, const double* x, double* y) {
   constexpr int GT = Group<W>::GT;
-  const int gtid = G.gtid;
-  int tpr = 1;
-  while (tpr * 2 * n4 <= GT && tpr < 8) tpr *= 2;
-  const int rpp = GT / tpr, sub = gtid % tpr;
-  for (int base = 0; base < n4; base += rpp) {
-    const int row = base + gtid / tpr;
-    double s = 0.0;
-    if (row < n4) {
-      const int bi = row >> 2, ri = row & 3;
-      for (int bj = sub; bj < nblk; bj += tpr) {
-        if (bj <= bi) {
-          const double* A = H + ((size_t)blkoff(bi, bj, nblk) << 4) + 4 * ri;
-          s += A[0] * x[4 * bj] + A[1] * x[4 * bj + 1] + A[2] * x[4 * bj + 2] + A[3] * x[4 * bj + 3];
-        } else {
-          const double* A = H + ((size_t)blkoff(bj, bi, nblk) << 4) + ri;
-          s += A[0] * x[4 * bj] + A[4] * x[4 * bj + 1] + A[8] * x[4 * bj + 2] + A[12] * x[4 * bj + 3];
-        }
-      }
+  for (int row = G.gtid; row < n4; row += GT) {
+    const int bi = row >> 2, ri = row & 3;
+    double s0 = 0.0, s1 = 0.0;
+    // tiles (bi, bj), bj <= bi : row ri
+    for (int bj = 0; bj <= bi; ++bj) {
+      const double2* A2 = reinterpret_cast<const double2*>(H + (size_t)blkoff(bi, bj, nblk) * kTS + (ri << 2));
+      const double2* x2 = reinterpret_cast<const double2*>(x + (bj << 2));
+      const double2 u = A2[0], v = A2[1], xa = x2[0], xb = x2[1];
+      s0 += u.x * xa.x + u.y * xa.y;
+      s1 += v.x * xb.x + v.y * xb.y;
     }
-    for (int o = tpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (row < n4 && sub == 0) y[row] = s;
+    // tiles (bj, bi), bj > bi : column ri; consecutive in storage
+    const double* A = H + (size_t)(blkoff(bi, bi, nblk) + 1) * kTS + ri;
+    for (int bj = bi + 1; bj < nblk; ++bj, A += kTS) {
+      const double2* x2 = reinterpret_cast<const double2*>(x + (bj << 2));
+      const double2 xa = x2[0], xb = x2[1];
+      s0 += A[0] * xa.x + A[4] * xa.y;
+      s1 += A[8] * xb.x + A[12] * xb.y;
+    }
+    y[row] = s0 + s1;
   }
   G.sync();
 }
 
-// Copy a BC4 matrix (global scratch -> shared), 16 bytes per access.
+// Copy a BC4 matrix, 16 bytes per access (global scratch <-> shared).
 template <int W>
 __device__ __forceinline__ void copy_mat(const Group<W>& G, double* dst, const double* src, int ndoubles) {
   const double2* s2 = reinterpret_cast<const double2*>(src);
   double2* d2 = reinterpret_cast<double2*>(dst);
   for (int t = G.gtid; t < (ndoubles >> 1); t += Group<W>::GT) d2[t] = __ldcg(s2 + t);
+}
+template <int W>
+__device__ __forceinline__ void store_mat(const Group<W>& G, double* dst, const double* src, int ndoubles) {
+  const double2* s2 = reinterpret_cast<const double2*>(src);
+  double2* d2 = reinterpret_cast<double2*>(dst);
+  for (int t = G.gtid; t < (ndoubles >> 1); t += Group<W>::GT) __stcg(d2 + t, s2[t]);
 }
 
 // ------------------------------------------------------------------ friction pyramid rows
@@ -483,34 +590,38 @@ __device__ __noinline__ bool block_multipliers(int k, const double (*Nrm)[3], co
 }
 
 // ------------------------------------------------------------------ shared-memory plan (per group)
+// Aliases (lifetimes do not overlap): eq/qz (build only) live in tv..up; the lever arms
+// (build only) in du; the desired fz (build + start point) in rhs; the polish's null-space
+// bases Zt in isl..isu (recomputed every IPM iteration).
 struct SmemPlan {
   // offsets in doubles from the start of the group's slab
-  int eq, qz, ce, fzref, arm, g, u, rd, rhs, du, tv, up;
-  int sl, su, zl, zu, cdu, dzl, dzu, Zt, red, ints, Mm;
+  int ce, g, u, rd, rhs, du, tv, up;
+  int sl, zl, zu, isl, isu, cdu, dzl, dzu, red, exch, ints, Mm;
   int total;  // doubles, multiple of 16
 };
-__host__ __device__ inline SmemPlan make_plan(int N, int L, int nbmax, int n4max, int m_in_smem) {
+__host__ __device__ inline SmemPlan make_plan(int N, int L, int W, int nbmax, int n4max, int m_in_smem) {
   SmemPlan p;
   const int mmax = 5 * nbmax;
   int o = 0;
   auto take = [&](int cnt) { int r = o; o += (cnt + 1) & ~1; return r; };
-  p.eq = take(9 * N); p.qz = take(N);
-  p.ce = take(nbmax); p.fzref = take(nbmax); p.arm = take(3 * nbmax);
+  p.ce = take(nbmax);
   p.g = take(n4max); p.u = take(n4max); p.rd = take(n4max); p.rhs = take(n4max); p.du = take(n4max);
-  p.tv = take(n4max); p.up = take(n4max);
-  p.sl = take(mmax); p.su = take(mmax); p.zl = take(mmax); p.zu = take(mmax);
+  const int nv = (2 * n4max >= 10 * N + 2) ? n4max : (10 * N + 2 + 1) / 2;  // tv+up also host eq[9N], qz[N]
+  p.tv = take(nv); p.up = take(nv);
+  p.sl = take(mmax); p.zl = take(mmax); p.zu = take(mmax);
+  p.isl = take(mmax); p.isu = take(mmax);
   p.cdu = take(mmax); p.dzl = take(mmax); p.dzu = take(mmax);
-  p.Zt = take(9 * nbmax);
-  p.red = take(24);
+  p.red = take(W > 1 ? 3 * W : 2);
+  p.exch = take(8);
   // ints: blk_j, blk_i, rk, off [nbmax each], blk_of [N*L], misc[8]; bytes: actl, actu [mmax each];
   // uint16 tile table [tiles]
   const int nints = 4 * nbmax + N * L + 8;
   const int nbytes = 2 * mmax + 2 + 2 * bc4_tiles(n4max);
   p.ints = take((nints * 4 + nbytes + 15) / 8);
-  o = (o + 15) & ~15;  // 128-byte align tiles
+  o = (o + 1) & ~1;  // 16-byte align tiles
   p.Mm = o;
   if (m_in_smem) o += bc4_doubles(n4max);
-  p.total = (o + 15) & ~15;
+  p.total = (o + 1) & ~1;
   return p;
 }
 
@@ -544,34 +655,36 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
   const int ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = L * (4 * N + 3), nf = 3 * L * N;
   const int nbfull = L * N, mfull = 5 * nbfull;
   const int nbmax = args.nbmax, mmax = 5 * nbmax;
-  const SmemPlan P = make_plan(N, L, nbmax, args.n4max, args.m_in_smem);
+  const SmemPlan P = make_plan(N, L, W, nbmax, args.n4max, args.m_in_smem);
   Group<W> G;
   G.gtid = threadIdx.x % GT;
   G.gid = threadIdx.x / GT;
   const int gtid = G.gtid;
   double* base = smem + (size_t)G.gid * P.total;
   G.red = base + P.red;
-  double* s_eq = base + P.eq;
-  double* s_qz = base + P.qz;
+  double* s_exch = base + P.exch;
   double* s_ce = base + P.ce;
-  double* s_fz = base + P.fzref;
-  double* s_arm = base + P.arm;
   double* s_g = base + P.g;
   double* s_u = base + P.u;
   double* s_rd = base + P.rd;
-  double* s_f0 = s_rd;  // polish only; rd is recomputed after a rejected polish
+  double* s_f0 = s_rd;   // polish only; rd is recomputed after a rejected polish
   double* s_rhs = base + P.rhs;
+  double* s_fz = s_rhs;  // desired fz: build + start point only
   double* s_du = base + P.du;
+  double* s_arm = s_du;  // lever arms: build only
   double* s_tv = base + P.tv;
   double* s_up = base + P.up;
+  double* s_eq = s_tv;   // build only: 9N weighted errors then N z-weights
+  double* s_qz = s_tv + 9 * N;
   double* s_sl = base + P.sl;
-  double* s_su = base + P.su;
   double* s_zl = base + P.zl;
   double* s_zu = base + P.zu;
+  double* s_isl = base + P.isl;
+  double* s_isu = base + P.isu;
+  double* s_Zt = s_isl;  // polish only: 9 nb doubles <= isl + isu
   double* s_cdu = base + P.cdu;
   double* s_dzl = base + P.dzl;
   double* s_dzu = base + P.dzu;
-  double* s_Zt = base + P.Zt;
   int* s_blk_j = reinterpret_cast<int*>(base + P.ints);
   int* s_blk_i = s_blk_j + nbmax;
   int* s_rk = s_blk_i + nbmax;
@@ -654,6 +767,7 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
     const int nb = s_misc[0];
     const int n = 3 * nb, nblk = (n + 3) >> 2, n4 = nblk << 2, m = 5 * nb;
     const int ntiles = (nblk * (nblk + 1)) >> 1;
+    const int matd = ntiles * kTS;
     const bool invalid = s_misc[1] != 0;
 
     if (MODE == 0 && (!finite || invalid)) {
@@ -678,12 +792,13 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
       const int o = blkoff(bj, bj, nblk);
       for (int bi = bj; bi < nblk; ++bi) s_tb[o + bi - bj] = (uint16_t)(bi | (bj << 8));
     }
-    // ---- H = 2 (Bqp' L Bqp + K) on the free variables, one thread per block pair (b >= b2).
+    // ---- H = 2 (Bqp' L Bqp + K) on the free variables, one thread per block pair (b >= b2),
+    // assembled on chip (in the factor's buffer) and then streamed to the L2-resident copy.
     // Column (j,i) of Bqp at row block k >= j is A_d^{k-j} B_j =
     //   [ dt^2 (k-j+zeta) (c/m) I ; dt (c/m) I ; dt c [r]x ]   (a2/a3; Euler zeta=0, ZOH 1/2)
+    double* Hb = args.m_in_smem ? Mm : Hm;
     {
-      const int mat = ntiles << 4;
-      for (int t = gtid; t < mat; t += GT) Hm[t] = 0.0;
+      for (int t = gtid; t < matd; t += GT) Hb[t] = 0.0;
       G.sync();
       const int npairs = (nb * (nb + 1)) >> 1;
       const double dt2 = dt * dt, dt4 = dt2 * dt2;
@@ -737,16 +852,16 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
             const int gi = 3 * b + aa, gj = 3 * b2 + bb;
             const double v = 2.0 * blk[aa][bb];
             if (b != b2) {
-              Hm[midx(gi, gj, nblk)] = v;                              // gi > gj always here
-              if ((gi >> 2) == (gj >> 2)) Hm[midx(gj, gi, nblk)] = v;  // same diagonal tile: mirror
+              Hb[midx(gi, gj, nblk)] = v;                              // gi > gj always here
+              if ((gi >> 2) == (gj >> 2)) Hb[midx(gj, gi, nblk)] = v;  // same diagonal tile: mirror
             } else if ((gi >> 2) >= (gj >> 2)) {
               // diagonal 3x3 block: all 9 (aa,bb) are visited, so both triangles of a
               // diagonal tile get written; a straddling entry lands in the lower tile only
-              Hm[midx(gi, gj, nblk)] = v;
+              Hb[midx(gi, gj, nblk)] = v;
             }
           }
       }
-      if (gtid < n4 - n) Hm[midx(n + gtid, n + gtid, nblk)] = 1.0;  // padding rows: identity
+      if (gtid < n4 - n) Hb[midx(n + gtid, n + gtid, nblk)] = 1.0;  // padding rows: identity
       // ---- g = 2 Bqp' L (Aqp x0 + dqp - Xref) - 2 W_f Uref, one thread per block (adjoint sum)
       for (int b = gtid; b < nb; b += GT) {
         const int j = s_blk_j[b], i = s_blk_i[b];
@@ -769,8 +884,8 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
         }
       }
       if (gtid < n4 - n) s_g[n + gtid] = 0.0;
-      __threadfence_block();
       G.sync();
+      if (args.m_in_smem) store_mat<W>(G, Hm, Mm, matd);
     }
 
     if (MODE == 1) {
@@ -783,7 +898,7 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
         const int ba = s_blk_of[(a / nu) * L + (a % nu) / 3], bc = s_blk_of[(c / nu) * L + (c % nu) / 3];
         double v;
         if (ba < 0 || bc < 0) v = (a == c) ? 1.0 : 0.0;
-        else v = __ldcg(Hm + sidx(3 * ba + a % 3, 3 * bc + c % 3, nblk));
+        else v = Hb[sidx(3 * ba + a % 3, 3 * bc + c % 3, nblk)];
         Ho[t] = v;
       }
       for (int t = gtid; t < p; t += GT) {
@@ -803,9 +918,11 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
       fz = fmin(fz, 0.5 * kFricUb * s_ce[b] / mub);
       s_u[3 * b] = 0.0; s_u[3 * b + 1] = 0.0; s_u[3 * b + 2] = fz;
     }
-    if (gtid < n4 - n) { s_u[n + gtid] = 0.0; s_rhs[n + gtid] = 0.0; s_du[n + gtid] = 0.0; s_rd[n + gtid] = 0.0; s_tv[n + gtid] = 0.0; s_up[n + gtid] = 0.0; }
-    copy_mat<W>(G, Mm, Hm, ntiles << 4);
+    if (gtid < n4 - n) s_u[n + gtid] = 0.0;
+    if (!args.m_in_smem) copy_mat<W>(G, Mm, Hm, matd);
     G.sync();
+    // (s_fz aliases s_rhs, s_arm aliases s_du, s_eq aliases s_tv/s_up: all dead from here on)
+    if (gtid < n4 - n) { s_rhs[n + gtid] = 0.0; s_du[n + gtid] = 0.0; s_rd[n + gtid] = 0.0; s_tv[n + gtid] = 0.0; s_up[n + gtid] = 0.0; }
     symv_bc4<W>(G, Mm, n4, nblk, s_u, s_rd);
     double gmax = 0.0, r0max = 0.0;
     for (int t = gtid; t < n; t += GT) { gmax = fmax(gmax, fabs(s_g[t])); r0max = fmax(r0max, fabs(s_rd[t] + s_g[t])); }
@@ -820,7 +937,7 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
       cmul5(mub, s_u + 3 * b, y);
       for (int q = 0; q < 5; ++q) {
         const double ub = q < 4 ? ubxy : ubz;
-        s_sl[5 * b + q] = y[q]; s_su[5 * b + q] = ub - y[q];
+        s_sl[5 * b + q] = y[q];
         s_zl[5 * b + q] = mu0 / y[q]; s_zu[5 * b + q] = mu0 / (ub - y[q]);
       }
     }
@@ -831,14 +948,17 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
     double us = 1.0;
     for (it = 0; it <= cfg.max_iter; ++it) {
       // ---- residuals (M holds a fresh copy of H here)
-      if (!m_is_h) { copy_mat<W>(G, Mm, Hm, ntiles << 4); G.sync(); m_is_h = true; }
+      if (!m_is_h) { copy_mat<W>(G, Mm, Hm, matd); G.sync(); m_is_h = true; }
       symv_bc4<W>(G, Mm, n4, nblk, s_u, s_rd);
       double rmax = 0.0, umax = 0.0, gap = 0.0;
       for (int b = gtid; b < nb; b += GT) {
+        const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
         double w[5], o[3];
         for (int q = 0; q < 5; ++q) {
-          w[q] = s_zl[5 * b + q] - s_zu[5 * b + q];
-          gap += s_sl[5 * b + q] * s_zl[5 * b + q] + s_su[5 * b + q] * s_zu[5 * b + q];
+          const int t = 5 * b + q;
+          const double sl = s_sl[t], su = (q < 4 ? ubxy : ubz) - sl;
+          w[q] = s_zl[t] - s_zu[t];
+          gap += sl * s_zl[t] + su * s_zu[t];
         }
         ctmul5(cfg.mu[s_blk_i[b]], w, o);
         for (int q = 0; q < 3; ++q) {
@@ -860,10 +980,15 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
       if (cfg.polish && ready && npolish < 3) {
         ++npolish;
         bool any_act = false;
-        for (int t = gtid; t < m; t += GT) {
-          const bool al = s_zl[t] * us > s_sl[t] * gs, au = s_zu[t] * us > s_su[t] * gs;
-          s_actl[t] = al; s_actu[t] = au;
-          any_act = any_act || al || au;
+        for (int b = gtid; b < nb; b += GT) {
+          const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
+          for (int q = 0; q < 5; ++q) {
+            const int t = 5 * b + q;
+            const double sl = s_sl[t], su = (q < 4 ? ubxy : ubz) - sl;
+            const bool al = s_zl[t] * us > sl * gs, au = s_zu[t] * us > su * gs;
+            s_actl[t] = al; s_actu[t] = au;
+            any_act = any_act || al || au;
+          }
         }
         bool none_active = G.all(!any_act);
         // ---- active-set polish with correction passes
@@ -875,7 +1000,7 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
             nr = n; nblk_r = nblk;
             for (int b = gtid; b < nb; b += GT) { s_rk[b] = 0; s_off[b] = 3 * b; }
             for (int t = gtid; t < n4; t += GT) { s_f0[t] = 0.0; s_tv[t] = t < n ? -s_g[t] : 0.0; }
-            if (!m_is_h) copy_mat<W>(G, Mm, Hm, ntiles << 4);
+            if (!m_is_h) copy_mat<W>(G, Mm, Hm, matd);
             G.sync();
           } else {
             bool ok_all = true;
@@ -902,7 +1027,7 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
               for (int b = 0; b < nb; ++b) { s_off[b] = o; o += 3 - s_rk[b]; }
               s_misc[3] = o;
             }
-            if (!m_is_h) copy_mat<W>(G, Mm, Hm, ntiles << 4);
+            if (!m_is_h) copy_mat<W>(G, Mm, Hm, matd);
             G.sync();
             nr = s_misc[3];
             nblk_r = (nr + 3) >> 2;
@@ -932,20 +1057,20 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
               const int b2 = idx - ((a * (a + 1)) >> 1), b = a;
               const int d1 = 3 - s_rk[b], d2 = 3 - s_rk[b2];
               if (d1 == 0 || d2 == 0) continue;
-              double Hb[3][3];
+              double Hb3[3][3];
               for (int aa = 0; aa < 3; ++aa)
-                for (int bb = 0; bb < 3; ++bb) Hb[aa][bb] = __ldcg(Hm + sidx(3 * b + aa, 3 * b2 + bb, nblk));
+                for (int bb = 0; bb < 3; ++bb) Hb3[aa][bb] = __ldcg(Hm + sidx(3 * b + aa, 3 * b2 + bb, nblk));
               for (int cc = 0; cc < d1; ++cc)
                 for (int c2 = 0; c2 < d2; ++c2) {
                   if (b == b2 && c2 > cc) continue;  // lower part of the diagonal block; mirrored below
                   const double* z = s_Zt + 9 * b + 3 * cc;
                   const double* z2 = s_Zt + 9 * b2 + 3 * c2;
-                  double s = 0.0;
+                  double sacc = 0.0;
                   for (int aa = 0; aa < 3; ++aa)
-                    for (int bb = 0; bb < 3; ++bb) s += z[aa] * Hb[aa][bb] * z2[bb];
+                    for (int bb = 0; bb < 3; ++bb) sacc += z[aa] * Hb3[aa][bb] * z2[bb];
                   const int gi = s_off[b] + cc, gj = s_off[b2] + c2;  // gi >= gj
-                  Mm[midx(gi, gj, nblk_r)] = s;
-                  if ((gi >> 2) == (gj >> 2)) Mm[midx(gj, gi, nblk_r)] = s;
+                  Mm[midx(gi, gj, nblk_r)] = sacc;
+                  if ((gi >> 2) == (gj >> 2)) Mm[midx(gj, gi, nblk_r)] = sacc;
                 }
             }
             G.sync();
@@ -960,8 +1085,8 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
           m_is_h = false;
           bool fact_ok = true;
           if (nr > 0) {
-            fact_ok = chol_bc4<W>(G, Mm, nblk_r, s_tb);
-            if (fact_ok) chol_solve_bc4<W>(G, Mm, nblk_r, s_tv, s_du);
+            fact_ok = chol_bc4<W>(G, Mm, nblk_r, s_tb, s_tv, s_exch);  // forward pass fused
+            if (fact_ok) chol_bwd_bc4<W>(G, Mm, nblk_r, s_tv, s_exch);
           }
           if (!none_active && nr > 0) {  // restore the tile table of the full system
             for (int bj = gtid; bj < nblk; bj += GT) {
@@ -983,7 +1108,7 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
             for (int q = 0; q < 3; ++q) s_up[3 * b + q] = f[q];
           }
           if (gtid < n4 - n) s_up[n + gtid] = 0.0;
-          copy_mat<W>(G, Mm, Hm, ntiles << 4);
+          copy_mat<W>(G, Mm, Hm, matd);
           m_is_h = true;
           G.sync();
           symv_bc4<W>(G, Mm, n4, nblk, s_up, s_rhs);
@@ -1006,7 +1131,7 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
                 idx[k++] = 5 + q;
               }
               okm = block_multipliers(k, Nrm, rb, 1e-9 * gs, lam) && okm;
-              for (int s = 0; s < k; ++s) { if (idx[s] < 5) ll[idx[s]] = lam[s]; else lu[idx[s] - 5] = lam[s]; }
+              for (int sI = 0; sI < k; ++sI) { if (idx[sI] < 5) ll[idx[sI]] = lam[sI]; else lu[idx[sI] - 5] = lam[sI]; }
             }
             cmul5(mub, s_up + 3 * b, y);
             for (int q = 0; q < 5; ++q) {
@@ -1028,21 +1153,14 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
         }
         if (accepted) {
           for (int t = gtid; t < n; t += GT) s_u[t] = s_up[t];
-          for (int b = gtid; b < nb; b += GT) {
-            const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
-            for (int q = 0; q < 5; ++q) {
-              const double ub = q < 4 ? ubxy : ubz;
-              s_sl[5 * b + q] = s_cdu[5 * b + q]; s_su[5 * b + q] = ub - s_cdu[5 * b + q];
-              s_zl[5 * b + q] = s_dzl[5 * b + q]; s_zu[5 * b + q] = s_dzu[5 * b + q];
-            }
-          }
+          for (int t = gtid; t < m; t += GT) { s_sl[t] = s_cdu[t]; s_zl[t] = s_dzl[t]; s_zu[t] = s_dzu[t]; }
           G.sync();
           status = CMPC_STATUS_OK;
           break;
         }
         G.sync();
         // polish not accepted: rd was used as f0 scratch -> recompute the residual
-        if (!m_is_h) { copy_mat<W>(G, Mm, Hm, ntiles << 4); G.sync(); m_is_h = true; }
+        if (!m_is_h) { copy_mat<W>(G, Mm, Hm, matd); G.sync(); m_is_h = true; }
         symv_bc4<W>(G, Mm, n4, nblk, s_u, s_rd);
         for (int b = gtid; b < nb; b += GT) {
           double w[5], o[3];
@@ -1056,10 +1174,19 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
       if (mu <= 1e-8 * cfg.tol * gs * us) break;  // far past convergence: stop before 0/0
       if (it == cfg.max_iter) break;
 
-      // ---- M = H + C' diag(zl/sl + zu/su) C  (only the 3x3 diagonal blocks change)
+      // ---- M = H + C' diag(zl/sl + zu/su) C  (only the 3x3 diagonal blocks change), and the
+      // affine (predictor) right-hand side  -rd + C'(rcl/sl - rcu/su)  with rc = -s z
       for (int b = gtid; b < nb; b += GT) {
-        double sg[5];
-        for (int q = 0; q < 5; ++q) sg[q] = s_zl[5 * b + q] / s_sl[5 * b + q] + s_zu[5 * b + q] / s_su[5 * b + q];
+        const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
+        double sg[5], tq[5], o[3];
+        for (int q = 0; q < 5; ++q) {
+          const int t = 5 * b + q;
+          const double sl = s_sl[t], su = (q < 4 ? ubxy : ubz) - sl;
+          const double isl = fast_rcp(sl), isu = fast_rcp(su);
+          s_isl[t] = isl; s_isu[t] = isu;
+          sg[q] = s_zl[t] * isl + s_zu[t] * isu;
+          tq[q] = s_zu[t] - s_zl[t];
+        }
         const double mb = cfg.mu[s_blk_i[b]], sx = sg[0] + sg[1], sy = sg[2] + sg[3];
         const int g0 = 3 * b, g1 = g0 + 1, g2 = g0 + 2;
         Mm[midx(g0, g0, nblk)] += sx;
@@ -1067,69 +1194,84 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
         Mm[midx(g2, g2, nblk)] += mb * mb * (sx + sy) + sg[4];
         Mm[midx(g2, g0, nblk)] += mb * (sg[1] - sg[0]);
         Mm[midx(g2, g1, nblk)] += mb * (sg[3] - sg[2]);
+        ctmul5(mb, tq, o);
+        for (int q = 0; q < 3; ++q) s_du[3 * b + q] = -s_rd[3 * b + q] + o[q];
       }
       m_is_h = false;
       G.sync();
-      if (!chol_bc4<W>(G, Mm, nblk, s_tb)) { numerical = true; break; }
+      // factor; the predictor's forward substitution is fused into the sweep
+      if (!chol_bc4<W>(G, Mm, nblk, s_tb, s_du, s_exch)) { numerical = true; break; }
 
-      double alpha = 1.0, sigma = 0.0;
+      double tmax = 0.0, sigma = 0.0;
       for (int phase = 0; phase < 2; ++phase) {
         // phase 0: affine predictor; phase 1: centred corrector (Mehrotra)
-        for (int b = gtid; b < nb; b += GT) {
-          double tq[5], o[3];
-          for (int q = 0; q < 5; ++q) {
-            const int t = 5 * b + q;
-            double rcl = -s_sl[t] * s_zl[t], rcu = -s_su[t] * s_zu[t];
-            if (phase) { rcl += sigma * mu - s_cdu[t] * s_dzl[t]; rcu += sigma * mu + s_cdu[t] * s_dzu[t]; }
-            tq[q] = rcl / s_sl[t] - rcu / s_su[t];
+        if (phase) {
+          for (int b = gtid; b < nb; b += GT) {
+            const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
+            double tq[5], o[3];
+            for (int q = 0; q < 5; ++q) {
+              const int t = 5 * b + q;
+              const double sl = s_sl[t], su = (q < 4 ? ubxy : ubz) - sl;
+              const double rcl = -sl * s_zl[t] + sigma * mu - s_cdu[t] * s_dzl[t];
+              const double rcu = -su * s_zu[t] + sigma * mu + s_cdu[t] * s_dzu[t];
+              tq[q] = rcl * s_isl[t] - rcu * s_isu[t];
+            }
+            ctmul5(cfg.mu[s_blk_i[b]], tq, o);
+            for (int q = 0; q < 3; ++q) s_du[3 * b + q] = -s_rd[3 * b + q] + o[q];
           }
-          ctmul5(cfg.mu[s_blk_i[b]], tq, o);
-          for (int q = 0; q < 3; ++q) s_du[3 * b + q] = -s_rd[3 * b + q] + o[q];
+          G.sync();
+          chol_fwd_bc4<W>(G, Mm, nblk, s_du, s_exch);
         }
-        G.sync();
-        chol_solve_bc4<W>(G, Mm, nblk, s_du, s_rhs);
-        double amin = 1.0, ga = 0.0;
+        chol_bwd_bc4<W>(G, Mm, nblk, s_du, s_exch);
+        // step to the boundary: alpha_max = 1 / max_i(-ds_i/s_i, -dz_i/z_i)
+        double tloc = 0.0;
         for (int b = gtid; b < nb; b += GT) {
+          const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
           double y[5];
           cmul5(cfg.mu[s_blk_i[b]], s_du + 3 * b, y);
           for (int q = 0; q < 5; ++q) {
             const int t = 5 * b + q;
-            double rcl = -s_sl[t] * s_zl[t], rcu = -s_su[t] * s_zu[t];
+            const double sl = s_sl[t], su = (q < 4 ? ubxy : ubz) - sl, zl = s_zl[t], zu = s_zu[t];
+            double rcl = -sl * zl, rcu = -su * zu;
             if (phase) { rcl += sigma * mu - s_cdu[t] * s_dzl[t]; rcu += sigma * mu + s_cdu[t] * s_dzu[t]; }
             const double cd = y[q];
-            const double dl = (rcl - s_zl[t] * cd) / s_sl[t];
-            const double du_ = (rcu + s_zu[t] * cd) / s_su[t];
-            if (cd < 0.0) amin = fmin(amin, -s_sl[t] / cd);
-            if (cd > 0.0) amin = fmin(amin, s_su[t] / cd);
-            if (dl < 0.0) amin = fmin(amin, -s_zl[t] / dl);
-            if (du_ < 0.0) amin = fmin(amin, -s_zu[t] / du_);
+            const double dl = (rcl - zl * cd) * s_isl[t];
+            const double du_ = (rcu + zu * cd) * s_isu[t];
+            tloc = fmax(tloc, fmax(-cd * s_isl[t], cd * s_isu[t]));
+            tloc = fmax(tloc, fmax(-dl * fast_rcp(zl), -du_ * fast_rcp(zu)));
             s_cdu[t] = cd; s_dzl[t] = dl; s_dzu[t] = du_;
           }
         }
-        alpha = -G.max(-amin);
+        tmax = G.max(tloc);
         if (!phase) {
-          G.sync();
-          for (int t = gtid; t < m; t += GT)
-            ga += (s_sl[t] + alpha * s_cdu[t]) * (s_zl[t] + alpha * s_dzl[t]) +
-                  (s_su[t] - alpha * s_cdu[t]) * (s_zu[t] + alpha * s_dzu[t]);
+          const double alpha = tmax > 1.0 ? 1.0 / tmax : 1.0;
+          double ga = 0.0;
+          for (int b = gtid; b < nb; b += GT) {
+            const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
+            for (int q = 0; q < 5; ++q) {
+              const int t = 5 * b + q;
+              const double sl = s_sl[t], su = (q < 4 ? ubxy : ubz) - sl;
+              ga += (sl + alpha * s_cdu[t]) * (s_zl[t] + alpha * s_dzl[t]) + (su - alpha * s_cdu[t]) * (s_zu[t] + alpha * s_dzu[t]);
+            }
+          }
           ga = G.sum(ga);
           const double ratio = ga / gap;
           sigma = ratio * ratio * ratio;
         }
       }
-      alpha = fmin(1.0, 0.995 * alpha);
+      const double alpha = fmin(1.0, 0.995 / fmax(tmax, 1e-300));
       bool fin = true;
-      for (int t = gtid; t < n; t += GT) { const double v = s_u[t] + alpha * s_du[t]; s_u[t] = v; fin = fin && isfinite(v); }
-      G.sync();
       for (int b = gtid; b < nb; b += GT) {
-        const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
         double y[5];
+        for (int q = 0; q < 3; ++q) {
+          const double v = s_u[3 * b + q] + alpha * s_du[3 * b + q];
+          s_u[3 * b + q] = v; fin = fin && isfinite(v);
+        }
         cmul5(cfg.mu[s_blk_i[b]], s_u + 3 * b, y);
         for (int q = 0; q < 5; ++q) {
           const int t = 5 * b + q;
-          const double ub = q < 4 ? ubxy : ubz;
           s_zl[t] += alpha * s_dzl[t]; s_zu[t] += alpha * s_dzu[t];
-          s_sl[t] = y[q]; s_su[t] = ub - y[q];
+          s_sl[t] = y[q];
         }
       }
       fin = G.all(fin);
@@ -1141,7 +1283,7 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
     // ---- outputs
     if (!numerical) {
       // scaled KKT residual (same definition as the oracle)
-      if (!m_is_h) { copy_mat<W>(G, Mm, Hm, ntiles << 4); G.sync(); m_is_h = true; }
+      if (!m_is_h) { copy_mat<W>(G, Mm, Hm, matd); G.sync(); m_is_h = true; }
       symv_bc4<W>(G, Mm, n4, nblk, s_u, s_rhs);
       double stat = 0.0, umax = 0.0, prim = 0.0, dual = 0.0, comp = 0.0;
       for (int b = gtid; b < nb; b += GT) {
@@ -1161,6 +1303,7 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
           prim = fmax(prim, fmax(-sl, -su));
           dual = fmax(dual, fmax(-zl, -zu));
           comp = fmax(comp, fmax(fabs(zl * sl), fabs(zu * su)));
+          s_sl[5 * b + q] = sl;
         }
       }
       stat = G.max(stat);
@@ -1171,9 +1314,14 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
       const double usf = 1.0 + umax;
       const double kkt = fmax(fmax(stat / gs, prim / usf), fmax(dual / gs, comp / (gs * usf)));
       if (status != CMPC_STATUS_OK) {
-        for (int t = gtid; t < m; t += GT) {
-          s_actl[t] = s_zl[t] * usf > s_sl[t] * gs;
-          s_actu[t] = s_zu[t] * usf > s_su[t] * gs;
+        for (int b = gtid; b < nb; b += GT) {
+          const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
+          for (int q = 0; q < 5; ++q) {
+            const int t = 5 * b + q;
+            const double sl = s_sl[t], su = (q < 4 ? ubxy : ubz) - sl;
+            s_actl[t] = s_zl[t] * usf > sl * gs;
+            s_actu[t] = s_zu[t] * usf > su * gs;
+          }
         }
       }
       G.sync();
