@@ -177,9 +177,9 @@ void fill_dev(cmpc_handle* h) {
   for (int i = 0; i < CMPC_NUM_WEIGHTS; ++i) d.w[i] = c.weights[i];
 }
 
-template <int W, int MODE>
+template <int W, int MODE, bool MS>
 cudaError_t launch_w(cmpc_handle* h, const cmpc_handle::ClassPlan& p, const SolveArgs& a) {
-  cmpc_solve_kernel<W, MODE><<<p.grid, 32 * W * p.groups, p.smem_bytes, h->stream>>>(h->dev, a);
+  cmpc_solve_kernel<W, MODE, MS><<<p.grid, 32 * W * p.groups, p.smem_bytes, h->stream>>>(h->dev, a);
   return cudaGetLastError();
 }
 
@@ -187,7 +187,10 @@ template <int MODE>
 int launch_class(cmpc_handle* h, const cmpc_handle::ClassPlan& p, SolveArgs a) {
   a.scratch = p.d_scratch; a.scratch_per_group = p.scratch_per_group;
   a.nbmax = p.nbmax; a.n4max = p.n4max; a.m_in_smem = p.m_in_smem; a.groups = p.groups;
-  cudaError_t e = p.W == 1 ? launch_w<1, MODE>(h, p, a) : p.W == 4 ? launch_w<4, MODE>(h, p, a) : launch_w<8, MODE>(h, p, a);
+  cudaError_t e;
+  if (MODE == 1 || !p.m_in_smem) e = launch_w<8, MODE, false>(h, p, a);
+  else if constexpr (MODE == 0) e = p.W == 1 ? launch_w<1, 0, true>(h, p, a) : p.W == 4 ? launch_w<4, 0, true>(h, p, a) : launch_w<8, 0, true>(h, p, a);
+  else e = cudaErrorInvalidValue;
   if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
   return CMPC_OK;
 }
@@ -236,9 +239,9 @@ int plan_class(cmpc_handle* h, cmpc_handle::ClassPlan& p, int W, int nbmax, int 
   return CMPC_OK;
 }
 
-template <int W, int MODE>
+template <int W, int MODE, bool MS>
 int set_smem_attr(cmpc_handle* h, size_t bytes) {
-  CUDA_TRY(h, cudaFuncSetAttribute(cmpc_solve_kernel<W, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  CUDA_TRY(h, cudaFuncSetAttribute(cmpc_solve_kernel<W, MODE, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return CMPC_OK;
 }
 
@@ -341,16 +344,18 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
     h->bounds = make_int4(b[0], b[1], b[2], b[3]);
     int rc = plan_class(h, h->exp_plan, 8, nbfull, 1);
     if (rc) return rc;
-    size_t s1 = 0, s4 = 0, s8 = 0;
+    size_t s1 = 0, s4 = 0, s8 = 0, s8g = 0;
     for (int c = 0; c < kNumClasses; ++c) {
       if (!h->cls[c].used) continue;
-      size_t& sref = h->cls[c].W == 1 ? s1 : h->cls[c].W == 4 ? s4 : s8;
+      if (!h->cls[c].m_in_smem) h->cls[c].W = 8;  // the global-factor variant exists for W = 8 only
+      size_t& sref = !h->cls[c].m_in_smem ? s8g : h->cls[c].W == 1 ? s1 : h->cls[c].W == 4 ? s4 : s8;
       sref = std::max(sref, h->cls[c].smem_bytes);
     }
-    if (s1 && (rc = set_smem_attr<1, 0>(h, s1))) return rc;
-    if (s4 && (rc = set_smem_attr<4, 0>(h, s4))) return rc;
-    if (s8 && (rc = set_smem_attr<8, 0>(h, s8))) return rc;
-    if ((rc = set_smem_attr<8, 1>(h, h->exp_plan.smem_bytes))) return rc;
+    if (s1 && (rc = set_smem_attr<1, 0, true>(h, s1))) return rc;
+    if (s4 && (rc = set_smem_attr<4, 0, true>(h, s4))) return rc;
+    if (s8 && (rc = set_smem_attr<8, 0, true>(h, s8))) return rc;
+    if (s8g && (rc = set_smem_attr<8, 0, false>(h, s8g))) return rc;
+    if ((rc = set_smem_attr<8, 1, false>(h, h->exp_plan.smem_bytes))) return rc;
   }
   h->max_batch = max_batch;
   h->ready = true;

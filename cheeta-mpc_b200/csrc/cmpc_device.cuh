@@ -189,6 +189,16 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return fma(r, e, r);
 }
 
+// 1/sqrt(x) to full double precision (not correctly rounded): MUFU seed + two Newton steps.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x * y, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  e = fma(-x * y, y, 1.0);
+  return fma(0.5 * y, e, y);
+}
+
 // Cholesky of a 4x4 SPD tile (row-major, lower part read) in "solve form" d[16]:
 //   strict lower  : L
 //   diagonal      : 1 / l_ii
@@ -200,19 +210,19 @@ __device__ __forceinline__ bool potrf4(const double* a, double* d) {
   const double a00 = a[0], a10 = a[4], a11 = a[5], a20 = a[8], a21 = a[9], a22 = a[10];
   const double a30 = a[12], a31 = a[13], a32 = a[14], a33 = a[15];
   bool ok = a00 > 0.0;
-  const double i0 = rsqrt(a00);
+  const double i0 = fast_rsqrt(a00);
   const double l10 = a10 * i0, l20 = a20 * i0, l30 = a30 * i0;
   const double d1 = a11 - l10 * l10;
   ok = ok && d1 > 0.0;
-  const double i1 = rsqrt(d1);
+  const double i1 = fast_rsqrt(d1);
   const double l21 = (a21 - l20 * l10) * i1, l31 = (a31 - l30 * l10) * i1;
   const double d2 = a22 - l20 * l20 - l21 * l21;
   ok = ok && d2 > 0.0;
-  const double i2 = rsqrt(d2);
+  const double i2 = fast_rsqrt(d2);
   const double l32 = (a32 - l30 * l20 - l31 * l21) * i2;
   const double d3 = a33 - l30 * l30 - l31 * l31 - l32 * l32;
   ok = ok && d3 > 0.0;
-  const double i3 = rsqrt(d3);
+  const double i3 = fast_rsqrt(d3);
   // inverse of the unit... of L: Linv(r,c), r > c
   const double v10 = -l10 * i0 * i1;
   const double v21 = -l21 * i1 * i2;
@@ -250,20 +260,13 @@ __device__ __forceinline__ void pivot4(const Group<W>& G, const double (&xr)[2],
                                        double& b0, double& b1, double& b2, double& b3) {
   constexpr int GT = Group<W>::GT;
   const int r0 = 4 * kb;
-  if constexpr (W == 1) {
-    const double v = (r0 >= GT) ? xr[1] : xr[0];
-    const int l0 = r0 & 31;
-    b0 = __shfl_sync(0xffffffffu, v, l0);
-    b1 = __shfl_sync(0xffffffffu, v, l0 + 1);
-    b2 = __shfl_sync(0xffffffffu, v, l0 + 2);
-    b3 = __shfl_sync(0xffffffffu, v, l0 + 3);
-  } else {
-    double* buf = exch + ((kb & 1) << 2);  // double-buffered: one barrier per step
-    const int q0 = G.gtid - (r0 % GT);
-    if (q0 >= 0 && q0 < 4) buf[q0] = (r0 >= GT) ? xr[1] : xr[0];
-    G.sync();
-    b0 = buf[0]; b1 = buf[1]; b2 = buf[2]; b3 = buf[3];
-  }
+  double* buf = exch + ((kb & 1) << 2);  // double-buffered: one barrier per step
+  const int q0 = G.gtid - (r0 % GT);
+  if (q0 >= 0 && q0 < 4) buf[q0] = (r0 >= GT) ? xr[1] : xr[0];
+  G.sync();
+  const double2* b2p = reinterpret_cast<const double2*>(buf);
+  const double2 u = b2p[0], v = b2p[1];
+  b0 = u.x; b1 = u.y; b2 = v.x; b3 = v.y;
 }
 
 // Tiled right-looking Cholesky in BC4 layout, in place; the whole group calls it.
@@ -272,7 +275,7 @@ __device__ __forceinline__ void pivot4(const Group<W>& G, const double (&xr)[2],
 // live in registers, the update of step kb rides along with the trailing update) and y
 // overwrites rhs.  Returns false (uniformly) on a non-positive pivot.
 template <int W>
-__device__ bool chol_bc4(const Group<W>& G, double* M, int nblk, const uint16_t* tb, double* rhs, double* exch) {
+__device__ __forceinline__ bool chol_bc4(const Group<W>& G, double* M, int nblk, const uint16_t* tb, double* rhs, double* exch) {
   constexpr int GT = Group<W>::GT;
   const int gtid = G.gtid;
   const int ntiles = (nblk * (nblk + 1)) >> 1;
@@ -287,11 +290,11 @@ __device__ bool chol_bc4(const Group<W>& G, double* M, int nblk, const uint16_t*
     const int col0 = blkoff(kb, kb, nblk);  // storage index of the diagonal tile of column kb
     const int nrows = nblk - kb;
     double d[16], a[16];
-    ld_tile(M + (size_t)col0 * kTS, a);     // broadcast loads: every lane factors the same tile
+    ld_tile(M + col0 * kTS, a);     // broadcast loads: every lane factors the same tile
     ok = potrf4(a, d) && ok;
     // TRSM: X = A L^-T, one panel tile per lane
     for (int t = 1 + gtid; t < nrows; t += GT) {
-      double* A = M + (size_t)(col0 + t) * kTS;
+      double* A = M + (col0 + t) * kTS;
       double x[16];
       ld_tile(A, a);
 #pragma unroll
@@ -306,7 +309,7 @@ __device__ bool chol_bc4(const Group<W>& G, double* M, int nblk, const uint16_t*
     }
     ok = G.all(ok);  // also the barrier between the panel and the trailing update
     if (!ok) return false;
-    if (gtid == 0) st_tile(M + (size_t)col0 * kTS, d);
+    if (gtid == 0) st_tile(M + col0 * kTS, d);
     if (rhs) {
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
@@ -314,7 +317,7 @@ __device__ bool chol_bc4(const Group<W>& G, double* M, int nblk, const uint16_t*
         const int q = r - 4 * kb;
         if (q >= 0 && q < 4) xr[s] = q == 0 ? y0 : (q == 1 ? y1 : (q == 2 ? y2 : y3));
         else if (q >= 4 && r < n4) {
-          const double2* A2 = reinterpret_cast<const double2*>(M + (size_t)(col0 + (r >> 2) - kb) * kTS + ((r & 3) << 2));
+          const double2* A2 = reinterpret_cast<const double2*>(M + (col0 + (r >> 2) - kb) * kTS + ((r & 3) << 2));
           const double2 u = A2[0], v = A2[1];
           xr[s] -= u.x * y0 + u.y * y1 + v.x * y2 + v.y * y3;
         }
@@ -325,9 +328,9 @@ __device__ bool chol_bc4(const Group<W>& G, double* M, int nblk, const uint16_t*
     for (int t = t0 + gtid; t < ntiles; t += GT) {
       const int bi = tb[t] & 0xff, bj = tb[t] >> 8;
       double li[16], lj[16], c[16];
-      double* C = M + (size_t)t * kTS;
-      ld_tile(M + (size_t)(col0 + bi - kb) * kTS, li);
-      ld_tile(M + (size_t)(col0 + bj - kb) * kTS, lj);
+      double* C = M + t * kTS;
+      ld_tile(M + (col0 + bi - kb) * kTS, li);
+      ld_tile(M + (col0 + bj - kb) * kTS, lj);
       ld_tile(C, c);
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr)
@@ -352,7 +355,7 @@ __device__ bool chol_bc4(const Group<W>& G, double* M, int nblk, const uint16_t*
 
 // Forward substitution y = L^-1 x (in place in shared memory), rows in registers.
 template <int W>
-__device__ void chol_fwd_bc4(const Group<W>& G, const double* M, int nblk, double* x, double* exch) {
+__device__ __forceinline__ void chol_fwd_bc4(const Group<W>& G, const double* M, int nblk, double* x, double* exch) {
   constexpr int GT = Group<W>::GT;
   const int gtid = G.gtid, n4 = nblk << 2;
   double xr[2] = {0.0, 0.0};
@@ -361,7 +364,7 @@ __device__ void chol_fwd_bc4(const Group<W>& G, const double* M, int nblk, doubl
   for (int kb = 0; kb < nblk; ++kb) {
     const int col0 = blkoff(kb, kb, nblk);
     double d[16], b0, b1, b2, b3, y0, y1, y2, y3;
-    ld_tile(M + (size_t)col0 * kTS, d);
+    ld_tile(M + col0 * kTS, d);
     pivot4<W>(G, xr, kb, exch, b0, b1, b2, b3);
     linv4(d, b0, b1, b2, b3, y0, y1, y2, y3);
 #pragma unroll
@@ -370,7 +373,7 @@ __device__ void chol_fwd_bc4(const Group<W>& G, const double* M, int nblk, doubl
       const int q = r - 4 * kb;
       if (q >= 0 && q < 4) xr[s] = q == 0 ? y0 : (q == 1 ? y1 : (q == 2 ? y2 : y3));
       else if (q >= 4 && r < n4) {
-        const double2* A2 = reinterpret_cast<const double2*>(M + (size_t)(col0 + (r >> 2) - kb) * kTS + ((r & 3) << 2));
+        const double2* A2 = reinterpret_cast<const double2*>(M + (col0 + (r >> 2) - kb) * kTS + ((r & 3) << 2));
         const double2 u = A2[0], v = A2[1];
         xr[s] -= u.x * y0 + u.y * y1 + v.x * y2 + v.y * y3;
       }
@@ -383,7 +386,7 @@ __device__ void chol_fwd_bc4(const Group<W>& G, const double* M, int nblk, doubl
 
 // Backward substitution x = L^-T y (in place in shared memory), rows in registers.
 template <int W>
-__device__ void chol_bwd_bc4(const Group<W>& G, const double* M, int nblk, double* x, double* exch) {
+__device__ __forceinline__ void chol_bwd_bc4(const Group<W>& G, const double* M, int nblk, double* x, double* exch) {
   constexpr int GT = Group<W>::GT;
   const int gtid = G.gtid, n4 = nblk << 2;
   double xr[2] = {0.0, 0.0};
@@ -391,7 +394,7 @@ __device__ void chol_bwd_bc4(const Group<W>& G, const double* M, int nblk, doubl
   if (gtid + GT < n4) xr[1] = x[gtid + GT];
   for (int kb = nblk - 1; kb >= 0; --kb) {
     double d[16], b0, b1, b2, b3, x0, x1, x2, x3;
-    ld_tile(M + (size_t)blkoff(kb, kb, nblk) * kTS, d);
+    ld_tile(M + blkoff(kb, kb, nblk) * kTS, d);
     pivot4<W>(G, xr, kb, exch, b0, b1, b2, b3);
     linvt4(d, b0, b1, b2, b3, x0, x1, x2, x3);
 #pragma unroll
@@ -400,7 +403,7 @@ __device__ void chol_bwd_bc4(const Group<W>& G, const double* M, int nblk, doubl
       const int q = r - 4 * kb;
       if (q >= 0 && q < 4) xr[s] = q == 0 ? x0 : (q == 1 ? x1 : (q == 2 ? x2 : x3));
       else if (q < 0) {
-        const double* A = M + (size_t)blkoff(kb, r >> 2, nblk) * kTS + (r & 3);  // column r&3 of L(kb, r>>2)
+        const double* A = M + blkoff(kb, r >> 2, nblk) * kTS + (r & 3);  // column r&3 of L(kb, r>>2)
         xr[s] -= A[0] * x0 + A[4] * x1 + A[8] * x2 + A[12] * x3;
       }
     }
@@ -413,21 +416,21 @@ __device__ void chol_bwd_bc4(const Group<W>& G, const double* M, int nblk, doubl
 // y = H x for symmetric H in BC4 layout (diagonal tiles hold both triangles), one row per
 // thread (two passes when n4 > GT).  The whole group calls it; ends with a group barrier.
 template <int W>
-__device__ void symv_bc4(const Group<W>& G, const double* H, int n4, int nblk, const double* x, double* y) {
+__device__ __forceinline__ void symv_bc4(const Group<W>& G, const double* H, int n4, int nblk, const double* x, double* y) {
   constexpr int GT = Group<W>::GT;
   for (int row = G.gtid; row < n4; row += GT) {
     const int bi = row >> 2, ri = row & 3;
     double s0 = 0.0, s1 = 0.0;
     // tiles (bi, bj), bj <= bi : row ri
     for (int bj = 0; bj <= bi; ++bj) {
-      const double2* A2 = reinterpret_cast<const double2*>(H + (size_t)blkoff(bi, bj, nblk) * kTS + (ri << 2));
+      const double2* A2 = reinterpret_cast<const double2*>(H + blkoff(bi, bj, nblk) * kTS + (ri << 2));
       const double2* x2 = reinterpret_cast<const double2*>(x + (bj << 2));
       const double2 u = A2[0], v = A2[1], xa = x2[0], xb = x2[1];
       s0 += u.x * xa.x + u.y * xa.y;
       s1 += v.x * xb.x + v.y * xb.y;
     }
     // tiles (bj, bi), bj > bi : column ri; consecutive in storage
-    const double* A = H + (size_t)(blkoff(bi, bi, nblk) + 1) * kTS + ri;
+    const double* A = H + (blkoff(bi, bi, nblk) + 1) * kTS + ri;
     for (int bj = bi + 1; bj < nblk; ++bj, A += kTS) {
       const double2* x2 = reinterpret_cast<const double2*>(x + (bj << 2));
       const double2 xa = x2[0], xb = x2[1];
@@ -647,7 +650,7 @@ __global__ void classify_kernel(const DevConfig cfg, int B, const double* des_in
 
 // ------------------------------------------------------------------ the fused kernel
 // MODE 0: solve.  MODE 1: build-export (H, g in the full 3LN layout to global memory).
-template <int W, int MODE>
+template <int W, int MODE, bool MS>
 __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, const SolveArgs args) {
   extern __shared__ __align__(128) double smem[];
   constexpr int GT = Group<W>::GT;
@@ -655,7 +658,7 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
   const int ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = L * (4 * N + 3), nf = 3 * L * N;
   const int nbfull = L * N, mfull = 5 * nbfull;
   const int nbmax = args.nbmax, mmax = 5 * nbmax;
-  const SmemPlan P = make_plan(N, L, W, nbmax, args.n4max, args.m_in_smem);
+  const SmemPlan P = make_plan(N, L, W, nbmax, args.n4max, MS ? 1 : 0);
   Group<W> G;
   G.gtid = threadIdx.x % GT;
   G.gid = threadIdx.x / GT;
@@ -696,7 +699,8 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
   uint16_t* s_tb = reinterpret_cast<uint16_t*>(s_actu + mmax);  // 2*mmax bytes past an int: even
   const int group_global = blockIdx.x * args.groups + G.gid;
   double* Hm = args.scratch + (size_t)group_global * args.scratch_per_group;
-  double* Mm = args.m_in_smem ? base + P.Mm : Hm + bc4_doubles(args.n4max);
+  double* Mm;
+  if constexpr (MS) Mm = base + P.Mm; else Mm = Hm + bc4_doubles(args.n4max);
 
   const double dt = cfg.dt, mass = cfg.mass;
   const double zeta = cfg.zoh ? 0.5 : 0.0;
@@ -796,7 +800,8 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
     // assembled on chip (in the factor's buffer) and then streamed to the L2-resident copy.
     // Column (j,i) of Bqp at row block k >= j is A_d^{k-j} B_j =
     //   [ dt^2 (k-j+zeta) (c/m) I ; dt (c/m) I ; dt c [r]x ]   (a2/a3; Euler zeta=0, ZOH 1/2)
-    double* Hb = args.m_in_smem ? Mm : Hm;
+    double* Hb;
+    if constexpr (MS) Hb = Mm; else Hb = Hm;
     {
       for (int t = gtid; t < matd; t += GT) Hb[t] = 0.0;
       G.sync();
@@ -885,7 +890,7 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
       }
       if (gtid < n4 - n) s_g[n + gtid] = 0.0;
       G.sync();
-      if (args.m_in_smem) store_mat<W>(G, Hm, Mm, matd);
+      if constexpr (MS) store_mat<W>(G, Hm, Mm, matd);
     }
 
     if (MODE == 1) {
@@ -919,7 +924,7 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
       s_u[3 * b] = 0.0; s_u[3 * b + 1] = 0.0; s_u[3 * b + 2] = fz;
     }
     if (gtid < n4 - n) s_u[n + gtid] = 0.0;
-    if (!args.m_in_smem) copy_mat<W>(G, Mm, Hm, matd);
+    if constexpr (!MS) copy_mat<W>(G, Mm, Hm, matd);
     G.sync();
     // (s_fz aliases s_rhs, s_arm aliases s_du, s_eq aliases s_tv/s_up: all dead from here on)
     if (gtid < n4 - n) { s_rhs[n + gtid] = 0.0; s_du[n + gtid] = 0.0; s_rd[n + gtid] = 0.0; s_tv[n + gtid] = 0.0; s_up[n + gtid] = 0.0; }
