@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -189,7 +190,7 @@ int launch_class(cmpc_handle* h, const cmpc_handle::ClassPlan& p, SolveArgs a) {
   a.nbmax = p.nbmax; a.n4max = p.n4max; a.m_in_smem = p.m_in_smem; a.groups = p.groups;
   cudaError_t e;
   if (MODE == 1 || !p.m_in_smem) e = launch_w<8, MODE, false>(h, p, a);
-  else if constexpr (MODE == 0) e = p.W == 1 ? launch_w<1, 0, true>(h, p, a) : p.W == 4 ? launch_w<4, 0, true>(h, p, a) : launch_w<8, 0, true>(h, p, a);
+  else if constexpr (MODE == 0) e = p.W == 1 ? launch_w<1, 0, true>(h, p, a) : p.W == 2 ? launch_w<2, 0, true>(h, p, a) : p.W == 4 ? launch_w<4, 0, true>(h, p, a) : launch_w<8, 0, true>(h, p, a);
   else e = cudaErrorInvalidValue;
   if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
   return CMPC_OK;
@@ -228,7 +229,7 @@ int plan_class(cmpc_handle* h, cmpc_handle::ClassPlan& p, int W, int nbmax, int 
   SmemPlan sp = make_plan(N, L, W, p.nbmax, p.n4max, 1);
   if (mode == 1 || (size_t)sp.total * 8 > kMaxSmem) { p.m_in_smem = 0; sp = make_plan(N, L, W, p.nbmax, p.n4max, 0); }
   if ((size_t)sp.total * 8 > kMaxSmem) return fail(h, CMPC_ERR_ARG, "horizon too large for the shared-memory vectors");
-  const int gmax = 256 / (32 * W);
+  const int gmax = (W == 2 ? 512 : 256) / (32 * W);
   p.groups = (int)std::min<size_t>((size_t)gmax, kMaxSmem / ((size_t)sp.total * 8));
   if (p.groups < 1) p.groups = 1;
   p.smem_bytes = (size_t)sp.total * 8 * p.groups;
@@ -329,7 +330,7 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
   {
     const int nbfull = L * N;
     const int cap[kNumClasses] = {20, 42, 64, nbfull};
-    const int Wc[kNumClasses] = {1, 4, 8, 8};
+    const int Wc[kNumClasses] = {getenv("CMPC_W0") ? atoi(getenv("CMPC_W0")) : 1, 4, 8, 8};
     int b[kNumClasses];
     int lower = 0;
     for (int c = 0; c < kNumClasses; ++c) {
@@ -344,14 +345,15 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
     h->bounds = make_int4(b[0], b[1], b[2], b[3]);
     int rc = plan_class(h, h->exp_plan, 8, nbfull, 1);
     if (rc) return rc;
-    size_t s1 = 0, s4 = 0, s8 = 0, s8g = 0;
+    size_t s1 = 0, s2 = 0, s4 = 0, s8 = 0, s8g = 0;
     for (int c = 0; c < kNumClasses; ++c) {
       if (!h->cls[c].used) continue;
       if (!h->cls[c].m_in_smem) h->cls[c].W = 8;  // the global-factor variant exists for W = 8 only
-      size_t& sref = !h->cls[c].m_in_smem ? s8g : h->cls[c].W == 1 ? s1 : h->cls[c].W == 4 ? s4 : s8;
+      size_t& sref = !h->cls[c].m_in_smem ? s8g : h->cls[c].W == 1 ? s1 : h->cls[c].W == 2 ? s2 : h->cls[c].W == 4 ? s4 : s8;
       sref = std::max(sref, h->cls[c].smem_bytes);
     }
     if (s1 && (rc = set_smem_attr<1, 0, true>(h, s1))) return rc;
+    if (s2 && (rc = set_smem_attr<2, 0, true>(h, s2))) return rc;
     if (s4 && (rc = set_smem_attr<4, 0, true>(h, s4))) return rc;
     if (s8 && (rc = set_smem_attr<8, 0, true>(h, s8))) return rc;
     if (s8g && (rc = set_smem_attr<8, 0, false>(h, s8g))) return rc;

@@ -290,22 +290,25 @@ __device__ __forceinline__ bool chol_bc4(const Group<W>& G, double* M, int nblk,
     const int col0 = blkoff(kb, kb, nblk);  // storage index of the diagonal tile of column kb
     const int nrows = nblk - kb;
     double d[16], a[16];
-    ld_tile(M + col0 * kTS, a);     // broadcast loads: every lane factors the same tile
+    ld_tile(M + col0 * kTS, a);             // broadcast loads: every lane factors the same tile
     ok = potrf4(a, d) && ok;
-    // TRSM: X = A L^-T, one panel tile per lane
-    for (int t = 1 + gtid; t < nrows; t += GT) {
-      double* A = M + (col0 + t) * kTS;
-      double x[16];
-      ld_tile(A, a);
-#pragma unroll
-      for (int r = 0; r < 4; ++r) linv4(d, a[4 * r], a[4 * r + 1], a[4 * r + 2], a[4 * r + 3], x[4 * r], x[4 * r + 1], x[4 * r + 2], x[4 * r + 3]);
-      st_tile(A, x);
+    // TRSM: X = A L^-T, one panel ROW per thread (rows 4(kb+1) .. n4-1)
+    for (int r = 4 * (kb + 1) + gtid; r < n4; r += GT) {
+      double2* A2 = reinterpret_cast<double2*>(M + (col0 + (r >> 2) - kb) * kTS + ((r & 3) << 2));
+      const double2 u = A2[0], v = A2[1];
+      double x0, x1, x2, x3;
+      linv4(d, u.x, u.y, v.x, v.y, x0, x1, x2, x3);
+      A2[0] = make_double2(x0, x1); A2[1] = make_double2(x2, x3);
     }
     double y0 = 0, y1 = 0, y2 = 0, y3 = 0;
     if (rhs) {
       double b0, b1, b2, b3;
       pivot4<W>(G, xr, kb, exch, b0, b1, b2, b3);
       linv4(d, b0, b1, b2, b3, y0, y1, y2, y3);
+      if (gtid == 0) {  // y of this step goes straight to the output vector (nobody reads rhs[] during the sweep)
+        double2* o2 = reinterpret_cast<double2*>(rhs + 4 * kb);
+        o2[0] = make_double2(y0, y1); o2[1] = make_double2(y2, y3);
+      }
     }
     ok = G.all(ok);  // also the barrier between the panel and the trailing update
     if (!ok) return false;
@@ -314,9 +317,7 @@ __device__ __forceinline__ bool chol_bc4(const Group<W>& G, double* M, int nblk,
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         const int r = gtid + s * GT;
-        const int q = r - 4 * kb;
-        if (q >= 0 && q < 4) xr[s] = q == 0 ? y0 : (q == 1 ? y1 : (q == 2 ? y2 : y3));
-        else if (q >= 4 && r < n4) {
+        if (r >= 4 * (kb + 1) && r < n4) {
           const double2* A2 = reinterpret_cast<const double2*>(M + (col0 + (r >> 2) - kb) * kTS + ((r & 3) << 2));
           const double2 u = A2[0], v = A2[1];
           xr[s] -= u.x * y0 + u.y * y1 + v.x * y2 + v.y * y3;
@@ -345,11 +346,6 @@ __device__ __forceinline__ bool chol_bc4(const Group<W>& G, double* M, int nblk,
     }
     G.sync();
   }
-  if (rhs) {
-    if (gtid < n4) rhs[gtid] = xr[0];
-    if (gtid + GT < n4) rhs[gtid + GT] = xr[1];
-    G.sync();
-  }
   return true;
 }
 
@@ -361,26 +357,27 @@ __device__ __forceinline__ void chol_fwd_bc4(const Group<W>& G, const double* M,
   double xr[2] = {0.0, 0.0};
   if (gtid < n4) xr[0] = x[gtid];
   if (gtid + GT < n4) xr[1] = x[gtid + GT];
+  G.sync();  // everybody holds its rows before step results overwrite x[]
   for (int kb = 0; kb < nblk; ++kb) {
     const int col0 = blkoff(kb, kb, nblk);
     double d[16], b0, b1, b2, b3, y0, y1, y2, y3;
     ld_tile(M + col0 * kTS, d);
     pivot4<W>(G, xr, kb, exch, b0, b1, b2, b3);
     linv4(d, b0, b1, b2, b3, y0, y1, y2, y3);
+    if (gtid == 0) {
+      double2* o2 = reinterpret_cast<double2*>(x + 4 * kb);
+      o2[0] = make_double2(y0, y1); o2[1] = make_double2(y2, y3);
+    }
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       const int r = gtid + s * GT;
-      const int q = r - 4 * kb;
-      if (q >= 0 && q < 4) xr[s] = q == 0 ? y0 : (q == 1 ? y1 : (q == 2 ? y2 : y3));
-      else if (q >= 4 && r < n4) {
+      if (r >= 4 * (kb + 1) && r < n4) {
         const double2* A2 = reinterpret_cast<const double2*>(M + (col0 + (r >> 2) - kb) * kTS + ((r & 3) << 2));
         const double2 u = A2[0], v = A2[1];
         xr[s] -= u.x * y0 + u.y * y1 + v.x * y2 + v.y * y3;
       }
     }
   }
-  if (gtid < n4) x[gtid] = xr[0];
-  if (gtid + GT < n4) x[gtid + GT] = xr[1];
   G.sync();
 }
 
@@ -392,24 +389,25 @@ __device__ __forceinline__ void chol_bwd_bc4(const Group<W>& G, const double* M,
   double xr[2] = {0.0, 0.0};
   if (gtid < n4) xr[0] = x[gtid];
   if (gtid + GT < n4) xr[1] = x[gtid + GT];
+  G.sync();
   for (int kb = nblk - 1; kb >= 0; --kb) {
     double d[16], b0, b1, b2, b3, x0, x1, x2, x3;
     ld_tile(M + blkoff(kb, kb, nblk) * kTS, d);
     pivot4<W>(G, xr, kb, exch, b0, b1, b2, b3);
     linvt4(d, b0, b1, b2, b3, x0, x1, x2, x3);
+    if (gtid == 0) {
+      double2* o2 = reinterpret_cast<double2*>(x + 4 * kb);
+      o2[0] = make_double2(x0, x1); o2[1] = make_double2(x2, x3);
+    }
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       const int r = gtid + s * GT;
-      const int q = r - 4 * kb;
-      if (q >= 0 && q < 4) xr[s] = q == 0 ? x0 : (q == 1 ? x1 : (q == 2 ? x2 : x3));
-      else if (q < 0) {
+      if (r < 4 * kb) {
         const double* A = M + blkoff(kb, r >> 2, nblk) * kTS + (r & 3);  // column r&3 of L(kb, r>>2)
         xr[s] -= A[0] * x0 + A[4] * x1 + A[8] * x2 + A[12] * x3;
       }
     }
   }
-  if (gtid < n4) x[gtid] = xr[0];
-  if (gtid + GT < n4) x[gtid + GT] = xr[1];
   G.sync();
 }
 
@@ -420,24 +418,24 @@ __device__ __forceinline__ void symv_bc4(const Group<W>& G, const double* H, int
   constexpr int GT = Group<W>::GT;
   for (int row = G.gtid; row < n4; row += GT) {
     const int bi = row >> 2, ri = row & 3;
-    double s0 = 0.0, s1 = 0.0;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     // tiles (bi, bj), bj <= bi : row ri
     for (int bj = 0; bj <= bi; ++bj) {
       const double2* A2 = reinterpret_cast<const double2*>(H + blkoff(bi, bj, nblk) * kTS + (ri << 2));
       const double2* x2 = reinterpret_cast<const double2*>(x + (bj << 2));
       const double2 u = A2[0], v = A2[1], xa = x2[0], xb = x2[1];
-      s0 += u.x * xa.x + u.y * xa.y;
-      s1 += v.x * xb.x + v.y * xb.y;
+      s0 = fma(u.x, xa.x, s0); s1 = fma(u.y, xa.y, s1);
+      s2 = fma(v.x, xb.x, s2); s3 = fma(v.y, xb.y, s3);
     }
     // tiles (bj, bi), bj > bi : column ri; consecutive in storage
     const double* A = H + (blkoff(bi, bi, nblk) + 1) * kTS + ri;
     for (int bj = bi + 1; bj < nblk; ++bj, A += kTS) {
       const double2* x2 = reinterpret_cast<const double2*>(x + (bj << 2));
       const double2 xa = x2[0], xb = x2[1];
-      s0 += A[0] * xa.x + A[4] * xa.y;
-      s1 += A[8] * xb.x + A[12] * xb.y;
+      s0 = fma(A[0], xa.x, s0); s1 = fma(A[4], xa.y, s1);
+      s2 = fma(A[8], xb.x, s2); s3 = fma(A[12], xb.y, s3);
     }
-    y[row] = s0 + s1;
+    y[row] = (s0 + s1) + (s2 + s3);
   }
   G.sync();
 }
@@ -651,7 +649,7 @@ __global__ void classify_kernel(const DevConfig cfg, int B, const double* des_in
 // ------------------------------------------------------------------ the fused kernel
 // MODE 0: solve.  MODE 1: build-export (H, g in the full 3LN layout to global memory).
 template <int W, int MODE, bool MS>
-__global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, const SolveArgs args) {
+__global__ void __launch_bounds__(W == 2 ? 512 : 256) cmpc_solve_kernel(const DevConfig cfg, const SolveArgs args) {
   extern __shared__ __align__(128) double smem[];
   constexpr int GT = Group<W>::GT;
   const int N = cfg.N, L = cfg.L, nu = 3 * L;
@@ -954,7 +952,7 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
     for (it = 0; it <= cfg.max_iter; ++it) {
       // ---- residuals (M holds a fresh copy of H here)
       if (!m_is_h) { copy_mat<W>(G, Mm, Hm, matd); G.sync(); m_is_h = true; }
-      symv_bc4<W>(G, Mm, n4, nblk, s_u, s_rd);
+      if (it > 0) symv_bc4<W>(G, Mm, n4, nblk, s_u, s_rd);  // it == 0: rd still holds H u0 from the start point
       double rmax = 0.0, umax = 0.0, gap = 0.0;
       for (int b = gtid; b < nb; b += GT) {
         const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
@@ -1288,8 +1286,10 @@ __global__ void __launch_bounds__(256) cmpc_solve_kernel(const DevConfig cfg, co
     // ---- outputs
     if (!numerical) {
       // scaled KKT residual (same definition as the oracle)
-      if (!m_is_h) { copy_mat<W>(G, Mm, Hm, matd); G.sync(); m_is_h = true; }
-      symv_bc4<W>(G, Mm, n4, nblk, s_u, s_rhs);
+      if (status != CMPC_STATUS_OK) {  // an accepted polish left H u in s_rhs already
+        if (!m_is_h) { copy_mat<W>(G, Mm, Hm, matd); G.sync(); m_is_h = true; }
+        symv_bc4<W>(G, Mm, n4, nblk, s_u, s_rhs);
+      }
       double stat = 0.0, umax = 0.0, prim = 0.0, dual = 0.0, comp = 0.0;
       for (int b = gtid; b < nb; b += GT) {
         const double mub = cfg.mu[s_blk_i[b]];

@@ -10,9 +10,9 @@ def find(s):
     for i, l in enumerate(src):
         if s in l: return i + 1
     return 10**6
-marks = [('group prims/layout', 1), ('tile helpers+potrf4', find('4x4 tile kernels')), ('chol', find('__device__ bool chol_bc4')),
-         ('fwd solve', find('__device__ void chol_fwd_bc4')), ('bwd solve', find('__device__ void chol_bwd_bc4')),
-         ('symv', find('__device__ void symv_bc4')), ('copy H', find('void copy_mat')), ('pyramid+polish helpers', find('friction pyramid rows')),
+marks = [('group prims/layout', 1), ('tile helpers+potrf4', find('4x4 tile kernels')), ('chol', find('bool chol_bc4(')),
+         ('fwd solve', find('void chol_fwd_bc4(')), ('bwd solve', find('void chol_bwd_bc4(')),
+         ('symv', find('void symv_bc4(')), ('copy H', find('void copy_mat')), ('pyramid+polish helpers', find('friction pyramid rows')),
          ('prologue/inputs', find('cmpc_solve_kernel(const DevConfig')), ('build H,g', find('// lever arms r = des_foot_pos')),
          ('start point', find('// ---- strictly feasible start')), ('residual+conv', find('// ---- residuals (M holds')),
          ('polish', find('if (cfg.polish && ready && npolish < 3)')), ('M=H+D, pred rhs', find("// ---- M = H + C' diag")),
