@@ -1,0 +1,120 @@
+"""-m gpu: the C++ shim (reference class surface) and the closed-loop rollout (BASELINE config 5)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cpp_shim_reproduces_reference_driver(pkg, orc, wl):
+    """tests/cpp/centoid_mpc_test.cpp = CentoidMPCTest.cpp against cheeta-mpc_b200/include/CentroidalMPC.h."""
+    exe = os.path.join(ROOT, "cheeta-mpc_b200", "csrc", "centoid_mpc_test")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][0]
+    out = json.loads(line)
+    assert out["invalid_table_throws"] is True
+    cfg, st, ds, di = wl.fixture_f1()
+    ref = orc.solve_batch(pkg.make_config(cfg), st[None], ds[None], di[None])
+    f = np.array(out["forces"])
+    assert np.abs(f - ref["forces"][0]).max() <= 1e-6 * np.abs(ref["forces"][0]).max()
+    assert "finished test" in r.stdout
+
+
+def advance_reference(orc, ccfg, cfg, st, ds, di, forces):
+    """NumPy statement of the rollout tick: reference plant (oracle plant_step), table rotation,
+    reference shift."""
+    N, L = cfg["horizon"], cfg["num_legs"]
+    B = len(st)
+    st, ds, di = st.copy(), ds.copy(), di.copy()
+    for b in range(B):
+        D = di[b].reshape(L, 4 * N + 3)
+        f0 = forces[b].reshape(L, N, 3)[:, 0, :]
+        st[b, :9] = orc.plant_step(ccfg, st[b, :9], st[b, 9:].reshape(L, 3), D[:, 0].copy(), f0)
+        D[:, :N] = np.roll(D[:, :N], -1, axis=1)
+        feet = D[:, N:].reshape(L, N + 1, 3)
+        feet[:, :N] = feet[:, 1:].copy()
+        S = ds[b].reshape(3, N + 1, 3)
+        for k in range(3):
+            last, prev = S[k, N].copy(), S[k, N - 1].copy()
+            S[k, :N] = S[k, 1:].copy()
+            S[k, N] = last + (last - prev) if k == 0 else last
+    return st, ds, di
+
+
+def test_rollout_matches_tickwise_oracle(pkg, orc, wl):
+    cfg = wl.default_config(10)
+    B, ticks = 48, 12
+    st, ds, di = wl.make_batch(cfg, B, gaits=wl.GAITS)
+    m = pkg.CentroidalMPC.from_dict(cfg)
+    m.SetupMPC(B)
+    out = m.Rollout(st, ds, di, ticks)
+    rs, rds, rdi = st.copy(), ds.copy(), di.copy()
+    for t in range(ticks):
+        ref = orc.solve_batch(m.cfg, rs, rds, rdi, nthreads=8, want_lam=False)
+        assert (ref["status"] == 0).all()
+        f0 = ref["forces"].reshape(B, 4, 10, 3)[:, :, 0, :].reshape(B, 12)
+        assert np.abs(out["force_log"][t] - f0).max() <= 1e-6 * np.abs(f0).max(), t
+        rs, rds, rdi = advance_reference(orc, m.cfg, cfg, rs, rds, rdi, ref["forces"])
+    assert np.abs(out["state"] - rs).max() <= 1e-9
+    assert np.array_equal(out["des_inputs"], rdi)
+    assert np.abs(out["des_state"] - rds).max() <= 1e-12
+    assert (out["status_or"] == 1).all()          # only CMPC_STATUS_OK seen
+    assert out["stats"]["launches"] >= 3 * ticks
+    m.close()
+
+
+def test_solve_is_deterministic_and_batch_invariant(pkg, wl):
+    """Size-independent properties at BASELINE's full batch: identical results when the same
+    instance sits in a different batch position / batch size; run-to-run bit identical."""
+    cfg = wl.default_config(10)
+    B = 4096
+    st, ds, di = wl.make_batch(cfg, B)
+    m = pkg.CentroidalMPC.from_dict(cfg)
+    m.SetupMPC(B)
+    a = m.UpdateMPCBatch(st, ds, di, want_lam=False)
+    b = m.UpdateMPCBatch(st, ds, di, want_lam=False)
+    assert np.array_equal(a["forces"], b["forces"])
+    assert (a["status"] == 0).all() and a["kkt"].max() <= 1e-8
+    perm = np.random.default_rng(0).permutation(B)[:512]
+    c = m.UpdateMPCBatch(st[perm], ds[perm], di[perm], want_lam=False)
+    assert np.array_equal(c["forces"], a["forces"][perm])
+    # physics sanity on every instance: swing legs carry no force, stance fz inside the bounds
+    F = a["forces"].reshape(B, 4, 10, 3)
+    contact = di.reshape(B, 4, 43)[:, :, :10]
+    assert np.all(F[contact == 0] == 0)
+    fz = F[..., 2][contact > 0]
+    assert fz.min() > 0 and fz.max() <= 8 * 9.81 * 4
+    m.close()
+
+
+def test_weights_update_and_zoh_mode(pkg, orc, wl):
+    from conftest import hard_config
+    cfg = wl.default_config(10)
+    st, ds, di = wl.make_batch(cfg, 32, gaits=wl.GAITS)
+    m = pkg.CentroidalMPC.from_dict(cfg)
+    m.SetupMPC(32)
+    hard = hard_config(wl, 10, 0.8)
+    m.UpdateWeights(hard["weights"])                     # NonlinearMPC::UpdateWeights
+    out = m.UpdateMPCBatch(st, ds, di)
+    cfg2 = dict(cfg, weights=hard["weights"])
+    ref = orc.solve_batch(pkg.make_config(cfg2), st, ds, di)
+    assert np.abs(out["forces"] - ref["forces"]).max() <= 1e-6 * np.abs(ref["forces"]).max()
+    with pytest.raises(pkg.CmpcError):
+        m.UpdateWeights(hard["weights"][:10])
+    m.close()
+    cfgz = hard_config(wl, 10, 0.3, disc_mode=1)
+    stz, dsz, diz = wl.make_batch(cfgz, 32, gaits=wl.GAITS)
+    mz = pkg.CentroidalMPC.from_dict(cfgz)
+    mz.SetupMPC(32)
+    out = mz.UpdateMPCBatch(stz, dsz, diz)
+    ref = orc.solve_batch(mz.cfg, stz, dsz, diz)
+    assert (out["status"] == ref["status"]).all()
+    assert np.abs(out["forces"] - ref["forces"]).max() <= 1e-6 * np.abs(ref["forces"]).max()
+    assert np.array_equal(out["active"], ref["active"])
+    mz.close()
