@@ -184,6 +184,10 @@ def main():
     for _ in range(max(3, args.warmup)):
         step_device()
     torch.cuda.synchronize()
+    st0 = pkg.CmpcStats()
+    mpc.solve_device(B, d_st.data_ptr(), d_ds.data_ptr(), d_di.data_ptr(), d_forces.data_ptr(),
+                     d_status.data_ptr(), d_iters.data_ptr(), d_kkt.data_ptr(), stats=st0)
+    launches_per_step = int(st0.launches)   # classify + one solve kernel per size class
     status = d_status.cpu().numpy()
     iters = d_iters.cpu().numpy()
     kkt = d_kkt.cpu().numpy()
@@ -244,6 +248,13 @@ def main():
         except Exception:
             pass
         fp64_peak = mpc.measure_fp64_peak()
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if B == 4096 and args.horizon == 10 and gaits == ("trot",):
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        except Exception:
+            pass
         med_ms = float(np.median(step_ms))
         achieved = flops / (med_ms * 1e-3) / 1e12
         in_bytes = 8 * (mpc.n_state + mpc.n_des_state + mpc.n_des_inputs)
@@ -263,9 +274,9 @@ def main():
             "e2e": {"value": world * B * e2e_steps / e2e_s_max, "unit": UNIT,
                     "h2d_bytes_per_step": B * in_bytes, "d2h_bytes_per_step": B * (8 * mpc.n_forces + 4),
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s_max / e2e_steps},
-            "gpu_launches": args.steps,
+            "gpu_launches": args.steps * launches_per_step,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
                          "peak_source": "DFMA microbenchmark run by this bench (MEASURED_PEAKS.json has no FP64 entry)",
                          "flops_per_solve": flops / B, "n_free": n_free,
                          "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": peaks.get("hbm_gbs"),
