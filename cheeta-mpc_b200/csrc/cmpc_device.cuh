@@ -1262,7 +1262,9 @@ __global__ void __launch_bounds__(W == 2 ? 512 : 256) cmpc_solve_kernel(const De
           sigma = ratio * ratio * ratio;
         }
       }
-      const double alpha = fmin(1.0, 0.995 / fmax(tmax, 1e-300));
+      // fraction to the boundary tau -> 1 as the gap closes (superlinear tail)
+      const double tau = fmax(0.995, 1.0 - mu / (gs * us));
+      const double alpha = fmin(1.0, tau / fmax(tmax, 1e-300));
       bool fin = true;
       for (int b = gtid; b < nb; b += GT) {
         double y[5];
@@ -1318,15 +1320,16 @@ __global__ void __launch_bounds__(W == 2 ? 512 : 256) cmpc_solve_kernel(const De
       comp = G.max(comp);
       const double usf = 1.0 + umax;
       const double kkt = fmax(fmax(stat / gs, prim / usf), fmax(dual / gs, comp / (gs * usf)));
-      if (status != CMPC_STATUS_OK) {
-        for (int b = gtid; b < nb; b += GT) {
-          const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
-          for (int q = 0; q < 5; ++q) {
-            const int t = 5 * b + q;
-            const double sl = s_sl[t], su = (q < 4 ? ubxy : ubz) - sl;
-            s_actl[t] = s_zl[t] * usf > sl * gs;
-            s_actu[t] = s_zu[t] * usf > su * gs;
-          }
+      // reported active set. Polished: the rows with zero slack at the KKT point (primal
+      // definition, unique because the optimum is unique -- the polish's working set can omit
+      // redundant rows at the degenerate apex f = 0). Otherwise: the IPM guess.
+      for (int b = gtid; b < nb; b += GT) {
+        const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
+        for (int q = 0; q < 5; ++q) {
+          const int t = 5 * b + q;
+          const double sl = s_sl[t], su = (q < 4 ? ubxy : ubz) - sl;
+          if (status == CMPC_STATUS_OK) { s_actl[t] = sl <= 1e-9 * usf; s_actu[t] = su <= 1e-9 * usf; }
+          else { s_actl[t] = s_zl[t] * usf > sl * gs; s_actu[t] = s_zu[t] * usf > su * gs; }
         }
       }
       G.sync();

@@ -666,7 +666,9 @@ int cmpc_oracle_solve(const cmpc_config* c, const double* state, const double* d
         sigma = ratio * ratio * ratio;
       }
     }
-    alpha *= 0.995; if (alpha > 1) alpha = 1;
+    /* fraction to the boundary tau -> 1 as the gap closes (superlinear tail) */
+    { double tau = 1.0 - mu / (gs * us); if (tau < 0.995) tau = 0.995; alpha *= tau; }
+    if (alpha > 1) alpha = 1;
     for (int a = 0; a < n; ++a) u[a] += alpha * du[a];
     for (int t = 0; t < m; ++t) { zl[t] += alpha * dzl[t]; zu[t] += alpha * dzu[t]; }
     Cmul(P.mu, nb, u, sl);
@@ -677,9 +679,17 @@ int cmpc_oracle_solve(const cmpc_config* c, const double* state, const double* d
   else if (status != CMPC_STATUS_OK) status = ipm_ok ? CMPC_STATUS_OK_IPM : CMPC_STATUS_MAX_ITER;
   if (status <= CMPC_STATUS_MAX_ITER && !numerical) {
     kkt = kkt_scaled(&P, u, zl, zu);
-    if (status != CMPC_STATUS_OK) {
+    {
+      /* reported active set. Polished: the rows with zero slack at the KKT point (primal
+       * definition, unique because the optimum is unique -- the polish's working set can
+       * omit redundant rows at the degenerate apex f = 0). Otherwise: the IPM guess. */
       double us = 1 + maxabs(u, n);
-      for (int t = 0; t < m; ++t) { actl[t] = zl[t] * us > sl[t] * gs; actu[t] = zu[t] * us > su[t] * gs; }
+      Cmul(P.mu, nb, u, sl);
+      for (int t = 0; t < m; ++t) {
+        su[t] = P.ub[t] - sl[t];
+        if (status == CMPC_STATUS_OK) { actl[t] = sl[t] <= 1e-9 * us; actu[t] = su[t] <= 1e-9 * us; }
+        else { actl[t] = zl[t] * us > sl[t] * gs; actu[t] = zu[t] * us > su[t] * gs; }
+      }
     }
     for (int b = 0; b < nb; ++b) {
       int j = P.blk_j[b], i = P.blk_i[b];
