@@ -27,7 +27,7 @@ struct cmpc_handle {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // device buffers
   double *d_state = nullptr, *d_ds = nullptr, *d_di = nullptr, *d_forces = nullptr, *d_kkt = nullptr,
-         *d_lam = nullptr, *d_flog = nullptr;
+         *d_lam = nullptr, *d_flog = nullptr, *d_hip = nullptr;
   int32_t *d_status = nullptr, *d_iters = nullptr, *d_iters_sum = nullptr, *d_status_or = nullptr;
   uint16_t* d_active = nullptr;
   void* d_stats = nullptr;
@@ -69,13 +69,26 @@ __global__ void stats_kernel(const int32_t* status, const int32_t* iters, const 
   }
 }
 
-// Closed loop, one tick (BASELINE config 5): plant = the reference's nonlinear Euler step
-// (CentroidalMPC.cpp:85-92) with the TRUE lever arm foot - com and the first-step forces;
-// contact table rotated by one step (period N); reference trajectory and desired feet
-// shifted by one node (last node extrapolated at constant velocity / held).
+// Closed loop (BASELINE config 5).  rollout_init captures the hip offsets foot_i - com at t = 0.
+__global__ void rollout_init_kernel(const DevConfig cfg, int B, const double* state, double* hip) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int L = cfg.L, ns = 9 + 3 * L;
+  const double* x = state + (size_t)b * ns;
+  for (int i = 0; i < L; ++i)
+    for (int q = 0; q < 3; ++q) hip[((size_t)b * L + i) * 3 + q] = x[9 + 3 * i + q] - (q < 2 ? x[q] : 0.0);
+}
+
+// One tick: (1) plant = the reference's nonlinear Euler step (CentroidalMPC.cpp:85-92) with the
+// TRUE lever arm foot - com and the first-step forces; (2) contact table rotated by one step
+// (period N); (3) a leg that is in swing at the new step 0 has its foot carried under its hip
+// (com_xy + hip offset), a stance foot stays where it is; (4) the references are regenerated
+// from the new state: des_com_pos_k = (c_xy + k dt vd_xy, z_d) with vd, z_d, L_d held from the
+// inputs; des_foot_pos_i[:,k] = current foot while leg i stays in stance from step 0 through
+// min(k, N-1), else the hip point of the reference at node k.
 __global__ void advance_kernel(const DevConfig cfg, int B, double* state, double* des_state, double* des_inputs,
-                               const double* forces, const int32_t* status, double* flog, int32_t* iters_sum,
-                               const int32_t* iters, int32_t* status_or) {
+                               const double* hip, const double* forces, const int32_t* status, double* flog,
+                               int32_t* iters_sum, const int32_t* iters, int32_t* status_or) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int N = cfg.N, L = cfg.L;
@@ -102,24 +115,30 @@ __global__ void advance_kernel(const DevConfig cfg, int B, double* state, double
     xn[6 + q] = x[6 + q] + ld[q] * cfg.dt;
   }
   for (int q = 0; q < 9; ++q) x[q] = xn[q];
-  // rotate the contact table, shift desired feet
+  // reference, re-anchored at the new state
+  const double vd0 = ds[3 * (N + 1)], vd1 = ds[3 * (N + 1) + 1], vd2 = ds[3 * (N + 1) + 2];
+  const double zd = ds[2];
+  const double ad0 = ds[6 * (N + 1)], ad1 = ds[6 * (N + 1) + 1], ad2 = ds[6 * (N + 1) + 2];
+  for (int k = 0; k <= N; ++k) {
+    ds[3 * k] = x[0] + k * cfg.dt * vd0; ds[3 * k + 1] = x[1] + k * cfg.dt * vd1; ds[3 * k + 2] = zd;
+    ds[3 * (N + 1) + 3 * k] = vd0; ds[3 * (N + 1) + 3 * k + 1] = vd1; ds[3 * (N + 1) + 3 * k + 2] = vd2;
+    ds[6 * (N + 1) + 3 * k] = ad0; ds[6 * (N + 1) + 3 * k + 1] = ad1; ds[6 * (N + 1) + 3 * k + 2] = ad2;
+  }
   for (int i = 0; i < L; ++i) {
     double* blk = di + i * (4 * N + 3);
     const double c0 = blk[0];
     for (int j = 0; j + 1 < N; ++j) blk[j] = blk[j + 1];
     blk[N - 1] = c0;
+    const double* hp = hip + ((size_t)b * L + i) * 3;
+    if (!(blk[0] > 0.0)) { x[9 + 3 * i] = x[0] + hp[0]; x[9 + 3 * i + 1] = x[1] + hp[1]; x[9 + 3 * i + 2] = hp[2]; }
     double* fp = blk + N;
-    for (int k = 0; k < N; ++k)
-      for (int q = 0; q < 3; ++q) fp[3 * k + q] = fp[3 * (k + 1) + q];
-  }
-  // shift the reference: pos extrapolated, vel / angular momentum held
-  for (int blkid = 0; blkid < 3; ++blkid) {
-    double* t = ds + blkid * 3 * (N + 1);
-    double last[3], prev[3];
-    for (int q = 0; q < 3; ++q) { last[q] = t[3 * N + q]; prev[q] = t[3 * (N - 1) + q]; }
-    for (int k = 0; k < N; ++k)
-      for (int q = 0; q < 3; ++q) t[3 * k + q] = t[3 * (k + 1) + q];
-    for (int q = 0; q < 3; ++q) t[3 * N + q] = blkid == 0 ? last[q] + (last[q] - prev[q]) : last[q];
+    bool planted = true;  // in stance continuously since step 0
+    for (int k = 0; k <= N; ++k) {
+      const int j = k < N ? k : N - 1;
+      planted = planted && blk[j] > 0.0;
+      if (planted) { for (int q = 0; q < 3; ++q) fp[3 * k + q] = x[9 + 3 * i + q]; }
+      else { fp[3 * k] = ds[3 * k] + hp[0]; fp[3 * k + 1] = ds[3 * k + 1] + hp[1]; fp[3 * k + 2] = hp[2]; }
+    }
   }
   if (iters_sum && iters) iters_sum[b] += iters[b];
   if (status_or) status_or[b] |= (1 << status[b]);
@@ -316,6 +335,7 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
   CUDA_TRY(h, cudaMalloc(&h->d_forces, B * nf * 8));
   CUDA_TRY(h, cudaMalloc(&h->d_kkt, B * 8));
   CUDA_TRY(h, cudaMalloc(&h->d_lam, B * 10 * L * N * 8));
+  CUDA_TRY(h, cudaMalloc(&h->d_hip, B * 3 * L * 8));
   CUDA_TRY(h, cudaMalloc(&h->d_status, B * 4));
   CUDA_TRY(h, cudaMalloc(&h->d_iters, B * 4));
   CUDA_TRY(h, cudaMalloc(&h->d_iters_sum, B * 4));
@@ -499,7 +519,6 @@ int cmpc_build_batch(cmpc_handle* h, int B, const double* state, const double* d
 
 int cmpc_rollout(cmpc_handle* h, int B, int ticks, int warm_start, double* state, double* des_state,
                  double* des_inputs, double* force_log, int32_t* iters_sum, int32_t* status_or, cmpc_stats* stats) {
-  (void)warm_start;
   if (!h || !h->ready) return fail(h, CMPC_ERR_STATE, "cmpc_rollout: call cmpc_setup first");
   if (B < 1 || B > h->max_batch || ticks < 1) return fail(h, CMPC_ERR_ARG, "cmpc_rollout: bad B or ticks");
   if (!state || !des_state || !des_inputs) return fail(h, CMPC_ERR_ARG, "null buffer");
@@ -517,6 +536,12 @@ int cmpc_rollout(cmpc_handle* h, int B, int ticks, int warm_start, double* state
   SolveArgs a = base_args(h, B);
   a.state = h->d_state; a.des_state = h->d_ds; a.des_inputs = h->d_di;
   a.forces = h->d_forces; a.status = h->d_status; a.iters = h->d_iters; a.kkt = h->d_kkt;
+  a.active = h->d_active;
+  if (warm_start) {  // previous tick's active set = the polish's first guess (tick 0: nothing active)
+    a.warm_active = h->d_active;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_active, 0, (size_t)B * L * N * 2, s));
+  }
+  rollout_init_kernel<<<(B + 127) / 128, 128, 0, s>>>(h->dev, B, h->d_state, h->d_hip);
   CUDA_TRY(h, cudaEventRecord(h->ev[0], s));
   int rc = CMPC_OK;
   int launches = 0;
@@ -525,7 +550,7 @@ int cmpc_rollout(cmpc_handle* h, int B, int ticks, int warm_start, double* state
     if (rc < 0) break;
     launches += rc + 1;
     rc = CMPC_OK;
-    advance_kernel<<<(B + 127) / 128, 128, 0, s>>>(h->dev, B, h->d_state, h->d_ds, h->d_di, h->d_forces, h->d_status,
+    advance_kernel<<<(B + 127) / 128, 128, 0, s>>>(h->dev, B, h->d_state, h->d_ds, h->d_di, h->d_hip, h->d_forces, h->d_status,
                                                     d_flog ? d_flog + (size_t)t * B * 3 * L : nullptr, h->d_iters_sum,
                                                     h->d_iters, h->d_status_or);
   }
@@ -580,7 +605,7 @@ void cmpc_destroy(cmpc_handle* h) {
   if (!h) return;
   if (h->device >= 0) cudaSetDevice(h->device);
   cudaFree(h->d_state); cudaFree(h->d_ds); cudaFree(h->d_di); cudaFree(h->d_forces); cudaFree(h->d_kkt);
-  cudaFree(h->d_lam); cudaFree(h->d_counts); cudaFree(h->d_perm); cudaFree(h->exp_plan.d_scratch);
+  cudaFree(h->d_lam); cudaFree(h->d_hip); cudaFree(h->d_counts); cudaFree(h->d_perm); cudaFree(h->exp_plan.d_scratch);
   for (auto& c : h->cls) cudaFree(c.d_scratch);
   cudaFree(h->d_status); cudaFree(h->d_iters);
   cudaFree(h->d_iters_sum); cudaFree(h->d_status_or); cudaFree(h->d_active); cudaFree(h->d_stats);

@@ -52,6 +52,7 @@ struct SolveArgs {
   double* kkt;
   double* lam;
   uint16_t* active;
+  const uint16_t* warm_active;  // optional: previous tick's active set (closed loop), tried first
   double* Hout;  // build-export mode only
   double* gout;
   double* scratch;           // global (L2-resident) scratch: H per group, and M when it does not fit on chip
@@ -947,7 +948,7 @@ __global__ void __launch_bounds__(W == 2 ? 512 : 256) cmpc_solve_kernel(const De
     G.sync();
 
     int status = CMPC_STATUS_MAX_ITER, it = 0, npolish = 0;
-    bool numerical = false, ipm_ok = false, m_is_h = true;
+    bool numerical = false, ipm_ok = false, m_is_h = true, warm_done = false;
     double us = 1.0;
     for (it = 0; it <= cfg.max_iter; ++it) {
       // ---- residuals (M holds a fresh copy of H here)
@@ -980,17 +981,36 @@ __global__ void __launch_bounds__(W == 2 ? 512 : 256) cmpc_solve_kernel(const De
       const bool strict = conv_mu && rmax <= cfg.tol * gs;
       const bool ready = conv_mu && rmax <= 1e4 * cfg.tol * gs;
       ipm_ok = conv_mu && rmax <= 10.0 * cfg.tol * gs;
-      if (cfg.polish && ready && npolish < 3) {
-        ++npolish;
+      // Warm start (closed loop): before the first factorisation, try the previous tick's
+      // active set, shifted by one step, as the polish's guess. The polish verifies the KKT
+      // conditions, so a wrong guess only costs its correction passes and the IPM runs cold.
+      const bool warm_now = cfg.polish && args.warm_active != nullptr && it == 0 && !warm_done;
+      if (cfg.polish && ((ready && npolish < 3) || warm_now)) {
         bool any_act = false;
-        for (int b = gtid; b < nb; b += GT) {
-          const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
-          for (int q = 0; q < 5; ++q) {
-            const int t = 5 * b + q;
-            const double sl = s_sl[t], su = (q < 4 ? ubxy : ubz) - sl;
-            const bool al = s_zl[t] * us > sl * gs, au = s_zu[t] * us > su * gs;
-            s_actl[t] = al; s_actu[t] = au;
-            any_act = any_act || al || au;
+        if (warm_now) {
+          warm_done = true;
+          const uint16_t* wa = args.warm_active + (size_t)inst * nbfull;
+          for (int b = gtid; b < nb; b += GT) {
+            const int j = s_blk_j[b], i = s_blk_i[b];
+            const int jj = j + 1 < N ? j + 1 : j;
+            const unsigned a = wa[jj * L + i];
+            for (int q = 0; q < 5; ++q) {
+              const bool al = !(a & 0x8000u) && ((a >> q) & 1u), au = !(a & 0x8000u) && ((a >> (5 + q)) & 1u);
+              s_actl[5 * b + q] = al; s_actu[5 * b + q] = au;
+              any_act = any_act || al || au;
+            }
+          }
+        } else {
+          ++npolish;
+          for (int b = gtid; b < nb; b += GT) {
+            const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
+            for (int q = 0; q < 5; ++q) {
+              const int t = 5 * b + q;
+              const double sl = s_sl[t], su = (q < 4 ? ubxy : ubz) - sl;
+              const bool al = s_zl[t] * us > sl * gs, au = s_zu[t] * us > su * gs;
+              s_actl[t] = al; s_actu[t] = au;
+              any_act = any_act || al || au;
+            }
           }
         }
         bool none_active = G.all(!any_act);

@@ -122,11 +122,17 @@ int cmpc_solve_batch_device(cmpc_handle* h, int B, const double* d_state,
 int cmpc_build_batch(cmpc_handle* h, int B, const double* state, const double* des_state,
                      const double* des_inputs, double* H, double* g, int32_t* status);
 
-/* Closed loop (BASELINE config 5): `ticks` MPC ticks on device; after each solve the
- * first-step forces drive the reference's nonlinear Euler plant (CentroidalMPC.cpp:85-92),
- * the contact table is rotated by one step (period = horizon) and the reference
- * trajectory is re-anchored at the new state.  state is updated in place (host buffers).
- * force_log (optional) [ticks][B][3L] first-step forces; iters_sum (optional) [B]. */
+/* Closed loop (BASELINE config 5): `ticks` MPC ticks on device. Per tick: solve; drive the
+ * reference's nonlinear Euler plant (CentroidalMPC.cpp:85-92, true lever arms foot - com) with
+ * the first-step forces; rotate the contact table by one step (period = horizon); carry the
+ * feet that are in swing under their hips (offsets captured at tick 0); regenerate the
+ * references from the new state (constant desired velocity / height / angular momentum taken
+ * from node 0 of the inputs).  warm_start != 0: each tick first tries the previous tick's
+ * active set (shifted by one step) in the active-set polish and only falls back to the cold
+ * interior-point iteration if that guess does not verify.  state / des_state / des_inputs are
+ * updated in place (host buffers).  force_log (optional) [ticks][B][3L] first-step forces;
+ * iters_sum (optional) [B] factorisations of H + C'SC summed over ticks; status_or (optional)
+ * [B] OR of (1 << status) over ticks. */
 int cmpc_rollout(cmpc_handle* h, int B, int ticks, int warm_start, double* state,
                  double* des_state, double* des_inputs, double* force_log,
                  int32_t* iters_sum, int32_t* status_or, cmpc_stats* stats);
