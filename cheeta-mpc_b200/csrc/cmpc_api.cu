@@ -24,6 +24,7 @@ struct cmpc_handle {
   bool ready = false;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  bool zero_copy = true;  // CMPC_NO_ZEROCOPY=1 forces the staged-copy path
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // device buffers
   double *d_state = nullptr, *d_ds = nullptr, *d_di = nullptr, *d_forces = nullptr, *d_kkt = nullptr,
@@ -159,6 +160,14 @@ __global__ void fp64_peak_kernel(double* out, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// device alias of a pinned (page-locked) host pointer, or nullptr for pageable / device memory
+void* mapped_device_pointer(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (at.type == cudaMemoryTypeHost && at.devicePointer) return at.devicePointer;
+  return nullptr;
+}
+
 int fail(cmpc_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg;
   return code;
@@ -219,7 +228,7 @@ int launch_class(cmpc_handle* h, const cmpc_handle::ClassPlan& p, SolveArgs a) {
 int launch_solve(cmpc_handle* h, SolveArgs a, int B) {
   if (cudaMemsetAsync(h->d_counts, 0, 2 * kNumClasses * sizeof(int32_t), h->stream) != cudaSuccess)
     return fail(h, CMPC_ERR_CUDA, "memset counts");
-  classify_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(h->dev, B, a.des_inputs, h->bounds, h->d_counts, h->d_perm);
+  classify_kernel<<<(B + 3) / 4, 128, 0, h->stream>>>(h->dev, B, a.des_inputs, h->bounds, h->d_counts, h->d_perm);
   int launches = 1;
   for (int c = 0; c < kNumClasses; ++c) {
     if (!h->cls[c].used) continue;
@@ -253,7 +262,7 @@ int plan_class(cmpc_handle* h, cmpc_handle::ClassPlan& p, int W, int nbmax, int 
   if (p.groups < 1) p.groups = 1;
   p.smem_bytes = (size_t)sp.total * 8 * p.groups;
   p.grid = h->num_sms;
-  p.scratch_per_group = (size_t)bc4_doubles(p.n4max) * (p.m_in_smem ? 1 : 2);
+  p.scratch_per_group = (size_t)mat_region_doubles(N, L, p.n4max) * (p.m_in_smem ? 1 : 2);
   CUDA_TRY(h, cudaMalloc(&p.d_scratch, p.scratch_per_group * 8 * (size_t)p.grid * p.groups));
   p.used = true;
   return CMPC_OK;
@@ -307,6 +316,7 @@ int cmpc_create(const cmpc_config* cfg, cmpc_handle** out) {
   if (!h) return CMPC_ERR_ARG;
   h->cfg = *cfg;
   fill_dev(h);
+  h->zero_copy = !(getenv("CMPC_NO_ZEROCOPY") && atoi(getenv("CMPC_NO_ZEROCOPY")) != 0);
   *out = h;
   return CMPC_OK;
 }
@@ -449,6 +459,42 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
   const int N = h->cfg.horizon, L = h->cfg.num_legs;
   const size_t ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = (size_t)L * (4 * N + 3), nf = (size_t)3 * L * N;
   cudaStream_t s = h->stream;
+  // Zero-copy path: when every buffer is pinned (page-locked, hence device-mapped under UVA) the
+  // kernels read the inputs and write the outputs in place over PCIe/C2C -- each byte crosses the
+  // bus once, overlapped with the other resident instances' compute, and no staging copy runs.
+  {
+    void* dp[9] = {nullptr};
+    const void* hp[9] = {state, des_state, des_inputs, forces, status, iters, kkt, lam, active};
+    bool all_mapped = h->zero_copy;
+    for (int q = 0; q < 9 && all_mapped; ++q) {
+      if (!hp[q]) continue;
+      dp[q] = mapped_device_pointer(hp[q]);
+      all_mapped = dp[q] != nullptr;
+    }
+    if (all_mapped) {
+      SolveArgs a = base_args(h, B);
+      a.state = (const double*)dp[0]; a.des_state = (const double*)dp[1]; a.des_inputs = (const double*)dp[2];
+      a.forces = (double*)dp[3]; a.status = (int32_t*)dp[4];
+      a.iters = iters ? (int32_t*)dp[5] : (stats ? h->d_iters : nullptr);
+      a.kkt = kkt ? (double*)dp[6] : (stats ? h->d_kkt : nullptr);
+      a.lam = (double*)dp[7]; a.active = (uint16_t*)dp[8];
+      CUDA_TRY(h, cudaEventRecord(h->ev[0], s));
+      int rc = launch_solve(h, a, B);
+      if (rc < 0) return rc;
+      const int launches = rc;
+      CUDA_TRY(h, cudaEventRecord(h->ev[1], s));
+      CUDA_TRY(h, cudaStreamSynchronize(s));
+      if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        rc = collect_stats(h, B, a.status, a.iters, a.kkt, stats, launches);
+        if (rc) return rc;
+        float t1 = 0;
+        CUDA_TRY(h, cudaEventElapsedTime(&t1, h->ev[0], h->ev[1]));
+        stats->kernel_ms = t1;
+      }
+      return CMPC_OK;
+    }
+  }
   CUDA_TRY(h, cudaEventRecord(h->ev[0], s));
   CUDA_TRY(h, cudaMemcpyAsync(h->d_state, state, B * ns * 8, cudaMemcpyHostToDevice, s));
   CUDA_TRY(h, cudaMemcpyAsync(h->d_ds, des_state, B * nds * 8, cudaMemcpyHostToDevice, s));

@@ -86,6 +86,12 @@ __host__ __device__ inline int bc4_tiles(int n) {
   return (nblk * (nblk + 1)) >> 1;
 }
 __host__ __device__ inline int bc4_doubles(int n) { return bc4_tiles(n) * 18; }
+// size of a matrix buffer: it also stages the raw inputs of an instance before the build
+__host__ __device__ inline int mat_region_doubles(int N, int L, int n4max) {
+  const int nin = (9 + 3 * L) + 9 * (N + 1) + L * (4 * N + 3);
+  const int m = bc4_doubles(n4max);
+  return ((m > nin ? m : nin) + 1) & ~1;
+}
 
 // ------------------------------------------------------------------ group primitives
 template <int W>
@@ -622,29 +628,38 @@ __host__ __device__ inline SmemPlan make_plan(int N, int L, int W, int nbmax, in
   p.ints = take((nints * 4 + nbytes + 15) / 8);
   o = (o + 1) & ~1;  // 16-byte align tiles
   p.Mm = o;
-  if (m_in_smem) o += bc4_doubles(n4max);
+  // the factor's buffer doubles as the staging area of the raw inputs (dead before the build)
+  if (m_in_smem) o += mat_region_doubles(N, L, n4max);
   p.total = (o + 1) & ~1;
   return p;
 }
 
 // ------------------------------------------------------------------ classification
-// One thread per instance: number of free blocks -> size class -> permutation slot.
+// One warp per instance (coalesced reads of the contact flags, which may sit in mapped host
+// memory): number of free blocks -> size class -> permutation slot.
 // bounds = largest nb of classes 0..2 (ascending); class 3 takes the rest.
 __global__ void classify_kernel(const DevConfig cfg, int B, const double* des_inputs, int4 bounds,
                                 int32_t* counts, int32_t* perm) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (b >= B) return;
   const int N = cfg.N, L = cfg.L;
   const double* di = des_inputs + (size_t)b * L * (4 * N + 3);
   int nb = 0;
-  for (int i = 0; i < L; ++i)
-    for (int j = 0; j < N; ++j) nb += di[i * (4 * N + 3) + j] > 0.0 ? 1 : 0;
-  int c = 3;
-  if (nb <= bounds.x) c = 0;
-  else if (nb <= bounds.y) c = 1;
-  else if (nb <= bounds.z) c = 2;
-  const int slot = atomicAdd(&counts[c], 1);
-  perm[(size_t)c * B + slot] = b;
+  for (int e = lane; e < L * N; e += 32) {
+    const int i = e / N, j = e - i * N;
+    nb += __ldg(di + i * (4 * N + 3) + j) > 0.0 ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nb += __shfl_xor_sync(0xffffffffu, nb, o);
+  if (lane == 0) {
+    int c = 3;
+    if (nb <= bounds.x) c = 0;
+    else if (nb <= bounds.y) c = 1;
+    else if (nb <= bounds.z) c = 2;
+    const int slot = atomicAdd(&counts[c], 1);
+    perm[(size_t)c * B + slot] = b;
+  }
 }
 
 // ------------------------------------------------------------------ the fused kernel
@@ -699,7 +714,7 @@ __global__ void __launch_bounds__(W == 2 ? 512 : 256) cmpc_solve_kernel(const De
   const int group_global = blockIdx.x * args.groups + G.gid;
   double* Hm = args.scratch + (size_t)group_global * args.scratch_per_group;
   double* Mm;
-  if constexpr (MS) Mm = base + P.Mm; else Mm = Hm + bc4_doubles(args.n4max);
+  if constexpr (MS) Mm = base + P.Mm; else Mm = Hm + mat_region_doubles(N, L, args.n4max);
 
   const double dt = cfg.dt, mass = cfg.mass;
   const double zeta = cfg.zoh ? 0.5 : 0.0;
@@ -711,18 +726,25 @@ __global__ void __launch_bounds__(W == 2 ? 512 : 256) cmpc_solve_kernel(const De
     slot = G.bcast0(slot, s_misc + 2);
     if (slot >= count) break;
     const int inst = args.perm ? args.perm[slot] : slot;
-    const double* g_state = args.state + (size_t)inst * ns;
-    const double* g_ds = args.des_state + (size_t)inst * nds;
-    const double* g_di = args.des_inputs + (size_t)inst * ndi;
+    // ---- stage the raw inputs once, coalesced (CentroidalMPC.cpp:284-317 copies them blindly;
+    // here non-finite values are caught).  The buffers may be HBM or mapped pinned host memory
+    // (zero-copy end-to-end path): every input byte crosses the bus exactly once.  The staging
+    // area is the factor's buffer, which is dead until the build.
+    double* g_state = Mm;
+    double* g_ds = Mm + ns;
+    double* g_di = Mm + ns + nds;
+    bool finite = true;
+    {
+      const double* src = args.state + (size_t)inst * ns;
+      for (int t = gtid; t < ns; t += GT) { const double v = __ldg(src + t); g_state[t] = v; finite = finite && isfinite(v); }
+      src = args.des_state + (size_t)inst * nds;
+      for (int t = gtid; t < nds; t += GT) { const double v = __ldg(src + t); g_ds[t] = v; finite = finite && isfinite(v); }
+      src = args.des_inputs + (size_t)inst * ndi;
+      for (int t = gtid; t < ndi; t += GT) { const double v = __ldg(src + t); g_di[t] = v; finite = finite && isfinite(v); }
+    }
     const double* g_dpos = g_ds;
     const double* g_dvel = g_ds + 3 * (N + 1);
     const double* g_dam = g_ds + 6 * (N + 1);
-
-    // ---- scan inputs for non-finite values (CentroidalMPC.cpp:284-317 copies them blindly)
-    bool finite = true;
-    for (int t = gtid; t < ns; t += GT) finite = finite && isfinite(g_state[t]);
-    for (int t = gtid; t < nds; t += GT) finite = finite && isfinite(g_ds[t]);
-    for (int t = gtid; t < ndi; t += GT) finite = finite && isfinite(g_di[t]);
     finite = G.all(finite);
 
     // ---- contact table -> free blocks; validity (CentroidalMPC.cpp:328-330)
@@ -802,6 +824,7 @@ __global__ void __launch_bounds__(W == 2 ? 512 : 256) cmpc_solve_kernel(const De
     double* Hb;
     if constexpr (MS) Hb = Mm; else Hb = Hm;
     {
+      G.sync();  // all reads of the staged inputs (they live in the factor's buffer) are done
       for (int t = gtid; t < matd; t += GT) Hb[t] = 0.0;
       G.sync();
       const int npairs = (nb * (nb + 1)) >> 1;

@@ -161,3 +161,33 @@ def test_weights_update_and_zoh_mode(pkg, orc, wl):
     assert np.abs(out["forces"] - ref["forces"]).max() <= 1e-6 * np.abs(ref["forces"]).max()
     assert np.array_equal(out["active"], ref["active"])
     mz.close()
+
+
+def test_zero_copy_pinned_buffers_match_staged(pkg, wl):
+    """cmpc_solve_batch with page-locked host buffers runs in place over the bus (no staging
+    copies); results must be bit-identical to the staged path used for pageable buffers."""
+    import ctypes as C
+    import torch
+    cfg = wl.default_config(10)
+    B = 1024
+    st, ds, di = wl.make_batch(cfg, B, gaits=wl.GAITS)
+    m = pkg.CentroidalMPC.from_dict(cfg)
+    m.SetupMPC(B)
+    staged = m.UpdateMPCBatch(st, ds, di)                       # pageable numpy -> staged copies
+    assert staged["stats"]["h2d_ms"] > 0
+    pin = [torch.from_numpy(a).pin_memory() for a in (st, ds, di)]
+    f = torch.zeros(B, m.n_forces, dtype=torch.float64).pin_memory()
+    s = torch.full((B,), -1, dtype=torch.int32).pin_memory()
+    it = torch.zeros(B, dtype=torch.int32).pin_memory()
+    kk = torch.zeros(B, dtype=torch.float64).pin_memory()
+    act = torch.zeros(B, 10, 4, dtype=torch.int16).pin_memory()
+    stats = pkg.CmpcStats()
+    vp = C.c_void_p
+    rc = m.lib.cmpc_solve_batch(m.h, B, vp(pin[0].data_ptr()), vp(pin[1].data_ptr()), vp(pin[2].data_ptr()), vp(f.data_ptr()),
+                                vp(s.data_ptr()), vp(it.data_ptr()), vp(kk.data_ptr()), None, vp(act.data_ptr()), C.byref(stats))
+    assert rc == 0
+    assert stats.h2d_ms == 0 and stats.d2h_ms == 0            # no staging copies ran
+    assert np.array_equal(f.numpy(), staged["forces"])
+    assert np.array_equal(s.numpy(), staged["status"]) and np.array_equal(it.numpy(), staged["iters"])
+    assert np.array_equal(act.numpy().view(np.uint16), staged["active"])
+    m.close()
