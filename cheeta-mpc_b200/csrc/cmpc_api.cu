@@ -257,7 +257,7 @@ int plan_class(cmpc_handle* h, cmpc_handle::ClassPlan& p, int W, int nbmax, int 
   SmemPlan sp = make_plan(N, L, W, p.nbmax, p.n4max, 1);
   if (mode == 1 || (size_t)sp.total * 8 > kMaxSmem) { p.m_in_smem = 0; sp = make_plan(N, L, W, p.nbmax, p.n4max, 0); }
   if ((size_t)sp.total * 8 > kMaxSmem) return fail(h, CMPC_ERR_ARG, "horizon too large for the shared-memory vectors");
-  const int gmax = (W == 2 ? 512 : 256) / (32 * W);
+  const int gmax = (W == 2 ? 512 : (W == 1 ? 288 : 256)) / (32 * W);
   p.groups = (int)std::min<size_t>((size_t)gmax, kMaxSmem / ((size_t)sp.total * 8));
   if (p.groups < 1) p.groups = 1;
   p.smem_bytes = (size_t)sp.total * 8 * p.groups;

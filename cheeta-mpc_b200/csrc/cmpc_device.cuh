@@ -598,14 +598,15 @@ __device__ __noinline__ bool block_multipliers(int k, const double (*Nrm)[3], co
 }
 
 // ------------------------------------------------------------------ shared-memory plan (per group)
-// Aliases (lifetimes do not overlap): eq/qz (build only) live in tv..up; the lever arms
-// (build only) in du; the desired fz (build + start point) in rhs; the polish's null-space
-// bases Zt in isl..isu (recomputed every IPM iteration).
+// Aliases (lifetimes do not overlap): eq/qz (build only) live in rd..tv; the lever arms (build
+// only) and the polish's candidate point `up` in du; the desired fz (build + start point) in
+// rhs; the polish's null-space bases Zt in cdu..dzl (the candidates that share those arrays are
+// written after the last use of Zt in a pass).  3228 doubles at nb <= 20, N = 10: 9 groups/SM.
 struct SmemPlan {
   // offsets in doubles from the start of the group's slab
-  int ce, g, u, rd, rhs, du, tv, up;
-  int sl, zl, zu, isl, isu, cdu, dzl, dzu, red, exch, ints, Mm;
-  int total;  // doubles, multiple of 16
+  int ce, g, u, rd, tv, rhs, du;
+  int sl, zl, zu, cdu, dzl, dzu, red, exch, ints, Mm;
+  int total;  // doubles, multiple of 2
 };
 __host__ __device__ inline SmemPlan make_plan(int N, int L, int W, int nbmax, int n4max, int m_in_smem) {
   SmemPlan p;
@@ -613,22 +614,20 @@ __host__ __device__ inline SmemPlan make_plan(int N, int L, int W, int nbmax, in
   int o = 0;
   auto take = [&](int cnt) { int r = o; o += (cnt + 1) & ~1; return r; };
   p.ce = take(nbmax);
-  p.g = take(n4max); p.u = take(n4max); p.rd = take(n4max); p.rhs = take(n4max); p.du = take(n4max);
-  const int nv = (2 * n4max >= 10 * N + 2) ? n4max : (10 * N + 2 + 1) / 2;  // tv+up also host eq[9N], qz[N]
-  p.tv = take(nv); p.up = take(nv);
+  p.g = take(n4max); p.u = take(n4max);
+  const int nv = (2 * n4max >= 10 * N + 2) ? n4max : (10 * N + 2 + 1) / 2;  // rd+tv also host eq[9N], qz[N]
+  p.rd = take(nv); p.tv = take(nv);
+  p.rhs = take(n4max); p.du = take(n4max);
   p.sl = take(mmax); p.zl = take(mmax); p.zu = take(mmax);
-  p.isl = take(mmax); p.isu = take(mmax);
   p.cdu = take(mmax); p.dzl = take(mmax); p.dzu = take(mmax);
   p.red = take(W > 1 ? 3 * W : 2);
   p.exch = take(8);
-  // ints: blk_j, blk_i, rk, off [nbmax each], blk_of [N*L], misc[8]; bytes: actl, actu [mmax each];
-  // uint16 tile table [tiles]
-  const int nints = 4 * nbmax + N * L + 8;
-  const int nbytes = 2 * mmax + 2 + 2 * bc4_tiles(n4max);
-  p.ints = take((nints * 4 + nbytes + 15) / 8);
+  // bytes: blk_j, blk_i, rk [nbmax each], blk_of [N*L] (int8), actl, actu [mmax each];
+  // uint16: off [nbmax], tile table [tiles]; int32 misc[4]
+  const int nbytes = 3 * nbmax + N * L + 2 * mmax + 2 + 2 * nbmax + 2 * bc4_tiles(n4max) + 2 + 16;
+  p.ints = take((nbytes + 7) / 8);
   o = (o + 1) & ~1;  // 16-byte align tiles
   p.Mm = o;
-  // the factor's buffer doubles as the staging area of the raw inputs (dead before the build)
   if (m_in_smem) o += mat_region_doubles(N, L, n4max);
   p.total = (o + 1) & ~1;
   return p;
@@ -665,7 +664,7 @@ __global__ void classify_kernel(const DevConfig cfg, int B, const double* des_in
 // ------------------------------------------------------------------ the fused kernel
 // MODE 0: solve.  MODE 1: build-export (H, g in the full 3LN layout to global memory).
 template <int W, int MODE, bool MS>
-__global__ void __launch_bounds__(W == 2 ? 512 : 256) cmpc_solve_kernel(const DevConfig cfg, const SolveArgs args) {
+__global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 288 : 256)) cmpc_solve_kernel(const DevConfig cfg, const SolveArgs args) {
   extern __shared__ __align__(128) double smem[];
   constexpr int GT = Group<W>::GT;
   const int N = cfg.N, L = cfg.L, nu = 3 * L;
@@ -690,27 +689,25 @@ __global__ void __launch_bounds__(W == 2 ? 512 : 256) cmpc_solve_kernel(const De
   double* s_du = base + P.du;
   double* s_arm = s_du;  // lever arms: build only
   double* s_tv = base + P.tv;
-  double* s_up = base + P.up;
-  double* s_eq = s_tv;   // build only: 9N weighted errors then N z-weights
-  double* s_qz = s_tv + 9 * N;
+  double* s_up = s_du;   // polish only: candidate point (du is dead there; chol's rhs is tv)
+  double* s_eq = s_rd;   // build only: 9N weighted errors then N z-weights, spanning rd..tv
+  double* s_qz = s_rd + 9 * N;
   double* s_sl = base + P.sl;
   double* s_zl = base + P.zl;
   double* s_zu = base + P.zu;
-  double* s_isl = base + P.isl;
-  double* s_isu = base + P.isu;
-  double* s_Zt = s_isl;  // polish only: 9 nb doubles <= isl + isu
   double* s_cdu = base + P.cdu;
   double* s_dzl = base + P.dzl;
   double* s_dzu = base + P.dzu;
-  int* s_blk_j = reinterpret_cast<int*>(base + P.ints);
-  int* s_blk_i = s_blk_j + nbmax;
-  int* s_rk = s_blk_i + nbmax;
-  int* s_off = s_rk + nbmax;
-  int* s_blk_of = s_off + nbmax;    // [N*L] free block index or -1
-  int* s_misc = s_blk_of + nbfull;  // [0]=nb, [1]=invalid, [2]=work slot, [3]=nr
-  unsigned char* s_actl = reinterpret_cast<unsigned char*>(s_misc + 8);
+  double* s_Zt = s_cdu;  // polish only: 9 nb doubles <= cdu + dzl
+  int* s_misc = reinterpret_cast<int*>(base + P.ints);  // [0]=nb, [1]=invalid, [2]=work slot, [3]=nr
+  uint16_t* s_off = reinterpret_cast<uint16_t*>(s_misc + 4);
+  uint16_t* s_tb = s_off + nbmax + (nbmax & 1);
+  uint8_t* s_blk_j = reinterpret_cast<uint8_t*>(s_tb + bc4_tiles(args.n4max) + (bc4_tiles(args.n4max) & 1));
+  uint8_t* s_blk_i = s_blk_j + nbmax;
+  uint8_t* s_rk = s_blk_i + nbmax;
+  int8_t* s_blk_of = reinterpret_cast<int8_t*>(s_rk + nbmax);  // [N*L] free block index or -1 (nb <= 127)
+  unsigned char* s_actl = reinterpret_cast<unsigned char*>(s_blk_of + nbfull);
   unsigned char* s_actu = s_actl + mmax;
-  uint16_t* s_tb = reinterpret_cast<uint16_t*>(s_actu + mmax);  // 2*mmax bytes past an int: even
   const int group_global = blockIdx.x * args.groups + G.gid;
   double* Hm = args.scratch + (size_t)group_global * args.scratch_per_group;
   double* Mm;
@@ -948,8 +945,8 @@ __global__ void __launch_bounds__(W == 2 ? 512 : 256) cmpc_solve_kernel(const De
     if (gtid < n4 - n) s_u[n + gtid] = 0.0;
     if constexpr (!MS) copy_mat<W>(G, Mm, Hm, matd);
     G.sync();
-    // (s_fz aliases s_rhs, s_arm aliases s_du, s_eq aliases s_tv/s_up: all dead from here on)
-    if (gtid < n4 - n) { s_rhs[n + gtid] = 0.0; s_du[n + gtid] = 0.0; s_rd[n + gtid] = 0.0; s_tv[n + gtid] = 0.0; s_up[n + gtid] = 0.0; }
+    // (s_fz aliases s_rhs, s_arm aliases s_du, s_eq aliases s_rd/s_tv: all dead from here on)
+    if (gtid < n4 - n) { s_rhs[n + gtid] = 0.0; s_du[n + gtid] = 0.0; s_rd[n + gtid] = 0.0; s_tv[n + gtid] = 0.0; }
     symv_bc4<W>(G, Mm, n4, nblk, s_u, s_rd);
     double gmax = 0.0, r0max = 0.0;
     for (int t = gtid; t < n; t += GT) { gmax = fmax(gmax, fabs(s_g[t])); r0max = fmax(r0max, fabs(s_rd[t] + s_g[t])); }
@@ -1229,7 +1226,6 @@ __global__ void __launch_bounds__(W == 2 ? 512 : 256) cmpc_solve_kernel(const De
           const int t = 5 * b + q;
           const double sl = s_sl[t], su = (q < 4 ? ubxy : ubz) - sl;
           const double isl = fast_rcp(sl), isu = fast_rcp(su);
-          s_isl[t] = isl; s_isu[t] = isu;
           sg[q] = s_zl[t] * isl + s_zu[t] * isu;
           tq[q] = s_zu[t] - s_zl[t];
         }
@@ -1260,7 +1256,7 @@ __global__ void __launch_bounds__(W == 2 ? 512 : 256) cmpc_solve_kernel(const De
               const double sl = s_sl[t], su = (q < 4 ? ubxy : ubz) - sl;
               const double rcl = -sl * s_zl[t] + sigma * mu - s_cdu[t] * s_dzl[t];
               const double rcu = -su * s_zu[t] + sigma * mu + s_cdu[t] * s_dzu[t];
-              tq[q] = rcl * s_isl[t] - rcu * s_isu[t];
+              tq[q] = rcl * fast_rcp(sl) - rcu * fast_rcp(su);
             }
             ctmul5(cfg.mu[s_blk_i[b]], tq, o);
             for (int q = 0; q < 3; ++q) s_du[3 * b + q] = -s_rd[3 * b + q] + o[q];
@@ -1281,9 +1277,10 @@ __global__ void __launch_bounds__(W == 2 ? 512 : 256) cmpc_solve_kernel(const De
             double rcl = -sl * zl, rcu = -su * zu;
             if (phase) { rcl += sigma * mu - s_cdu[t] * s_dzl[t]; rcu += sigma * mu + s_cdu[t] * s_dzu[t]; }
             const double cd = y[q];
-            const double dl = (rcl - zl * cd) * s_isl[t];
-            const double du_ = (rcu + zu * cd) * s_isu[t];
-            tloc = fmax(tloc, fmax(-cd * s_isl[t], cd * s_isu[t]));
+            const double isl = fast_rcp(sl), isu = fast_rcp(su);
+            const double dl = (rcl - zl * cd) * isl;
+            const double du_ = (rcu + zu * cd) * isu;
+            tloc = fmax(tloc, fmax(-cd * isl, cd * isu));
             tloc = fmax(tloc, fmax(-dl * fast_rcp(zl), -du_ * fast_rcp(zu)));
             s_cdu[t] = cd; s_dzl[t] = dl; s_dzu[t] = du_;
           }
