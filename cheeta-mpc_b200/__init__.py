@@ -9,7 +9,7 @@ There is NO CPU fallback: every call goes through the CUDA library and raises if
 missing or no GPU is present.
 """
 from . import abi, workloads  # noqa: F401
-from .abi import (CmpcConfig, CmpcStats, CentroidalMPC, CmpcError, lib_path, load_library,  # noqa: F401
+from .abi import (CmpcConfig, CmpcGait, CmpcStats, make_gait, CentroidalMPC, CmpcError, lib_path, load_library,  # noqa: F401
                   make_config, STATUS_NAMES)
 
 __all__ = ["abi", "workloads", "CmpcConfig", "CmpcStats", "CentroidalMPC", "CmpcError",

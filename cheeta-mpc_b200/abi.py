@@ -35,6 +35,21 @@ class CmpcStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+class CmpcGait(C.Structure):
+    _fields_ = [("num_modes", C.c_int32), ("modes", C.c_int32 * 8), ("switching_times", C.c_double * 9)]
+
+
+def make_gait(modes, switching_times) -> "CmpcGait":
+    """modes: OCS2 ModeNumber values 0..15 (bits LF=8, RF=4, LH=2, RH=1); switching_times: len(modes)+1."""
+    g = CmpcGait()
+    g.num_modes = len(modes)
+    for k, m in enumerate(modes):
+        g.modes[k] = int(m)
+    for k, t in enumerate(switching_times):
+        g.switching_times[k] = float(t)
+    return g
+
+
 class CmpcError(RuntimeError):
     pass
 
@@ -83,6 +98,8 @@ def load_library():
     lib.cmpc_solve_batch_device.argtypes = [vp, C.c_int] + [vp] * 9 + [C.POINTER(CmpcStats)]
     lib.cmpc_build_batch.argtypes = [vp, C.c_int] + [vp] * 6
     lib.cmpc_rollout.argtypes = [vp, C.c_int, C.c_int, C.c_int] + [vp] * 6 + [C.POINTER(CmpcStats)]
+    lib.cmpc_fill_contact_tables.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp]
+    lib.cmpc_fill_contact_tables_device.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp]
     lib.cmpc_set_stream.argtypes = [vp, vp]
     lib.cmpc_synchronize.argtypes = [vp]
     lib.cmpc_measure_fp64_peak.argtypes = [vp, dp]
@@ -204,6 +221,16 @@ class CentroidalMPC:
                                           _ptr(flog), _ptr(iters), _ptr(stor), C.byref(stats)))
         return dict(state=st, des_state=ds, des_inputs=di, force_log=flog, iters_sum=iters, status_or=stor,
                     stats=stats.as_dict())
+
+    def FillContactTables(self, gaits, gait_id, t0, des_inputs):
+        """Device-side gait -> contact table. gaits: list of CmpcGait; returns des_inputs copy."""
+        di = _f64(des_inputs).copy(); B = di.shape[0]
+        gid = np.ascontiguousarray(gait_id, dtype=np.int32); tt = _f64(t0)
+        arr = (CmpcGait * len(gaits))(*gaits)
+        if self.max_batch == 0:
+            self.SetupMPC(B)
+        self._check(self.lib.cmpc_fill_contact_tables(self.h, B, C.cast(arr, C.c_void_p), len(gaits), _ptr(gid), _ptr(tt), _ptr(di)))
+        return di
 
     def set_stream(self, stream_ptr):
         self._check(self.lib.cmpc_set_stream(self.h, C.c_void_p(stream_ptr)))

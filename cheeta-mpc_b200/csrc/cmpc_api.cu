@@ -145,6 +145,33 @@ __global__ void advance_kernel(const DevConfig cfg, int B, double* state, double
   if (status_or) status_or[b] |= (1 << status[b]);
 }
 
+// Gait -> contact table. One thread per (instance, step).
+constexpr int kMaxGaits = 16;
+struct GaitTable {
+  int num_gaits;
+  cmpc_gait g[kMaxGaits];
+};
+__global__ void gait_kernel(const DevConfig cfg, int B, const GaitTable tab, const int32_t* gait_id, const double* t0,
+                            double* des_inputs) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = cfg.N, L = cfg.L;
+  if (idx >= B * N) return;
+  const int b = idx / N, j = idx - b * N;
+  int gid = gait_id[b];
+  if (gid < 0 || gid >= tab.num_gaits) gid = 0;
+  const cmpc_gait& g = tab.g[gid];
+  const double start = g.switching_times[0], duration = g.switching_times[g.num_modes] - start;
+  // no fused multiply-add here: a step that lands exactly on a switching time must round like the host code
+  const double t = __dadd_rn(t0[b], __dmul_rn((double)j, cfg.dt));
+  double phase = fmod(__ddiv_rn(t, duration), 1.0);  // wrapPhase, Gait.cpp:63-69
+  if (phase < 0.0) phase += 1.0;
+  int k = 0;  // upper_bound over eventPhases = (switching_times[1..n-1] - start) / duration
+  while (k < g.num_modes - 1 && !(phase < __ddiv_rn(__dsub_rn(g.switching_times[k + 1], start), duration))) ++k;
+  const int mode = g.modes[k];
+  const int bit[4] = {8, 4, 1, 2};  // {lf, rf, rh, lh} <- {LF, RF, RH, LH}
+  for (int i = 0; i < L; ++i) des_inputs[(size_t)b * L * (4 * N + 3) + i * (4 * N + 3) + j] = (mode & bit[i]) ? 1.0 : 0.0;
+}
+
 // FP64 throughput probe: 8 independent DFMA chains per thread.
 __global__ void fp64_peak_kernel(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1e-9, a2 = a0 + 2e-9, a3 = a0 + 3e-9;
@@ -621,6 +648,56 @@ int cmpc_rollout(cmpc_handle* h, int B, int ticks, int warm_start, double* state
     CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
     stats->kernel_ms = ms;
   }
+  return CMPC_OK;
+}
+
+static int check_gaits(cmpc_handle* h, const cmpc_gait* gaits, int num_gaits, GaitTable* tab) {
+  if (!gaits || num_gaits < 1 || num_gaits > kMaxGaits) return fail(h, CMPC_ERR_ARG, "gaits: 1..16 templates");
+  tab->num_gaits = num_gaits;
+  for (int q = 0; q < num_gaits; ++q) {
+    const cmpc_gait& g = gaits[q];
+    if (g.num_modes < 1 || g.num_modes > CMPC_MAX_GAIT_MODES) return fail(h, CMPC_ERR_ARG, "gait: num_modes out of range");
+    for (int k = 0; k < g.num_modes; ++k) {
+      if (g.modes[k] < 0 || g.modes[k] > 15) return fail(h, CMPC_ERR_ARG, "gait: mode numbers are 0..15");
+      if (!(g.switching_times[k + 1] > g.switching_times[k])) return fail(h, CMPC_ERR_ARG, "gait: switching times must ascend");
+    }
+    tab->g[q] = g;
+  }
+  return CMPC_OK;
+}
+
+int cmpc_fill_contact_tables_device(cmpc_handle* h, int B, const cmpc_gait* gaits, int num_gaits, const int32_t* d_gait_id,
+                                    const double* d_t0, double* d_des_inputs) {
+  if (!h || !h->ready) return fail(h, CMPC_ERR_STATE, "cmpc_fill_contact_tables: call cmpc_setup first");
+  if (B < 0 || !d_gait_id || !d_t0 || !d_des_inputs) return fail(h, CMPC_ERR_ARG, "null buffer");
+  GaitTable tab;
+  int rc = check_gaits(h, gaits, num_gaits, &tab);
+  if (rc) return rc;
+  if (B == 0) return CMPC_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const int total = B * h->cfg.horizon;
+  gait_kernel<<<(total + 255) / 256, 256, 0, h->stream>>>(h->dev, B, tab, d_gait_id, d_t0, d_des_inputs);
+  CUDA_TRY(h, cudaGetLastError());
+  return CMPC_OK;
+}
+
+int cmpc_fill_contact_tables(cmpc_handle* h, int B, const cmpc_gait* gaits, int num_gaits, const int32_t* gait_id,
+                             const double* t0, double* des_inputs) {
+  if (!h || !h->ready) return fail(h, CMPC_ERR_STATE, "cmpc_fill_contact_tables: call cmpc_setup first");
+  if (B < 0 || B > h->max_batch) return fail(h, CMPC_ERR_STATE, "batch exceeds max_batch given to cmpc_setup");
+  if (!gait_id || !t0 || !des_inputs) return fail(h, CMPC_ERR_ARG, "null buffer");
+  if (B == 0) return CMPC_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t ndi = (size_t)h->cfg.num_legs * (4 * h->cfg.horizon + 3);
+  cudaStream_t s = h->stream;
+  // the handle's per-instance scratch arrays double as staging: status (int32) and kkt (double)
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_status, gait_id, (size_t)B * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_kkt, t0, (size_t)B * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_di, des_inputs, B * ndi * 8, cudaMemcpyHostToDevice, s));
+  int rc = cmpc_fill_contact_tables_device(h, B, gaits, num_gaits, h->d_status, h->d_kkt, h->d_di);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(des_inputs, h->d_di, B * ndi * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
   return CMPC_OK;
 }
 

@@ -137,6 +137,30 @@ int cmpc_rollout(cmpc_handle* h, int B, int ticks, int warm_start, double* state
                  double* des_state, double* des_inputs, double* force_log,
                  int32_t* iters_sum, int32_t* status_or, cmpc_stats* stats);
 
+/* Gait template = ModeSequenceTemplate of the vendored OCS2 stack (ocs2_legged_robot/
+ * config/command/gait.info; src/gait/ModeSequenceTemplate.cpp:74-87 converts it to a Gait).
+ * modes[] are ModeNumber values 0..15 with bits {LF = 8, RF = 4, LH = 2, RH = 1}
+ * (include/ocs2_legged_robot/gait/MotionPhaseDefinition.h:47-64,129-132). */
+#define CMPC_MAX_GAIT_MODES 8
+typedef struct cmpc_gait {
+  int32_t num_modes;
+  int32_t modes[CMPC_MAX_GAIT_MODES];
+  double switching_times[CMPC_MAX_GAIT_MODES + 1]; /* num_modes + 1 ascending times */
+} cmpc_gait;
+
+/* Device-side gait -> contact table: for instance b and step j the contact
+ * flags at time t0[b] + j*dt are those of gait gait_id[b]:  phase = wrapPhase(t / duration)
+ * (Gait.cpp:63-69), mode = modeSequence[upper_bound(eventPhases, phase)] (Gait.cpp:74-88),
+ * stance legs = modeNumber2StanceLeg(mode).  OCS2's leg order {LF, RF, LH, RH} is mapped to
+ * the reference driver's {lf, rf, rh, lh} (CentoidMPCTest.cpp:43-46).  Only the contact
+ * entries of des_inputs are written.  A FLY mode yields a column without stance leg, which
+ * the solve flags CMPC_STATUS_INVALID_TABLE like the reference (CentroidalMPC.cpp:328-330).
+ * Host buffers; `_device` takes device pointers for gait_id, t0 and des_inputs. */
+int cmpc_fill_contact_tables(cmpc_handle* h, int B, const cmpc_gait* gaits, int num_gaits,
+                             const int32_t* gait_id, const double* t0, double* des_inputs);
+int cmpc_fill_contact_tables_device(cmpc_handle* h, int B, const cmpc_gait* gaits, int num_gaits,
+                                    const int32_t* d_gait_id, const double* d_t0, double* d_des_inputs);
+
 /* Use an externally owned CUDA stream (cudaStream_t as void*) for all device work. */
 int cmpc_set_stream(cmpc_handle* h, void* cuda_stream);
 int cmpc_synchronize(cmpc_handle* h);

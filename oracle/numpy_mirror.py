@@ -291,3 +291,41 @@ def stage_cost(cfg, qp, U):
             i, r = divmod(a, 3)
             J += w[9 + 6 * L + 3 * i + r] * (U[nu * (j + 1) + a] - U[nu * j + a]) ** 2
     return J
+
+
+# ---------------------------------------------------------------------------- gait
+# ModeNumber bits {LF=8, RF=4, LH=2, RH=1}: ocs2_legged_robot/include/ocs2_legged_robot/gait/
+# MotionPhaseDefinition.h:47-64,129-132.  Templates: ocs2_legged_robot/config/command/gait.info.
+MODE = dict(FLY=0, RH=1, LH=2, LH_RH=3, RF=4, RF_RH=5, RF_LH=6, RF_LH_RH=7, LF=8, LF_RH=9, LF_LH=10,
+            LF_LH_RH=11, LF_RF=12, LF_RF_RH=13, LF_RF_LH=14, STANCE=15)
+GAIT_INFO = {  # name -> (modeSequence, switchingTimes), values of gait.info:17-180
+    "stance": (["STANCE"], [0.0, 0.5]),
+    "trot": (["LF_RH", "RF_LH"], [0.0, 0.35, 0.70]),
+    "standing_trot": (["LF_RH", "STANCE", "RF_LH", "STANCE"], [0.00, 0.30, 0.35, 0.65, 0.70]),
+    "flying_trot": (["LF_RH", "FLY", "RF_LH", "FLY"], [0.00, 0.27, 0.30, 0.57, 0.60]),
+    "pace": (["LF_LH", "FLY", "RF_RH", "FLY"], [0.0, 0.28, 0.30, 0.58, 0.60]),
+    "standing_pace": (["LF_LH", "STANCE", "RF_RH", "STANCE"], [0.0, 0.30, 0.35, 0.65, 0.70]),
+    "dynamic_walk": (["LF_RF_RH", "RF_RH", "RF_LH_RH", "LF_RF_LH", "LF_LH", "LF_LH_RH"], [0.0, 0.2, 0.3, 0.5, 0.7, 0.8, 1.0]),
+    "static_walk": (["LF_RF_RH", "RF_LH_RH", "LF_RF_LH", "LF_LH_RH"], [0.0, 0.3, 0.6, 0.9, 1.2]),
+    "amble": (["RF_LH", "LF_LH", "LF_RH", "RF_RH"], [0.0, 0.15, 0.40, 0.55, 0.80]),
+}
+
+
+def gait_contact_table(mode_sequence, switching_times, t0, dt, N, L=4):
+    """Contact table [L, N] in the reference driver's leg order {lf, rf, rh, lh}
+    (CentoidMPCTest.cpp:43-46).  Restates toGait (ModeSequenceTemplate.cpp:74-87), wrapPhase and
+    getModeFromPhase (Gait.cpp:63-88, std::upper_bound) and modeNumber2StanceLeg."""
+    st = np.asarray(switching_times, float)
+    start, duration = st[0], st[-1] - st[0]
+    event_phases = (st[1:-1] - start) / duration
+    modes = [MODE[m] if isinstance(m, str) else int(m) for m in mode_sequence]
+    bit = [8, 4, 1, 2]  # {lf, rf, rh, lh} <- {LF, RF, RH, LH}
+    out = np.zeros((L, N))
+    for j in range(N):
+        phase = np.fmod((t0 + j * dt) / duration, 1.0)
+        if phase < 0:
+            phase += 1.0
+        k = int(np.searchsorted(event_phases, phase, side="right"))
+        for i in range(L):
+            out[i, j] = 1.0 if modes[k] & bit[i] else 0.0
+    return out

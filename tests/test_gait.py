@@ -1,0 +1,80 @@
+"""gait template -> contact table. CPU: the NumPy restatement of the vendored OCS2
+gait logic against hand-derived tables; GPU: the device kernel bit-exact against the restatement,
+and the generated tables solved with parity."""
+import numpy as np
+import pytest
+
+import numpy_mirror as nm
+
+
+def test_mirror_trot_template_matches_gait_info_by_hand():
+    # gait.info:30-43: LF_RH on [0, 0.35), RF_LH on [0.35, 0.70); dt = 0.05 -> 7 steps per phase
+    modes, times = nm.GAIT_INFO["trot"]
+    t = nm.gait_contact_table(modes, times, 0.0, 0.05, 14)
+    lf, rf, rh, lh = t
+    assert lf[:7].tolist() == [1] * 7 and lf[7:].tolist() == [0] * 7       # LF_RH = {LF, RH}
+    assert np.array_equal(lf, rh) and np.array_equal(rf, lh) and np.array_equal(lf + rf, np.ones(14))
+    # wrapPhase: one period later / earlier gives the same table (Gait.cpp:63-69)
+    assert np.array_equal(nm.gait_contact_table(modes, times, 0.70, 0.05, 14), t)
+    assert np.array_equal(nm.gait_contact_table(modes, times, -0.70, 0.05, 14), t)
+
+
+def test_mirror_mode_numbers_and_upper_bound_edges():
+    # stanceLeg2ModeNumber = RH + 2 LH + 4 RF + 8 LF (MotionPhaseDefinition.h:129-132)
+    assert nm.MODE["LF_RH"] == 9 and nm.MODE["RF_LH"] == 6 and nm.MODE["STANCE"] == 15 and nm.MODE["LF_RF_LH"] == 14
+    # a phase exactly on an event belongs to the NEXT mode (std::upper_bound, Gait.cpp:74-79)
+    modes, times = ["LF", "RF", "LH", "RH"], [0.0, 0.25, 0.5, 0.75, 1.0]
+    t = nm.gait_contact_table(modes, times, 0.0, 0.25, 4)
+    assert t.tolist() == [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]]  # rows lf, rf, rh, lh
+    # static_walk: always three stance legs; flying_trot has flight columns (invalid for this MPC)
+    sw = nm.gait_contact_table(*nm.GAIT_INFO["static_walk"], 0.13, 0.01, 120)
+    assert (sw.sum(axis=0) == 3).all()
+    ft = nm.gait_contact_table(*nm.GAIT_INFO["flying_trot"], 0.0, 0.01, 60)
+    assert (ft.sum(axis=0) == 0).any()
+
+
+@pytest.mark.gpu
+def test_device_gait_tables_bit_exact_and_solvable(pkg, orc, wl):
+    names = ["stance", "trot", "standing_trot", "static_walk", "dynamic_walk", "amble", "standing_pace", "flying_trot"]
+    gaits = [pkg.make_gait([nm.MODE[m] for m in nm.GAIT_INFO[n][0]], nm.GAIT_INFO[n][1]) for n in names]
+    for N, dt in ((10, 0.01), (30, 0.015), (6, 0.05)):
+        cfg = wl.default_config(N, dt=dt)
+        B = 256
+        st, ds, di = wl.make_batch(cfg, B)
+        rng = np.random.default_rng(N)
+        gid = rng.integers(0, len(names), B).astype(np.int32)
+        t0 = rng.uniform(-2.0, 5.0, B)
+        t0[:8] = [0.0, 0.35, 0.7, 0.3, 0.65, 0.27, 0.6, 1.2]           # on the switching times
+        m = pkg.CentroidalMPC.from_dict(cfg)
+        m.SetupMPC(B)
+        out = m.FillContactTables(gaits, gid, t0, di)
+        exp = di.copy()
+        for b in range(B):
+            tab = nm.gait_contact_table(*nm.GAIT_INFO[names[gid[b]]], t0[b], dt, N)
+            exp[b].reshape(4, 4 * N + 3)[:, :N] = tab
+        assert np.array_equal(out, exp)                                 # flags AND untouched foot positions
+        # the generated tables go straight into the solve; flight columns are flagged, not fatal
+        res = m.UpdateMPCBatch(st, ds, out, want_lam=False)
+        ref = orc.solve_batch(m.cfg, st, ds, out, nthreads=8, want_lam=False)
+        assert np.array_equal(res["status"], ref["status"])
+        flight = np.array([(out[b].reshape(4, 4 * N + 3)[:, :N].sum(axis=0) == 0).any() for b in range(B)])
+        assert np.array_equal(res["status"] == 3, flight) and flight.any()
+        ok = res["status"] == 0
+        assert ok.sum() > B // 2
+        scale = np.abs(ref["forces"][ok]).max(axis=1, keepdims=True)
+        assert (np.abs(res["forces"][ok] - ref["forces"][ok]) / scale).max() <= 1e-6
+        m.close()
+
+
+@pytest.mark.gpu
+def test_gait_argument_validation(pkg, wl):
+    cfg = wl.default_config(10)
+    st, ds, di = wl.make_batch(cfg, 4)
+    m = pkg.CentroidalMPC.from_dict(cfg)
+    m.SetupMPC(4)
+    bad = pkg.make_gait([9, 6], [0.0, 0.35, 0.30])                      # switching times must ascend
+    with pytest.raises(pkg.CmpcError, match="ascend"):
+        m.FillContactTables([bad], np.zeros(4, np.int32), np.zeros(4), di)
+    with pytest.raises(pkg.CmpcError, match="0..15"):
+        m.FillContactTables([pkg.make_gait([16], [0.0, 0.5])], np.zeros(4, np.int32), np.zeros(4), di)
+    m.close()
