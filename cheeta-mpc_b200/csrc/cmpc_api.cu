@@ -255,7 +255,7 @@ int launch_class(cmpc_handle* h, const cmpc_handle::ClassPlan& p, SolveArgs a) {
 int launch_solve(cmpc_handle* h, SolveArgs a, int B) {
   if (cudaMemsetAsync(h->d_counts, 0, 2 * kNumClasses * sizeof(int32_t), h->stream) != cudaSuccess)
     return fail(h, CMPC_ERR_CUDA, "memset counts");
-  classify_kernel<<<(B + 3) / 4, 128, 0, h->stream>>>(h->dev, B, a.des_inputs, h->bounds, h->d_counts, h->d_perm);
+  classify_kernel<<<(B + 31) / 32, 1024, 0, h->stream>>>(h->dev, B, a.des_inputs, h->bounds, h->d_counts, h->d_perm);
   int launches = 1;
   for (int c = 0; c < kNumClasses; ++c) {
     if (!h->cls[c].used) continue;

@@ -634,31 +634,46 @@ __host__ __device__ inline SmemPlan make_plan(int N, int L, int W, int nbmax, in
 }
 
 // ------------------------------------------------------------------ classification
-// One warp per instance (coalesced reads of the contact flags, which may sit in mapped host
-// memory): number of free blocks -> size class -> permutation slot.
+// Number of free blocks -> size class -> permutation slot.  One 1024-thread block handles 32
+// instances: warp w counts the contact flags of instance 32*blockIdx + w (coalesced reads, all
+// misses in flight at once; the flags may sit in mapped host memory), then warp 0 assigns the
+// slots, bumping each class counter once per block via __match_any_sync -- one atomic per
+// instance on the same address would serialise in L2.
 // bounds = largest nb of classes 0..2 (ascending); class 3 takes the rest.
-__global__ void classify_kernel(const DevConfig cfg, int B, const double* des_inputs, int4 bounds,
-                                int32_t* counts, int32_t* perm) {
-  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (b >= B) return;
+__global__ void __launch_bounds__(1024) classify_kernel(const DevConfig cfg, int B, const double* des_inputs, int4 bounds,
+                                                        int32_t* counts, int32_t* perm) {
+  __shared__ int s_nb[32];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 32 + w;
   const int N = cfg.N, L = cfg.L;
-  const double* di = des_inputs + (size_t)b * L * (4 * N + 3);
-  int nb = 0;
-  for (int e = lane; e < L * N; e += 32) {
-    const int i = e / N, j = e - i * N;
-    nb += __ldg(di + i * (4 * N + 3) + j) > 0.0 ? 1 : 0;
-  }
+  if (b < B) {
+    const double* di = des_inputs + (size_t)b * L * (4 * N + 3);
+    int nb = 0;
+    for (int e = lane; e < L * N; e += 32) {
+      const int i = e / N, j = e - i * N;
+      nb += __ldg(di + i * (4 * N + 3) + j) > 0.0 ? 1 : 0;
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) nb += __shfl_xor_sync(0xffffffffu, nb, o);
-  if (lane == 0) {
-    int c = 3;
-    if (nb <= bounds.x) c = 0;
-    else if (nb <= bounds.y) c = 1;
-    else if (nb <= bounds.z) c = 2;
-    const int slot = atomicAdd(&counts[c], 1);
-    perm[(size_t)c * B + slot] = b;
+    for (int o = 16; o > 0; o >>= 1) nb += __shfl_xor_sync(0xffffffffu, nb, o);
+    if (lane == 0) s_nb[w] = nb;
   }
+  __syncthreads();
+  if (w != 0) return;
+  const int bb = blockIdx.x * 32 + lane;
+  const bool valid = bb < B;
+  const int mine = valid ? s_nb[lane] : 0;
+  int c = 3;
+  if (mine <= bounds.x) c = 0;
+  else if (mine <= bounds.y) c = 1;
+  else if (mine <= bounds.z) c = 2;
+  if (!valid) c = 4;  // lanes past the end form their own group and do nothing
+  const unsigned peers = __match_any_sync(0xffffffffu, c);
+  const int leader = __ffs(peers) - 1;
+  const int rank = __popc(peers & ((1u << lane) - 1u));
+  int base = 0;
+  if (lane == leader && valid) base = atomicAdd(&counts[c], __popc(peers));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (valid) perm[(size_t)c * B + base + rank] = bb;
 }
 
 // ------------------------------------------------------------------ the fused kernel
