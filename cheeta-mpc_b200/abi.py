@@ -98,6 +98,7 @@ def load_library():
     lib.cmpc_solve_batch_device.argtypes = [vp, C.c_int] + [vp] * 9 + [C.POINTER(CmpcStats)]
     lib.cmpc_build_batch.argtypes = [vp, C.c_int] + [vp] * 6
     lib.cmpc_rollout.argtypes = [vp, C.c_int, C.c_int, C.c_int] + [vp] * 6 + [C.POINTER(CmpcStats)]
+    lib.cmpc_solve_batch_sqp.argtypes = [vp, C.c_int, C.c_int] + [vp] * 6
     lib.cmpc_fill_contact_tables.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp]
     lib.cmpc_fill_contact_tables_device.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp]
     lib.cmpc_set_stream.argtypes = [vp, vp]
@@ -221,6 +222,16 @@ class CentroidalMPC:
                                           _ptr(flog), _ptr(iters), _ptr(stor), C.byref(stats)))
         return dict(state=st, des_state=ds, des_inputs=di, force_log=flog, iters_sum=iters, status_or=stor,
                     stats=stats.as_dict())
+
+    def SolveSQP(self, state, des_state, des_inputs, sqp_iters=2):
+        """Successive re-linearisation of the lever arms. Returns forces, status, defect [B, iters+1]."""
+        st = _f64(state); B = st.shape[0]
+        st = _f64(st, (B, self.n_state)); ds = _f64(des_state, (B, self.n_des_state)); di = _f64(des_inputs, (B, self.n_des_inputs))
+        if self.max_batch == 0:
+            self.SetupMPC(B)
+        forces = np.zeros((B, self.n_forces)); status = np.zeros(B, np.int32); defect = np.zeros((B, sqp_iters + 1))
+        self._check(self.lib.cmpc_solve_batch_sqp(self.h, B, int(sqp_iters), _ptr(st), _ptr(ds), _ptr(di), _ptr(forces), _ptr(status), _ptr(defect)))
+        return dict(forces=forces, status=status, defect=defect)
 
     def FillContactTables(self, gaits, gait_id, t0, des_inputs):
         """Device-side gait -> contact table. gaits: list of CmpcGait; returns des_inputs copy."""

@@ -145,6 +145,61 @@ __global__ void advance_kernel(const DevConfig cfg, int B, double* state, double
   if (status_or) status_or[b] |= (1 << status[b]);
 }
 
+// Re-linearisation. One thread per instance: roll the forces through the QP's linear
+// model (arms frozen at di_lin) and through the reference's nonlinear Euler plant (arms
+// p_ij - c_j with p = the ORIGINAL desired foot positions di_orig), report the largest state
+// difference, and (update != 0) move the linearisation point of the next solve to the
+// nonlinear centre-of-mass path by shifting the desired foot positions of di_lin:
+//   des_foot_lin_ij = p_ij + (des_com_pos_j - c_j)   =>   arm = des_foot_lin - des_com_pos = p - c.
+__global__ void relinearize_kernel(const DevConfig cfg, int B, const double* state, const double* des_state,
+                                   const double* di_orig, double* di_lin, const double* forces, double* defect,
+                                   int defect_stride, int update) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int N = cfg.N, L = cfg.L;
+  const int ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = L * (4 * N + 3), nf = 3 * L * N;
+  const double* x0 = state + (size_t)b * ns;
+  const double* dpos = des_state + (size_t)b * nds;
+  const double* d0 = di_orig + (size_t)b * ndi;
+  double* dl = di_lin + (size_t)b * ndi;
+  const double* F = forces + (size_t)b * nf;
+  const double dt = cfg.dt, m = cfg.mass;
+  const double zeta = cfg.zoh ? 0.5 : 0.0;
+  double cn[3], vn[3], ln[3], cl[3], vl[3], ll[3];
+  for (int q = 0; q < 3; ++q) { cn[q] = cl[q] = x0[q]; vn[q] = vl[q] = x0[3 + q]; ln[q] = ll[q] = x0[6 + q]; }
+  double worst = 0.0;
+  for (int j = 0; j < N; ++j) {
+    // node j: shift the linearisation point of the next solve (node N is never used as an arm)
+    double accn[3] = {0.0, 0.0, -kGrav}, ldn[3] = {0.0, 0.0, 0.0}, ldl[3] = {0.0, 0.0, 0.0};
+    for (int i = 0; i < L; ++i) {
+      const double ce = d0[i * (4 * N + 3) + j] > 0.0 ? d0[i * (4 * N + 3) + j] : 0.0;
+      const double* f = F + ((size_t)i * N + j) * 3;
+      double p[3], rl[3], rn[3];
+      for (int q = 0; q < 3; ++q) {
+        p[q] = d0[i * (4 * N + 3) + N + 3 * j + q];
+        rl[q] = dl[i * (4 * N + 3) + N + 3 * j + q] - dpos[3 * j + q];  // the arm the QP used
+        rn[q] = p[q] - cn[q];                                            // the reference's arm (:86)
+      }
+      for (int q = 0; q < 3; ++q) accn[q] += ce / m * f[q];
+      ldn[0] += ce * (rn[1] * f[2] - rn[2] * f[1]); ldn[1] += ce * (rn[2] * f[0] - rn[0] * f[2]); ldn[2] += ce * (rn[0] * f[1] - rn[1] * f[0]);
+      ldl[0] += ce * (rl[1] * f[2] - rl[2] * f[1]); ldl[1] += ce * (rl[2] * f[0] - rl[0] * f[2]); ldl[2] += ce * (rl[0] * f[1] - rl[1] * f[0]);
+      if (update) for (int q = 0; q < 3; ++q) dl[i * (4 * N + 3) + N + 3 * j + q] = p[q] + (dpos[3 * j + q] - cn[q]);
+    }
+    for (int q = 0; q < 3; ++q) {
+      // linear model of the QP (Euler, or ZOH with its dt^2/2 position terms)
+      cl[q] += dt * vl[q] + zeta * dt * dt * accn[q];
+      vl[q] += dt * accn[q];
+      ll[q] += dt * ldl[q];
+      // reference plant: explicit Euler (CentroidalMPC.cpp:90-92)
+      cn[q] += dt * vn[q];
+      vn[q] += dt * accn[q];
+      ln[q] += dt * ldn[q];
+      worst = fmax(worst, fmax(fabs(cn[q] - cl[q]), fmax(fabs(vn[q] - vl[q]), fabs(ln[q] - ll[q]))));
+    }
+  }
+  if (defect) defect[(size_t)b * defect_stride] = worst;
+}
+
 // Gait -> contact table. One thread per (instance, step).
 constexpr int kMaxGaits = 16;
 struct GaitTable {
@@ -648,6 +703,46 @@ int cmpc_rollout(cmpc_handle* h, int B, int ticks, int warm_start, double* state
     CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
     stats->kernel_ms = ms;
   }
+  return CMPC_OK;
+}
+
+int cmpc_solve_batch_sqp(cmpc_handle* h, int B, int sqp_iters, const double* state, const double* des_state,
+                         const double* des_inputs, double* forces, int32_t* status, double* defect) {
+  if (!h || !h->ready) return fail(h, CMPC_ERR_STATE, "cmpc_solve_batch_sqp: call cmpc_setup first");
+  if (B < 0 || B > h->max_batch) return fail(h, CMPC_ERR_STATE, "batch exceeds max_batch given to cmpc_setup");
+  if (sqp_iters < 0 || sqp_iters > 16) return fail(h, CMPC_ERR_ARG, "sqp_iters must be 0..16");
+  if (!state || !des_state || !des_inputs || !forces || !status) return fail(h, CMPC_ERR_ARG, "null buffer");
+  if (B == 0) return CMPC_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const int N = h->cfg.horizon, L = h->cfg.num_legs;
+  const size_t ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = (size_t)L * (4 * N + 3), nf = (size_t)3 * L * N;
+  cudaStream_t s = h->stream;
+  double *d_di0 = nullptr, *d_def = nullptr;  // not on the per-tick path: temporaries are fine here
+  CUDA_TRY(h, cudaMalloc(&d_di0, B * ndi * 8));
+  CUDA_TRY(h, cudaMalloc(&d_def, (size_t)B * (sqp_iters + 1) * 8));
+  cudaMemcpyAsync(h->d_state, state, B * ns * 8, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(h->d_ds, des_state, B * nds * 8, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(h->d_di, des_inputs, B * ndi * 8, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(d_di0, h->d_di, B * ndi * 8, cudaMemcpyDeviceToDevice, s);
+  SolveArgs a = base_args(h, B);
+  a.state = h->d_state; a.des_state = h->d_ds; a.des_inputs = h->d_di;
+  a.forces = h->d_forces; a.status = h->d_status; a.iters = h->d_iters; a.kkt = h->d_kkt;
+  int rc = CMPC_OK;
+  for (int it = 0; it <= sqp_iters && rc >= 0; ++it) {
+    rc = launch_solve(h, a, B);
+    if (rc < 0) break;
+    relinearize_kernel<<<(B + 127) / 128, 128, 0, s>>>(h->dev, B, h->d_state, h->d_ds, d_di0, h->d_di, h->d_forces,
+                                                       d_def + it, sqp_iters + 1, it < sqp_iters ? 1 : 0);
+  }
+  if (rc >= 0) {
+    cudaMemcpyAsync(forces, h->d_forces, B * nf * 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(status, h->d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, s);
+    if (defect) cudaMemcpyAsync(defect, d_def, (size_t)B * (sqp_iters + 1) * 8, cudaMemcpyDeviceToHost, s);
+  }
+  cudaError_t e = cudaStreamSynchronize(s);
+  cudaFree(d_di0); cudaFree(d_def);
+  if (rc < 0) return rc;
+  if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, cudaGetErrorString(e));
   return CMPC_OK;
 }
 

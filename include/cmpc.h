@@ -137,6 +137,19 @@ int cmpc_rollout(cmpc_handle* h, int B, int ticks, int warm_start, double* state
                  double* des_state, double* des_inputs, double* force_log,
                  int32_t* iters_sum, int32_t* status_or, cmpc_stats* stats);
 
+/* Successive re-linearisation of the frozen lever arms (the model-fidelity number
+ * of SURVEY §0).  Iteration 0 is the plain solve (arms = des_foot_pos - des_com_pos).  Every
+ * further iteration re-solves with arms = des_foot_pos - c(j), where c is the centre-of-mass
+ * path that the previous iteration's forces produce through the reference's NONLINEAR Euler
+ * plant (CentroidalMPC.cpp:85-92, lever arm foot - com with com a trajectory variable, :86).
+ * At a fixed point the condensed linear model reproduces the reference dynamics exactly.
+ * defect [B][sqp_iters + 1] (may be NULL): max_j |x_nonlinear(j) - x_linear(j)|_inf of every
+ * iteration's solution, i.e. how far the QP's prediction is from the reference plant.
+ * forces / status are those of the last iteration.  Host buffers. */
+int cmpc_solve_batch_sqp(cmpc_handle* h, int B, int sqp_iters, const double* state,
+                         const double* des_state, const double* des_inputs, double* forces,
+                         int32_t* status, double* defect);
+
 /* Gait template = ModeSequenceTemplate of the vendored OCS2 stack (ocs2_legged_robot/
  * config/command/gait.info; src/gait/ModeSequenceTemplate.cpp:74-87 converts it to a Gait).
  * modes[] are ModeNumber values 0..15 with bits {LF = 8, RF = 4, LH = 2, RH = 1}
