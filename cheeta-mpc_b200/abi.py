@@ -98,6 +98,7 @@ def load_library():
     lib.cmpc_solve_batch_device.argtypes = [vp, C.c_int] + [vp] * 9 + [C.POINTER(CmpcStats)]
     lib.cmpc_build_batch.argtypes = [vp, C.c_int] + [vp] * 6
     lib.cmpc_rollout.argtypes = [vp, C.c_int, C.c_int, C.c_int] + [vp] * 6 + [C.POINTER(CmpcStats)]
+    lib.cmpc_foot_plan_batch.argtypes = [vp, C.c_int, vp, vp, vp]
     lib.cmpc_solve_batch_sqp.argtypes = [vp, C.c_int, C.c_int] + [vp] * 6
     lib.cmpc_fill_contact_tables.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp]
     lib.cmpc_fill_contact_tables_device.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp]
@@ -222,6 +223,16 @@ class CentroidalMPC:
                                           _ptr(flog), _ptr(iters), _ptr(stor), C.byref(stats)))
         return dict(state=st, des_state=ds, des_inputs=di, force_log=flog, iters_sum=iters, status_or=stor,
                     stats=stats.as_dict())
+
+    def FootPlan(self, state, des_inputs):
+        """Optimal foot positions [B, L, N+1, 3] (the foot_pos outputs of the reference controller)."""
+        st = _f64(state); B = st.shape[0]
+        st = _f64(st, (B, self.n_state)); di = _f64(des_inputs, (B, self.n_des_inputs))
+        if self.max_batch == 0:
+            self.SetupMPC(B)
+        fp = np.zeros((B, self.L, self.N + 1, 3))
+        self._check(self.lib.cmpc_foot_plan_batch(self.h, B, _ptr(st), _ptr(di), _ptr(fp)))
+        return fp
 
     def SolveSQP(self, state, des_state, des_inputs, sqp_iters=2):
         """Successive re-linearisation of the lever arms. Returns forces, status, defect [B, iters+1]."""

@@ -145,6 +145,33 @@ __global__ void advance_kernel(const DevConfig cfg, int B, double* state, double
   if (status_or) status_or[b] |= (1 << status[b]);
 }
 
+// Foot plan (decoupled half of the reference NLP). One thread per (instance, leg, axis).
+__global__ void foot_plan_kernel(const DevConfig cfg, int B, const double* state, const double* des_inputs, double* foot_pos) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = cfg.N, L = cfg.L;
+  if (idx >= B * L * 3) return;
+  const int b = idx / (3 * L), i = (idx / 3) % L, q = idx % 3;
+  const double* blk = des_inputs + (size_t)b * L * (4 * N + 3) + i * (4 * N + 3);
+  const double* pd = blk + N;  // des_foot_pos, node k at pd[3k + q]
+  double* out = foot_pos + ((size_t)b * L + i) * 3 * (N + 1);
+  const double lb = q == 2 ? -0.1 : -0.2, ub = q == 2 ? 0.1 : 0.2;  // CentroidalMPC.cpp:30-31
+  int a = 0;
+  while (a <= N) {
+    int e = a;  // group of nodes a..e joined by locked intervals (1 - contact == 0, :94)
+    while (e < N && 1.0 - blk[e] == 0.0) ++e;
+    double v;
+    if (a == 0) {
+      v = state[(size_t)b * (9 + 3 * L) + 9 + 3 * i + q];  // initial value constraint, :166
+    } else {
+      double sum = 0.0, lo = -INFINITY, hi = INFINITY;
+      for (int k = a; k <= e; ++k) { const double d = pd[3 * k + q]; sum += d; lo = fmax(lo, d + lb); hi = fmin(hi, d + ub); }
+      v = fmin(fmax(sum / (double)(e - a + 1), lo), hi);
+    }
+    for (int k = a; k <= e; ++k) out[3 * k + q] = v;
+    a = e + 1;
+  }
+}
+
 // Re-linearisation. One thread per instance: roll the forces through the QP's linear
 // model (arms frozen at di_lin) and through the reference's nonlinear Euler plant (arms
 // p_ij - c_j with p = the ORIGINAL desired foot positions di_orig), report the largest state
@@ -703,6 +730,27 @@ int cmpc_rollout(cmpc_handle* h, int B, int ticks, int warm_start, double* state
     CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
     stats->kernel_ms = ms;
   }
+  return CMPC_OK;
+}
+
+int cmpc_foot_plan_batch(cmpc_handle* h, int B, const double* state, const double* des_inputs, double* foot_pos) {
+  if (!h || !h->ready) return fail(h, CMPC_ERR_STATE, "cmpc_foot_plan_batch: call cmpc_setup first");
+  if (B < 0 || B > h->max_batch) return fail(h, CMPC_ERR_STATE, "batch exceeds max_batch given to cmpc_setup");
+  if (!state || !des_inputs || !foot_pos) return fail(h, CMPC_ERR_ARG, "null buffer");
+  if (B == 0) return CMPC_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const int N = h->cfg.horizon, L = h->cfg.num_legs;
+  const size_t ns = 9 + 3 * L, ndi = (size_t)L * (4 * N + 3), nfp = (size_t)3 * L * (N + 1);
+  cudaStream_t s = h->stream;
+  // [B][L][N+1][3] <= [B][2][N][L][5] doubles of the multiplier buffer: reuse it as the output staging
+  static_assert(3 * (CMPC_MAX_HORIZON + 1) <= 10 * CMPC_MAX_HORIZON, "foot plan fits the multiplier buffer");
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_state, state, B * ns * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_di, des_inputs, B * ndi * 8, cudaMemcpyHostToDevice, s));
+  const int total = B * L * 3;
+  foot_plan_kernel<<<(total + 255) / 256, 256, 0, s>>>(h->dev, B, h->d_state, h->d_di, h->d_lam);
+  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaMemcpyAsync(foot_pos, h->d_lam, B * nfp * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
   return CMPC_OK;
 }
 

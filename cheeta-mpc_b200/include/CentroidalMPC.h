@@ -107,6 +107,15 @@ class CentroidalMPC {
   }
 #endif
 
+  /* the foot_pos half of the reference's controller outputs (CentroidalMPC.cpp:269): optimal
+   * foot positions, per leg 3 x (N+1) column-major, from the decoupled foot sub-problem */
+  std::vector<double> FootPlan(const double* state, const double* des_inputs) {
+    if (max_batch_ == 0) SetupMPC(1);
+    std::vector<double> fp(3 * (size_t)num_legs_ * ((size_t)horizon_ + 1));
+    check(cmpc_foot_plan_batch(h_, 1, state, des_inputs, fp.data()));
+    return fp;
+  }
+
   /* B instances, instance-major host buffers (layouts in include/cmpc.h) */
   BatchResult UpdateMPCBatch(int B, const double* states, const double* des_states, const double* des_inputs) {
     if (max_batch_ == 0) SetupMPC(B);

@@ -137,6 +137,18 @@ int cmpc_rollout(cmpc_handle* h, int B, int ticks, int warm_start, double* state
                  double* des_state, double* des_inputs, double* force_log,
                  int32_t* iters_sum, int32_t* status_or, cmpc_stats* stats);
 
+/* The foot-position half of the reference's outputs (`controller_output.push_back(foot_pos[i])`,
+ * CentroidalMPC.cpp:269).  With the lever arms frozen the foot variables decouple from the
+ * forces, and their optimum has a closed form per leg and axis:
+ *   foot_pos[:,0] = current foot (:166);  foot_pos[:,k+1] = foot_pos[:,k] when 1 - contact_k == 0
+ *   (:94), free otherwise;  cost w_p sum_k (foot_pos_k - des_foot_pos_k)^2 (:219-221);  box
+ *   step_lb <= foot_pos_k - des_foot_pos_k <= step_ub for k = 1..N, step box +-(0.2, 0.2, 0.1)
+ *   (:30-31, :198).  Nodes joined by locked intervals share one value: the current foot for the
+ *   group of node 0, else the mean of the desired positions clipped to the intersected boxes.
+ * foot_pos [B][L][N+1][3] (each leg 3 x (N+1) column-major like the reference output). Host buffers. */
+int cmpc_foot_plan_batch(cmpc_handle* h, int B, const double* state, const double* des_inputs,
+                         double* foot_pos);
+
 /* Successive re-linearisation of the frozen lever arms (the model-fidelity number
  * of SURVEY §0).  Iteration 0 is the plain solve (arms = des_foot_pos - des_com_pos).  Every
  * further iteration re-solves with arms = des_foot_pos - c(j), where c is the centre-of-mass

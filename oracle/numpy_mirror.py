@@ -329,3 +329,53 @@ def gait_contact_table(mode_sequence, switching_times, t0, dt, N, L=4):
         for i in range(L):
             out[i, j] = 1.0 if modes[k] & bit[i] else 0.0
     return out
+
+
+# ---------------------------------------------------------------------------- foot plan (a3 / a8)
+STEP_LB = np.array([-0.2, -0.2, -0.1])  # CentroidalMPC.cpp:30
+STEP_UB = np.array([0.2, 0.2, 0.1])     # CentroidalMPC.cpp:31
+
+
+def foot_plan(cfg, state, des_inputs):
+    """Optimal foot positions [L, N+1, 3] of the decoupled foot sub-problem of the reference NLP:
+    foot_pos[:,0] = current foot (CentroidalMPC.cpp:166); foot_pos[:,k+1] = foot_pos[:,k] when
+    1 - contact_k == 0 (:94) else free; cost w_p sum_k (p_k - pd_k)^2 (:219-221); box on
+    p_k - pd_k for k = 1..N (:198).  Nodes joined by locked intervals share one value."""
+    N, L = cfg["horizon"], cfg["num_legs"]
+    state = np.asarray(state, float)
+    D = np.asarray(des_inputs, float).reshape(L, 4 * N + 3)
+    out = np.zeros((L, N + 1, 3))
+    for i in range(L):
+        c, pd = D[i, :N], D[i, N:].reshape(N + 1, 3)
+        a = 0
+        while a <= N:
+            e = a
+            while e < N and 1.0 - c[e] == 0.0:
+                e += 1
+            if a == 0:
+                v = state[9 + 3 * i:12 + 3 * i]
+            else:
+                grp = pd[a:e + 1]
+                v = np.minimum(np.maximum(grp.sum(axis=0) / (e - a + 1), (grp + STEP_LB).max(axis=0)), (grp + STEP_UB).min(axis=0))
+            out[i, a:e + 1] = v
+            a = e + 1
+    return out
+
+
+def foot_cost_and_feasible(cfg, state, des_inputs, p):
+    """Cost and feasibility of a candidate foot trajectory p [L, N+1, 3] under the reference's
+    constraints -- used to check foot_plan against perturbations."""
+    N, L = cfg["horizon"], cfg["num_legs"]
+    w = np.asarray(cfg["weights"], float)
+    D = np.asarray(des_inputs, float).reshape(L, 4 * N + 3)
+    cost, ok = 0.0, True
+    for i in range(L):
+        c, pd = D[i, :N], D[i, N:].reshape(N + 1, 3)
+        cost += float((w[9 + 3 * i:12 + 3 * i] * (p[i] - pd) ** 2).sum())
+        ok &= bool(np.allclose(p[i, 0], np.asarray(state, float)[9 + 3 * i:12 + 3 * i], atol=1e-15))
+        for k in range(N):
+            if 1.0 - c[k] == 0.0:
+                ok &= bool(np.array_equal(p[i, k + 1], p[i, k]))
+        dlt = p[i, 1:] - pd[1:]
+        ok &= bool((dlt >= STEP_LB - 1e-12).all() and (dlt <= STEP_UB + 1e-12).all())
+    return cost, ok

@@ -78,3 +78,53 @@ def test_gait_argument_validation(pkg, wl):
     with pytest.raises(pkg.CmpcError, match="0..15"):
         m.FillContactTables([pkg.make_gait([16], [0.0, 0.5])], np.zeros(4, np.int32), np.zeros(4), di)
     m.close()
+
+
+# ---------------------------------------------------------------- foot plan (reference output foot_pos)
+def _foot_case(wl, seed, N=10):
+    cfg = wl.default_config(N)
+    rng = np.random.default_rng(seed)
+    st, ds, di = wl.make_batch(cfg, 1, first=seed, gaits=(wl.GAITS[seed % 5],))
+    D = di[0].reshape(4, 4 * N + 3)
+    D[:, N:] += rng.normal(scale=0.08, size=(4, 3 * (N + 1)))        # moving desired footholds
+    return cfg, st[0], di[0]
+
+
+def test_foot_plan_is_feasible_and_locally_optimal(wl):
+    for seed in range(12):
+        cfg, st, di = _foot_case(wl, seed)
+        p = nm.foot_plan(cfg, st, di)
+        cost, ok = nm.foot_cost_and_feasible(cfg, st, di, p)
+        if not ok:
+            continue  # current foot too far from a desired foothold in its initial stance run: the reference NLP is infeasible too
+        rng = np.random.default_rng(100 + seed)
+        D = di.reshape(4, 43)
+        for _ in range(200):  # feasible perturbations never do better (convex problem: local = global)
+            q = p.copy()
+            i, k = rng.integers(0, 4), rng.integers(1, 11)
+            a = k
+            while a > 0 and 1.0 - D[i, a - 1] == 0.0:
+                a -= 1
+            e = k
+            while e < 10 and 1.0 - D[i, e] == 0.0:
+                e += 1
+            if a == 0:
+                continue
+            q[i, a:e + 1] += rng.normal(scale=0.01, size=3)
+            c2, ok2 = nm.foot_cost_and_feasible(cfg, st, di, q)
+            assert (not ok2) or c2 >= cost - 1e-12
+
+
+@pytest.mark.gpu
+def test_device_foot_plan_matches_mirror(pkg, wl):
+    cfg = wl.default_config(10)
+    B = 128
+    st, ds, di = wl.make_batch(cfg, B, gaits=wl.GAITS)
+    rng = np.random.default_rng(5)
+    di.reshape(B, 4, 43)[:, :, 10:] += rng.normal(scale=0.08, size=(B, 4, 33))
+    m = pkg.CentroidalMPC.from_dict(cfg)
+    m.SetupMPC(B)
+    fp = m.FootPlan(st, di)
+    for b in range(B):
+        assert np.abs(fp[b] - nm.foot_plan(cfg, st[b], di[b])).max() <= 1e-15
+    m.close()
