@@ -598,14 +598,15 @@ __device__ __noinline__ bool block_multipliers(int k, const double (*Nrm)[3], co
 }
 
 // ------------------------------------------------------------------ shared-memory plan (per group)
-// Aliases (lifetimes do not overlap): eq/qz (build only) live in rd..tv; the lever arms (build
-// only) and the polish's candidate point `up` in du; the desired fz (build + start point) in
-// rhs; the polish's null-space bases Zt in cdu..dzl (the candidates that share those arrays are
-// written after the last use of Zt in a pass).  3228 doubles at nb <= 20, N = 10: 9 groups/SM.
+// Only the multipliers are stored per constraint row: the slacks are recomputed from u (5 flops per
+// leg-step), the affine step's row quantities from a copy of the affine direction (dua), and the
+// polish's null-space bases live in the group's L2 slab.  Aliases (lifetimes do not overlap):
+// eq/qz (build only) in rd..tv; the lever arms (build only) and the polish's candidate point `up`
+// in du; the desired fz (build + start point) in rhs.  2886 doubles at nb <= 20, N = 10: 10 groups/SM.
 struct SmemPlan {
   // offsets in doubles from the start of the group's slab
-  int ce, g, u, rd, tv, rhs, du;
-  int sl, zl, zu, cdu, dzl, dzu, red, exch, ints, Mm;
+  int ce, g, u, rd, tv, rhs, du, dua;
+  int zl, zu, red, exch, ints, Mm;
   int total;  // doubles, multiple of 2
 };
 __host__ __device__ inline SmemPlan make_plan(int N, int L, int W, int nbmax, int n4max, int m_in_smem) {
@@ -617,9 +618,8 @@ __host__ __device__ inline SmemPlan make_plan(int N, int L, int W, int nbmax, in
   p.g = take(n4max); p.u = take(n4max);
   const int nv = (2 * n4max >= 10 * N + 2) ? n4max : (10 * N + 2 + 1) / 2;  // rd+tv also host eq[9N], qz[N]
   p.rd = take(nv); p.tv = take(nv);
-  p.rhs = take(n4max); p.du = take(n4max);
-  p.sl = take(mmax); p.zl = take(mmax); p.zu = take(mmax);
-  p.cdu = take(mmax); p.dzl = take(mmax); p.dzu = take(mmax);
+  p.rhs = take(n4max); p.du = take(n4max); p.dua = take(n4max);
+  p.zl = take(mmax); p.zu = take(mmax);
   p.red = take(W > 1 ? 3 * W : 2);
   p.exch = take(8);
   // bytes: blk_j, blk_i, rk [nbmax each], blk_of [N*L] (int8), actl, actu [mmax each];
@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(1024) classify_kernel(const DevConfig cfg, int
 // ------------------------------------------------------------------ the fused kernel
 // MODE 0: solve.  MODE 1: build-export (H, g in the full 3LN layout to global memory).
 template <int W, int MODE, bool MS>
-__global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 288 : 256)) cmpc_solve_kernel(const DevConfig cfg, const SolveArgs args) {
+__global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solve_kernel(const DevConfig cfg, const SolveArgs args) {
   extern __shared__ __align__(128) double smem[];
   constexpr int GT = Group<W>::GT;
   const int N = cfg.N, L = cfg.L, nu = 3 * L;
@@ -707,13 +707,9 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 288 : 256)) cmpc_solv
   double* s_up = s_du;   // polish only: candidate point (du is dead there; chol's rhs is tv)
   double* s_eq = s_rd;   // build only: 9N weighted errors then N z-weights, spanning rd..tv
   double* s_qz = s_rd + 9 * N;
-  double* s_sl = base + P.sl;
+  double* s_dua = base + P.dua;  // copy of the affine (predictor) direction
   double* s_zl = base + P.zl;
   double* s_zu = base + P.zu;
-  double* s_cdu = base + P.cdu;
-  double* s_dzl = base + P.dzl;
-  double* s_dzu = base + P.dzu;
-  double* s_Zt = s_cdu;  // polish only: 9 nb doubles <= cdu + dzl
   int* s_misc = reinterpret_cast<int*>(base + P.ints);  // [0]=nb, [1]=invalid, [2]=work slot, [3]=nr
   uint16_t* s_off = reinterpret_cast<uint16_t*>(s_misc + 4);
   uint16_t* s_tb = s_off + nbmax + (nbmax & 1);
@@ -727,6 +723,8 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 288 : 256)) cmpc_solv
   double* Hm = args.scratch + (size_t)group_global * args.scratch_per_group;
   double* Mm;
   if constexpr (MS) Mm = base + P.Mm; else Mm = Hm + mat_region_doubles(N, L, args.n4max);
+  // polish only: null-space bases, 9 doubles per leg-step, behind the matrices in the L2 slab
+  double* g_Zt = Hm + (size_t)mat_region_doubles(N, L, args.n4max) * (MS ? 1 : 2);
 
   const double dt = cfg.dt, mass = cfg.mass;
   const double zeta = cfg.zoh ? 0.5 : 0.0;
@@ -961,7 +959,7 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 288 : 256)) cmpc_solv
     if constexpr (!MS) copy_mat<W>(G, Mm, Hm, matd);
     G.sync();
     // (s_fz aliases s_rhs, s_arm aliases s_du, s_eq aliases s_rd/s_tv: all dead from here on)
-    if (gtid < n4 - n) { s_rhs[n + gtid] = 0.0; s_du[n + gtid] = 0.0; s_rd[n + gtid] = 0.0; s_tv[n + gtid] = 0.0; }
+    if (gtid < n4 - n) { s_rhs[n + gtid] = 0.0; s_du[n + gtid] = 0.0; s_dua[n + gtid] = 0.0; s_rd[n + gtid] = 0.0; s_tv[n + gtid] = 0.0; }
     symv_bc4<W>(G, Mm, n4, nblk, s_u, s_rd);
     double gmax = 0.0, r0max = 0.0;
     for (int t = gtid; t < n; t += GT) { gmax = fmax(gmax, fabs(s_g[t])); r0max = fmax(r0max, fabs(s_rd[t] + s_g[t])); }
@@ -976,7 +974,6 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 288 : 256)) cmpc_solv
       cmul5(mub, s_u + 3 * b, y);
       for (int q = 0; q < 5; ++q) {
         const double ub = q < 4 ? ubxy : ubz;
-        s_sl[5 * b + q] = y[q];
         s_zl[5 * b + q] = mu0 / y[q]; s_zu[5 * b + q] = mu0 / (ub - y[q]);
       }
     }
@@ -992,10 +989,11 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 288 : 256)) cmpc_solv
       double rmax = 0.0, umax = 0.0, gap = 0.0;
       for (int b = gtid; b < nb; b += GT) {
         const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
-        double w[5], o[3];
+        double w[5], o[3], ys[5];
+        cmul5(cfg.mu[s_blk_i[b]], s_u + 3 * b, ys);
         for (int q = 0; q < 5; ++q) {
           const int t = 5 * b + q;
-          const double sl = s_sl[t], su = (q < 4 ? ubxy : ubz) - sl;
+          const double sl = ys[q], su = (q < 4 ? ubxy : ubz) - sl;
           w[q] = s_zl[t] - s_zu[t];
           gap += sl * s_zl[t] + su * s_zu[t];
         }
@@ -1039,9 +1037,11 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 288 : 256)) cmpc_solv
           ++npolish;
           for (int b = gtid; b < nb; b += GT) {
             const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
+            double ys[5];
+            cmul5(cfg.mu[s_blk_i[b]], s_u + 3 * b, ys);
             for (int q = 0; q < 5; ++q) {
               const int t = 5 * b + q;
-              const double sl = s_sl[t], su = (q < 4 ? ubxy : ubz) - sl;
+              const double sl = ys[q], su = (q < 4 ? ubxy : ubz) - sl;
               const bool al = s_zl[t] * us > sl * gs, au = s_zu[t] * us > su * gs;
               s_actl[t] = al; s_actu[t] = au;
               any_act = any_act || al || au;
@@ -1075,7 +1075,7 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 288 : 256)) cmpc_solv
               s_rk[b] = rk;
               for (int q = 0; q < 3; ++q) s_f0[3 * b + q] = f0[q];
               for (int cc = 0; cc < 3 - rk; ++cc)
-                for (int q = 0; q < 3; ++q) s_Zt[9 * b + 3 * cc + q] = Z[cc][q];
+                for (int q = 0; q < 3; ++q) g_Zt[9 * b + 3 * cc + q] = Z[cc][q];
             }
             if (gtid < n4 - n) s_f0[n + gtid] = 0.0;
             ok_all = G.all(ok_all);
@@ -1102,8 +1102,8 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 288 : 256)) cmpc_solv
             }
             for (int b = gtid; b < nb; b += GT)
               for (int cc = 0; cc < 3 - s_rk[b]; ++cc) {
-                const double* z = s_Zt + 9 * b + 3 * cc;
-                s_tv[s_off[b] + cc] = -(z[0] * s_rhs[3 * b] + z[1] * s_rhs[3 * b + 1] + z[2] * s_rhs[3 * b + 2]);
+                const double* z = g_Zt + 9 * b + 3 * cc;
+                s_tv[s_off[b] + cc] = -(__ldcg(z) * s_rhs[3 * b] + __ldcg(z + 1) * s_rhs[3 * b + 1] + __ldcg(z + 2) * s_rhs[3 * b + 2]);
               }
             G.sync();
             if (gtid < nr4 - nr) { s_tv[nr + gtid] = 0.0; Mm[midx(nr + gtid, nr + gtid, nblk_r)] = 1.0; }
@@ -1115,14 +1115,18 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 288 : 256)) cmpc_solv
               const int b2 = idx - ((a * (a + 1)) >> 1), b = a;
               const int d1 = 3 - s_rk[b], d2 = 3 - s_rk[b2];
               if (d1 == 0 || d2 == 0) continue;
-              double Hb3[3][3];
+              double Hb3[3][3], Za[3][3], Zb[3][3];
               for (int aa = 0; aa < 3; ++aa)
-                for (int bb = 0; bb < 3; ++bb) Hb3[aa][bb] = __ldcg(Hm + sidx(3 * b + aa, 3 * b2 + bb, nblk));
+                for (int bb = 0; bb < 3; ++bb) {
+                  Hb3[aa][bb] = __ldcg(Hm + sidx(3 * b + aa, 3 * b2 + bb, nblk));
+                  Za[aa][bb] = aa < d1 ? __ldcg(g_Zt + 9 * b + 3 * aa + bb) : 0.0;
+                  Zb[aa][bb] = aa < d2 ? __ldcg(g_Zt + 9 * b2 + 3 * aa + bb) : 0.0;
+                }
               for (int cc = 0; cc < d1; ++cc)
                 for (int c2 = 0; c2 < d2; ++c2) {
                   if (b == b2 && c2 > cc) continue;  // lower part of the diagonal block; mirrored below
-                  const double* z = s_Zt + 9 * b + 3 * cc;
-                  const double* z2 = s_Zt + 9 * b2 + 3 * c2;
+                  const double* z = Za[cc];
+                  const double* z2 = Zb[c2];
                   double sacc = 0.0;
                   for (int aa = 0; aa < 3; ++aa)
                     for (int bb = 0; bb < 3; ++bb) sacc += z[aa] * Hb3[aa][bb] * z2[bb];
@@ -1160,7 +1164,7 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 288 : 256)) cmpc_solv
             } else {
               for (int cc = 0; cc < 3 - s_rk[b]; ++cc) {
                 const double tv = s_tv[s_off[b] + cc];
-                for (int q = 0; q < 3; ++q) f[q] += s_Zt[9 * b + 3 * cc + q] * tv;
+                for (int q = 0; q < 3; ++q) f[q] += __ldcg(g_Zt + 9 * b + 3 * cc + q) * tv;
               }
             }
             for (int q = 0; q < 3; ++q) s_up[3 * b + q] = f[q];
@@ -1170,48 +1174,55 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 288 : 256)) cmpc_solv
           m_is_h = true;
           G.sync();
           symv_bc4<W>(G, Mm, n4, nblk, s_up, s_rhs);
-          // multipliers, verification, correction
-          bool okm = true, changed = false, any_act2 = false;
-          for (int b = gtid; b < nb; b += GT) {
-            const double mub = cfg.mu[s_blk_i[b]];
-            const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
-            double rb[3], y[5], ll[5] = {0, 0, 0, 0, 0}, lu[5] = {0, 0, 0, 0, 0};
-            for (int q = 0; q < 3; ++q) rb[q] = s_rhs[3 * b + q] + s_g[3 * b + q];
-            if (none_active) {
-              okm = okm && fmax(fabs(rb[0]), fmax(fabs(rb[1]), fabs(rb[2]))) <= 1e-9 * gs;
-            } else {
-              double Nrm[10][3], lam[10];
-              int idx[10], k = 0;
-              for (int q = 0; q < 5; ++q) if (s_actl[5 * b + q]) { row_vec(mub, q, Nrm[k]); idx[k++] = q; }
-              for (int q = 0; q < 5; ++q) if (s_actu[5 * b + q]) {
-                row_vec(mub, q, Nrm[k]);
-                Nrm[k][0] = -Nrm[k][0]; Nrm[k][1] = -Nrm[k][1]; Nrm[k][2] = -Nrm[k][2];
-                idx[k++] = 5 + q;
+          // multipliers, verification, correction; when the pass verifies, the same loop runs a
+          // second time to commit the multipliers (nothing is stored per row in between)
+          bool good = false;
+          for (int commit = 0; commit < 2; ++commit) {
+            bool okm = true, changed = false, any_act2 = false;
+            for (int b = gtid; b < nb; b += GT) {
+              const double mub = cfg.mu[s_blk_i[b]];
+              const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
+              double rb[3], y[5], ll[5] = {0, 0, 0, 0, 0}, lu[5] = {0, 0, 0, 0, 0};
+              for (int q = 0; q < 3; ++q) rb[q] = s_rhs[3 * b + q] + s_g[3 * b + q];
+              if (none_active) {
+                okm = okm && fmax(fabs(rb[0]), fmax(fabs(rb[1]), fabs(rb[2]))) <= 1e-9 * gs;
+              } else {
+                double Nrm[10][3], lam[10];
+                int idx[10], k = 0;
+                for (int q = 0; q < 5; ++q) if (s_actl[5 * b + q]) { row_vec(mub, q, Nrm[k]); idx[k++] = q; }
+                for (int q = 0; q < 5; ++q) if (s_actu[5 * b + q]) {
+                  row_vec(mub, q, Nrm[k]);
+                  Nrm[k][0] = -Nrm[k][0]; Nrm[k][1] = -Nrm[k][1]; Nrm[k][2] = -Nrm[k][2];
+                  idx[k++] = 5 + q;
+                }
+                okm = block_multipliers(k, Nrm, rb, 1e-9 * gs, lam) && okm;
+                for (int sI = 0; sI < k; ++sI) { if (idx[sI] < 5) ll[idx[sI]] = lam[sI]; else lu[idx[sI] - 5] = lam[sI]; }
               }
-              okm = block_multipliers(k, Nrm, rb, 1e-9 * gs, lam) && okm;
-              for (int sI = 0; sI < k; ++sI) { if (idx[sI] < 5) ll[idx[sI]] = lam[sI]; else lu[idx[sI] - 5] = lam[sI]; }
+              if (commit) {
+                for (int q = 0; q < 5; ++q) { s_zl[5 * b + q] = ll[q]; s_zu[5 * b + q] = lu[q]; }
+                continue;
+              }
+              cmul5(mub, s_up + 3 * b, y);
+              for (int q = 0; q < 5; ++q) {
+                const double ub = q < 4 ? ubxy : ubz;
+                const double sl = y[q], su = ub - y[q];
+                const bool vl = sl < -1e-9 * us, vu = su < -1e-9 * us;
+                const bool nl = ll[q] < -1e-9 * gs, nuu = lu[q] < -1e-9 * gs;
+                if (vl || vu || nl || nuu) changed = true;
+                const bool al = (s_actl[5 * b + q] || vl) && !nl, au = (s_actu[5 * b + q] || vu) && !nuu;
+                s_actl[5 * b + q] = al; s_actu[5 * b + q] = au;
+                any_act2 = any_act2 || al || au;
+              }
             }
-            cmul5(mub, s_up + 3 * b, y);
-            for (int q = 0; q < 5; ++q) {
-              const double ub = q < 4 ? ubxy : ubz;
-              const double sl = y[q], su = ub - y[q];
-              const bool vl = sl < -1e-9 * us, vu = su < -1e-9 * us;
-              const bool nl = ll[q] < -1e-9 * gs, nuu = lu[q] < -1e-9 * gs;
-              if (vl || vu || nl || nuu) changed = true;
-              const bool al = (s_actl[5 * b + q] || vl) && !nl, au = (s_actu[5 * b + q] || vu) && !nuu;
-              s_actl[5 * b + q] = al; s_actu[5 * b + q] = au;
-              any_act2 = any_act2 || al || au;
-              s_cdu[5 * b + q] = sl;   // candidate slacks / multipliers, committed on accept
-              s_dzl[5 * b + q] = ll[q]; s_dzu[5 * b + q] = lu[q];
-            }
+            if (commit) break;
+            good = G.all(okm && !changed);
+            none_active = G.all(!any_act2);  // unchanged when the pass verified (flags did not move)
+            if (!good) break;
           }
-          const bool good = G.all(okm && !changed);
-          none_active = G.all(!any_act2);
           if (good) accepted = true;
         }
         if (accepted) {
           for (int t = gtid; t < n; t += GT) s_u[t] = s_up[t];
-          for (int t = gtid; t < m; t += GT) { s_sl[t] = s_cdu[t]; s_zl[t] = s_dzl[t]; s_zu[t] = s_dzu[t]; }
           G.sync();
           status = CMPC_STATUS_OK;
           break;
@@ -1236,10 +1247,11 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 288 : 256)) cmpc_solv
       // affine (predictor) right-hand side  -rd + C'(rcl/sl - rcu/su)  with rc = -s z
       for (int b = gtid; b < nb; b += GT) {
         const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
-        double sg[5], tq[5], o[3];
+        double sg[5], tq[5], o[3], ys[5];
+        cmul5(cfg.mu[s_blk_i[b]], s_u + 3 * b, ys);
         for (int q = 0; q < 5; ++q) {
           const int t = 5 * b + q;
-          const double sl = s_sl[t], su = (q < 4 ? ubxy : ubz) - sl;
+          const double sl = ys[q], su = (q < 4 ? ubxy : ubz) - sl;
           const double isl = fast_rcp(sl), isu = fast_rcp(su);
           sg[q] = s_zl[t] * isl + s_zu[t] * isu;
           tq[q] = s_zu[t] - s_zl[t];
@@ -1259,21 +1271,31 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 288 : 256)) cmpc_solv
       // factor; the predictor's forward substitution is fused into the sweep
       if (!chol_bc4<W>(G, Mm, nblk, s_tb, s_du, s_exch)) { numerical = true; break; }
 
+      // Per-row step quantities are recomputed where needed instead of stored: with s = slack,
+      // z = multiplier, cd = a_r . du:  dz_l = (rc_l - z_l cd) / s_l,  dz_u = (rc_u + z_u cd) / s_u,
+      // rc = -s z  (+ sigma mu -/+ cdA dzA in the corrector, A = affine step kept in dua).
       double tmax = 0.0, sigma = 0.0;
       for (int phase = 0; phase < 2; ++phase) {
         // phase 0: affine predictor; phase 1: centred corrector (Mehrotra)
         if (phase) {
+          for (int t = gtid; t < n4; t += GT) s_dua[t] = s_du[t];
+          G.sync();
           for (int b = gtid; b < nb; b += GT) {
+            const double mub = cfg.mu[s_blk_i[b]];
             const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
-            double tq[5], o[3];
+            double tq[5], o[3], ys[5], ya[5];
+            cmul5(mub, s_u + 3 * b, ys);
+            cmul5(mub, s_dua + 3 * b, ya);
             for (int q = 0; q < 5; ++q) {
               const int t = 5 * b + q;
-              const double sl = s_sl[t], su = (q < 4 ? ubxy : ubz) - sl;
-              const double rcl = -sl * s_zl[t] + sigma * mu - s_cdu[t] * s_dzl[t];
-              const double rcu = -su * s_zu[t] + sigma * mu + s_cdu[t] * s_dzu[t];
-              tq[q] = rcl * fast_rcp(sl) - rcu * fast_rcp(su);
+              const double sl = ys[q], su = (q < 4 ? ubxy : ubz) - sl, zl = s_zl[t], zu = s_zu[t];
+              const double isl = fast_rcp(sl), isu = fast_rcp(su);
+              const double dla = (-sl * zl - zl * ya[q]) * isl, dua_ = (-su * zu + zu * ya[q]) * isu;
+              const double rcl = -sl * zl + sigma * mu - ya[q] * dla;
+              const double rcu = -su * zu + sigma * mu + ya[q] * dua_;
+              tq[q] = rcl * isl - rcu * isu;
             }
-            ctmul5(cfg.mu[s_blk_i[b]], tq, o);
+            ctmul5(mub, tq, o);
             for (int q = 0; q < 3; ++q) s_du[3 * b + q] = -s_rd[3 * b + q] + o[q];
           }
           G.sync();
@@ -1283,21 +1305,26 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 288 : 256)) cmpc_solv
         // step to the boundary: alpha_max = 1 / max_i(-ds_i/s_i, -dz_i/z_i)
         double tloc = 0.0;
         for (int b = gtid; b < nb; b += GT) {
+          const double mub = cfg.mu[s_blk_i[b]];
           const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
-          double y[5];
-          cmul5(cfg.mu[s_blk_i[b]], s_du + 3 * b, y);
+          double ys[5], yd[5], ya[5];
+          cmul5(mub, s_u + 3 * b, ys);
+          cmul5(mub, s_du + 3 * b, yd);
+          if (phase) cmul5(mub, s_dua + 3 * b, ya);
           for (int q = 0; q < 5; ++q) {
             const int t = 5 * b + q;
-            const double sl = s_sl[t], su = (q < 4 ? ubxy : ubz) - sl, zl = s_zl[t], zu = s_zu[t];
-            double rcl = -sl * zl, rcu = -su * zu;
-            if (phase) { rcl += sigma * mu - s_cdu[t] * s_dzl[t]; rcu += sigma * mu + s_cdu[t] * s_dzu[t]; }
-            const double cd = y[q];
+            const double sl = ys[q], su = (q < 4 ? ubxy : ubz) - sl, zl = s_zl[t], zu = s_zu[t];
             const double isl = fast_rcp(sl), isu = fast_rcp(su);
+            double rcl = -sl * zl, rcu = -su * zu;
+            if (phase) {
+              const double dla = (rcl - zl * ya[q]) * isl, dua_ = (rcu + zu * ya[q]) * isu;
+              rcl += sigma * mu - ya[q] * dla; rcu += sigma * mu + ya[q] * dua_;
+            }
+            const double cd = yd[q];
             const double dl = (rcl - zl * cd) * isl;
             const double du_ = (rcu + zu * cd) * isu;
             tloc = fmax(tloc, fmax(-cd * isl, cd * isu));
             tloc = fmax(tloc, fmax(-dl * fast_rcp(zl), -du_ * fast_rcp(zu)));
-            s_cdu[t] = cd; s_dzl[t] = dl; s_dzu[t] = du_;
           }
         }
         tmax = G.max(tloc);
@@ -1305,11 +1332,17 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 288 : 256)) cmpc_solv
           const double alpha = tmax > 1.0 ? 1.0 / tmax : 1.0;
           double ga = 0.0;
           for (int b = gtid; b < nb; b += GT) {
+            const double mub = cfg.mu[s_blk_i[b]];
             const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
+            double ys[5], yd[5];
+            cmul5(mub, s_u + 3 * b, ys);
+            cmul5(mub, s_du + 3 * b, yd);
             for (int q = 0; q < 5; ++q) {
               const int t = 5 * b + q;
-              const double sl = s_sl[t], su = (q < 4 ? ubxy : ubz) - sl;
-              ga += (sl + alpha * s_cdu[t]) * (s_zl[t] + alpha * s_dzl[t]) + (su - alpha * s_cdu[t]) * (s_zu[t] + alpha * s_dzu[t]);
+              const double sl = ys[q], su = (q < 4 ? ubxy : ubz) - sl, zl = s_zl[t], zu = s_zu[t];
+              const double cd = yd[q];
+              const double dl = (-sl * zl - zl * cd) * fast_rcp(sl), du_ = (-su * zu + zu * cd) * fast_rcp(su);
+              ga += (sl + alpha * cd) * (zl + alpha * dl) + (su - alpha * cd) * (zu + alpha * du_);
             }
           }
           ga = G.sum(ga);
@@ -1322,16 +1355,25 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 288 : 256)) cmpc_solv
       const double alpha = fmin(1.0, tau / fmax(tmax, 1e-300));
       bool fin = true;
       for (int b = gtid; b < nb; b += GT) {
-        double y[5];
+        const double mub = cfg.mu[s_blk_i[b]];
+        const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
+        double ys[5], yd[5], ya[5];
+        cmul5(mub, s_u + 3 * b, ys);       // slacks at the current point (before the update)
+        cmul5(mub, s_du + 3 * b, yd);
+        cmul5(mub, s_dua + 3 * b, ya);
+        for (int q = 0; q < 5; ++q) {
+          const int t = 5 * b + q;
+          const double sl = ys[q], su = (q < 4 ? ubxy : ubz) - sl, zl = s_zl[t], zu = s_zu[t];
+          const double isl = fast_rcp(sl), isu = fast_rcp(su);
+          const double dla = (-sl * zl - zl * ya[q]) * isl, dua_ = (-su * zu + zu * ya[q]) * isu;
+          const double rcl = -sl * zl + sigma * mu - ya[q] * dla;
+          const double rcu = -su * zu + sigma * mu + ya[q] * dua_;
+          s_zl[t] = zl + alpha * (rcl - zl * yd[q]) * isl;
+          s_zu[t] = zu + alpha * (rcu + zu * yd[q]) * isu;
+        }
         for (int q = 0; q < 3; ++q) {
           const double v = s_u[3 * b + q] + alpha * s_du[3 * b + q];
           s_u[3 * b + q] = v; fin = fin && isfinite(v);
-        }
-        cmul5(cfg.mu[s_blk_i[b]], s_u + 3 * b, y);
-        for (int q = 0; q < 5; ++q) {
-          const int t = 5 * b + q;
-          s_zl[t] += alpha * s_dzl[t]; s_zu[t] += alpha * s_dzu[t];
-          s_sl[t] = y[q];
         }
       }
       fin = G.all(fin);
@@ -1365,7 +1407,6 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 288 : 256)) cmpc_solv
           prim = fmax(prim, fmax(-sl, -su));
           dual = fmax(dual, fmax(-zl, -zu));
           comp = fmax(comp, fmax(fabs(zl * sl), fabs(zu * su)));
-          s_sl[5 * b + q] = sl;
         }
       }
       stat = G.max(stat);
@@ -1380,9 +1421,11 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 288 : 256)) cmpc_solv
       // redundant rows at the degenerate apex f = 0). Otherwise: the IPM guess.
       for (int b = gtid; b < nb; b += GT) {
         const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
+        double ys[5];
+        cmul5(cfg.mu[s_blk_i[b]], s_u + 3 * b, ys);
         for (int q = 0; q < 5; ++q) {
           const int t = 5 * b + q;
-          const double sl = s_sl[t], su = (q < 4 ? ubxy : ubz) - sl;
+          const double sl = ys[q], su = (q < 4 ? ubxy : ubz) - sl;
           if (status == CMPC_STATUS_OK) { s_actl[t] = sl <= 1e-9 * usf; s_actu[t] = su <= 1e-9 * usf; }
           else { s_actl[t] = s_zl[t] * usf > sl * gs; s_actu[t] = s_zu[t] * usf > su * gs; }
         }
