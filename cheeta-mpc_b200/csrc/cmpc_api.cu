@@ -26,6 +26,10 @@ struct cmpc_handle {
   bool own_stream = false;
   bool zero_copy = true;  // CMPC_NO_ZEROCOPY=1 forces the staged-copy path
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // chunked, overlapped staging of cmpc_solve_batch: copy-in / compute / copy-out pipelines
+  static constexpr int kMaxChunks = 8;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {}, ev_span[4] = {};
   // device buffers
   double *d_state = nullptr, *d_ds = nullptr, *d_di = nullptr, *d_forces = nullptr, *d_kkt = nullptr,
          *d_lam = nullptr, *d_flog = nullptr, *d_hip = nullptr;
@@ -445,6 +449,11 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
   h->num_sms = prop.multiProcessorCount;
   if (!h->stream) { CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
   for (auto& e : h->ev) CUDA_TRY(h, cudaEventCreate(&e));
+  CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+  CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+  for (auto& e : h->ev_in) CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : h->ev_k) CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : h->ev_span) CUDA_TRY(h, cudaEventCreate(&e));
 
   const int N = h->cfg.horizon, L = h->cfg.num_legs;
   const size_t ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = (size_t)L * (4 * N + 3), nf = (size_t)3 * L * N;
@@ -605,35 +614,59 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
       return CMPC_OK;
     }
   }
-  CUDA_TRY(h, cudaEventRecord(h->ev[0], s));
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_state, state, B * ns * 8, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_ds, des_state, B * nds * 8, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_di, des_inputs, B * ndi * 8, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(h, cudaEventRecord(h->ev[1], s));
-  SolveArgs a = base_args(h, B);
-  a.state = h->d_state; a.des_state = h->d_ds; a.des_inputs = h->d_di;
-  a.forces = h->d_forces; a.status = h->d_status; a.iters = h->d_iters; a.kkt = h->d_kkt;
-  a.lam = lam ? h->d_lam : nullptr; a.active = active ? h->d_active : nullptr;
-  int rc = launch_solve(h, a, B);
-  if (rc < 0) return rc;
-  const int launches = rc;
-  CUDA_TRY(h, cudaEventRecord(h->ev[2], s));
-  CUDA_TRY(h, cudaMemcpyAsync(forces, h->d_forces, B * nf * 8, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(h, cudaMemcpyAsync(status, h->d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-  if (iters) CUDA_TRY(h, cudaMemcpyAsync(iters, h->d_iters, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-  if (kkt) CUDA_TRY(h, cudaMemcpyAsync(kkt, h->d_kkt, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
-  if (lam) CUDA_TRY(h, cudaMemcpyAsync(lam, h->d_lam, (size_t)B * 10 * L * N * 8, cudaMemcpyDeviceToHost, s));
-  if (active) CUDA_TRY(h, cudaMemcpyAsync(active, h->d_active, (size_t)B * L * N * 2, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(h, cudaEventRecord(h->ev[3], s));
+  // Staged path, pipelined in chunks of one resident wave: the copy-in of chunk c+1 and the
+  // copy-out of chunk c-1 run on their own streams (both DMA directions) while chunk c computes.
+  const int wave = std::max(1, h->cls[0].used ? h->cls[0].grid * h->cls[0].groups : h->num_sms);
+  int nch = (B + wave - 1) / wave;
+  if (nch > cmpc_handle::kMaxChunks) nch = cmpc_handle::kMaxChunks;
+  const int per = ((B + nch - 1) / nch + 31) & ~31;
+  nch = (B + per - 1) / per;
+  CUDA_TRY(h, cudaEventRecord(h->ev_span[0], s));
+  CUDA_TRY(h, cudaStreamWaitEvent(h->s_in, h->ev_span[0], 0));   // order behind earlier work of the caller's stream
+  CUDA_TRY(h, cudaStreamWaitEvent(h->s_out, h->ev_span[0], 0));
+  int launches = 0;
+  for (int c = 0; c < nch; ++c) {
+    const size_t o = (size_t)c * per;
+    const size_t nbc = std::min<size_t>(per, (size_t)B - o);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_state + o * ns, state + o * ns, nbc * ns * 8, cudaMemcpyHostToDevice, h->s_in));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_ds + o * nds, des_state + o * nds, nbc * nds * 8, cudaMemcpyHostToDevice, h->s_in));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_di + o * ndi, des_inputs + o * ndi, nbc * ndi * 8, cudaMemcpyHostToDevice, h->s_in));
+    CUDA_TRY(h, cudaEventRecord(h->ev_in[c], h->s_in));
+  }
+  CUDA_TRY(h, cudaEventRecord(h->ev_span[1], h->s_in));
+  for (int c = 0; c < nch; ++c) {
+    const size_t o = (size_t)c * per;
+    const int nbc = (int)std::min<size_t>(per, (size_t)B - o);
+    CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_in[c], 0));
+    SolveArgs a = base_args(h, nbc);
+    a.state = h->d_state + o * ns; a.des_state = h->d_ds + o * nds; a.des_inputs = h->d_di + o * ndi;
+    a.forces = h->d_forces + o * nf; a.status = h->d_status + o; a.iters = h->d_iters + o; a.kkt = h->d_kkt + o;
+    a.lam = lam ? h->d_lam + o * 10 * L * N : nullptr; a.active = active ? h->d_active + o * L * N : nullptr;
+    int rc = launch_solve(h, a, nbc);
+    if (rc < 0) return rc;
+    launches += rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev_k[c], s));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->s_out, h->ev_k[c], 0));
+    CUDA_TRY(h, cudaMemcpyAsync(forces + o * nf, h->d_forces + o * nf, (size_t)nbc * nf * 8, cudaMemcpyDeviceToHost, h->s_out));
+    CUDA_TRY(h, cudaMemcpyAsync(status + o, h->d_status + o, (size_t)nbc * 4, cudaMemcpyDeviceToHost, h->s_out));
+    if (iters) CUDA_TRY(h, cudaMemcpyAsync(iters + o, h->d_iters + o, (size_t)nbc * 4, cudaMemcpyDeviceToHost, h->s_out));
+    if (kkt) CUDA_TRY(h, cudaMemcpyAsync(kkt + o, h->d_kkt + o, (size_t)nbc * 8, cudaMemcpyDeviceToHost, h->s_out));
+    if (lam) CUDA_TRY(h, cudaMemcpyAsync(lam + o * 10 * L * N, h->d_lam + o * 10 * L * N, (size_t)nbc * 10 * L * N * 8, cudaMemcpyDeviceToHost, h->s_out));
+    if (active) CUDA_TRY(h, cudaMemcpyAsync(active + o * L * N, h->d_active + o * L * N, (size_t)nbc * L * N * 2, cudaMemcpyDeviceToHost, h->s_out));
+  }
+  CUDA_TRY(h, cudaEventRecord(h->ev_span[2], s));
+  CUDA_TRY(h, cudaEventRecord(h->ev_span[3], h->s_out));
+  CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_span[3], 0));  // the caller's stream observes completion
+  CUDA_TRY(h, cudaStreamSynchronize(h->s_out));
   CUDA_TRY(h, cudaStreamSynchronize(s));
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
-    rc = collect_stats(h, B, h->d_status, h->d_iters, h->d_kkt, stats, launches);
+    int rc = collect_stats(h, B, h->d_status, h->d_iters, h->d_kkt, stats, launches);
     if (rc) return rc;
     float t0 = 0, t1 = 0, t2 = 0;
-    CUDA_TRY(h, cudaEventElapsedTime(&t0, h->ev[0], h->ev[1]));
-    CUDA_TRY(h, cudaEventElapsedTime(&t1, h->ev[1], h->ev[2]));
-    CUDA_TRY(h, cudaEventElapsedTime(&t2, h->ev[2], h->ev[3]));
+    CUDA_TRY(h, cudaEventElapsedTime(&t0, h->ev_span[0], h->ev_span[1]));  // copy-in pipeline span
+    CUDA_TRY(h, cudaEventElapsedTime(&t1, h->ev_span[0], h->ev_span[2]));  // until the last kernel ended
+    CUDA_TRY(h, cudaEventElapsedTime(&t2, h->ev_span[2], h->ev_span[3]));  // copy-out tail after it
     stats->h2d_ms = t0; stats->kernel_ms = t1; stats->d2h_ms = t2;
   }
   return CMPC_OK;
@@ -877,6 +910,11 @@ void cmpc_destroy(cmpc_handle* h) {
   cudaFree(h->d_status); cudaFree(h->d_iters);
   cudaFree(h->d_iters_sum); cudaFree(h->d_status_or); cudaFree(h->d_active); cudaFree(h->d_stats);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : h->ev_in) if (e) cudaEventDestroy(e);
+  for (auto& e : h->ev_k) if (e) cudaEventDestroy(e);
+  for (auto& e : h->ev_span) if (e) cudaEventDestroy(e);
+  if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
