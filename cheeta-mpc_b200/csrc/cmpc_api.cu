@@ -329,6 +329,7 @@ template <int MODE>
 int launch_class(cmpc_handle* h, const cmpc_handle::ClassPlan& p, SolveArgs a) {
   a.scratch = p.d_scratch; a.scratch_per_group = p.scratch_per_group;
   a.nbmax = p.nbmax; a.n4max = p.n4max; a.m_in_smem = p.m_in_smem; a.groups = p.groups;
+  a.plan = make_plan(h->cfg.horizon, h->cfg.num_legs, p.m_in_smem ? p.W : 8, p.nbmax, p.n4max, p.m_in_smem);
   cudaError_t e;
   if (MODE == 1 || !p.m_in_smem) e = launch_w<8, MODE, false>(h, p, a);
   else if constexpr (MODE == 0) e = p.W == 1 ? launch_w<1, 0, true>(h, p, a) : p.W == 2 ? launch_w<2, 0, true>(h, p, a) : p.W == 4 ? launch_w<4, 0, true>(h, p, a) : launch_w<8, 0, true>(h, p, a);

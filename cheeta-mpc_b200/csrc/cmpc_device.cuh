@@ -41,6 +41,13 @@ struct DevConfig {
   int L, N, zoh, max_iter, polish;
 };
 
+struct SmemPlan {
+  // offsets in doubles from the start of the group's slab
+  int ce, g, u, rd, tv, rhs, du, dua;
+  int zl, zu, red, exch, ints, Mm;
+  int total;  // doubles, multiple of 2
+};
+
 // One launch = one size class.
 struct SolveArgs {
   const double* state;
@@ -65,6 +72,7 @@ struct SolveArgs {
   int n4max;                 // padded free dimension bound of the class
   int m_in_smem;
   int groups;                // groups per CTA
+  SmemPlan plan;             // shared-memory layout of one group, computed on the host
 };
 
 // ------------------------------------------------------------------ BC4 layout
@@ -603,12 +611,6 @@ __device__ __noinline__ bool block_multipliers(int k, const double (*Nrm)[3], co
 // polish's null-space bases live in the group's L2 slab.  Aliases (lifetimes do not overlap):
 // eq/qz (build only) in rd..tv; the lever arms (build only) and the polish's candidate point `up`
 // in du; the desired fz (build + start point) in rhs.  2886 doubles at nb <= 20, N = 10: 10 groups/SM.
-struct SmemPlan {
-  // offsets in doubles from the start of the group's slab
-  int ce, g, u, rd, tv, rhs, du, dua;
-  int zl, zu, red, exch, ints, Mm;
-  int total;  // doubles, multiple of 2
-};
 __host__ __device__ inline SmemPlan make_plan(int N, int L, int W, int nbmax, int n4max, int m_in_smem) {
   SmemPlan p;
   const int mmax = 5 * nbmax;
@@ -686,7 +688,7 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solv
   const int ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = L * (4 * N + 3), nf = 3 * L * N;
   const int nbfull = L * N, mfull = 5 * nbfull;
   const int nbmax = args.nbmax, mmax = 5 * nbmax;
-  const SmemPlan P = make_plan(N, L, W, nbmax, args.n4max, MS ? 1 : 0);
+  const SmemPlan& P = args.plan;
   Group<W> G;
   G.gtid = threadIdx.x % GT;
   G.gid = threadIdx.x / GT;
@@ -757,26 +759,35 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solv
     const double* g_dam = g_ds + 6 * (N + 1);
     finite = G.all(finite);
 
-    // ---- contact table -> free blocks; validity (CentroidalMPC.cpp:328-330)
-    if (gtid == 0) {
-      int nb = 0, invalid = 0;
-      for (int j = 0; j < N; ++j) {
-        double colsum = 0.0;
-        for (int i = 0; i < L; ++i) colsum += g_di[i * (4 * N + 3) + j];
-        if (!(colsum > 0.0)) invalid = 1;
+    // ---- contact table -> free blocks; validity (CentroidalMPC.cpp:328-330).  Lane j of the
+    // group's first warp owns step j (N <= 32): column sum, stance count, exclusive prefix by
+    // shuffles, then it numbers its own stance legs.
+    if (gtid < 32) {
+      const int j = gtid;
+      double colsum = 0.0;
+      int cnt = 0;
+      if (j < N)
+        for (int i = 0; i < L; ++i) { const double ce = g_di[i * (4 * N + 3) + j]; colsum += ce; cnt += ce > 0.0 ? 1 : 0; }
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (gtid >= o) incl += v; }
+      const unsigned bad = __ballot_sync(0xffffffffu, j < N && !(colsum > 0.0));
+      const int total = __shfl_sync(0xffffffffu, incl, N - 1);
+      if (j < N) {
+        int b = incl - cnt;
         for (int i = 0; i < L; ++i) {
           const double ce = g_di[i * (4 * N + 3) + j];
-          if (ce > 0.0 && nb < nbmax) {
-            s_blk_j[nb] = j; s_blk_i[nb] = i; s_blk_of[j * L + i] = nb;
-            s_ce[nb] = ce;
-            s_fz[nb] = (colsum > 0.0) ? mass * kGrav / colsum : 0.0;  // desired fz, :331-333
-            ++nb;
+          if (ce > 0.0 && b < nbmax) {
+            s_blk_j[b] = j; s_blk_i[b] = i; s_blk_of[j * L + i] = b;
+            s_ce[b] = ce;
+            s_fz[b] = (colsum > 0.0) ? mass * kGrav / colsum : 0.0;  // desired fz, :331-333
+            ++b;
           } else {
             s_blk_of[j * L + i] = -1;
           }
         }
       }
-      s_misc[0] = nb; s_misc[1] = invalid;
+      if (gtid == 0) { s_misc[0] = total < nbmax ? total : nbmax; s_misc[1] = bad != 0u; }
     }
     // zero-input rollout (closed form of x_k = A^k x0 + sum A^p d) and e = Q (x - x_ref), nodes 1..N
     for (int k = gtid; k < N; k += GT) {
