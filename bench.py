@@ -99,7 +99,7 @@ def run_reference(args):
         return
     pkg = ge.load_package()
     wl = pkg.workloads
-    cfg = wl.default_config(horizon=args.horizon)
+    cfg = dict(wl.default_config(horizon=args.horizon), presolve=args.presolve)
     nsample = 1024
     st, ds, di = wl.make_batch(cfg, nsample)
     orc = ge.load_oracle()
@@ -136,6 +136,8 @@ def main():
     ap.add_argument("--gaits", default="trot")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--presolve", type=int, default=1, choices=[0, 1],
+                    help="1 (library default): unconstrained minimiser tried first, IPM only for the rest; 0: IPM for all")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -155,7 +157,7 @@ def main():
 
     pkg = ge.load_package()
     wl = pkg.workloads
-    cfg = wl.default_config(horizon=args.horizon)
+    cfg = dict(wl.default_config(horizon=args.horizon), presolve=args.presolve)
     gaits = tuple(args.gaits.split(","))
     B = args.batch
     # rank r owns instance ids [r*B, (r+1)*B): contiguous block split, no inter-GPU traffic
@@ -233,6 +235,32 @@ def main():
     assert np.array_equal(h_forces.numpy(), forces0), "e2e path disagrees with device-resident path"
     sampler.stop_flag = True
 
+    # ---- the same step with the presolve switched off (every instance through the interior-point
+    # kernel): reported beside the headline so the two routes can be compared
+    ipm_only = None
+    if args.presolve and world == 1:
+        m2 = pkg.CentroidalMPC.from_dict(dict(cfg, presolve=0), device=local_rank)
+        m2.SetupMPC(B)
+        m2.set_stream(stream.cuda_stream)
+
+        def step2():
+            m2.solve_device(B, d_st.data_ptr(), d_ds.data_ptr(), d_di.data_ptr(), d_forces.data_ptr(),
+                            d_status.data_ptr(), d_iters.data_ptr(), d_kkt.data_ptr())
+        for _ in range(3):
+            step2()
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 50))]
+        for s0, s1 in ev2:
+            flush.fill_(1)
+            s0.record(stream)
+            step2()
+            s1.record(stream)
+        torch.cuda.synchronize()
+        ms2 = float(np.median([a.elapsed_time(b) for a, b in ev2]))
+        it2 = float(d_iters.cpu().numpy().mean())
+        assert np.abs(d_forces.cpu().numpy() - forces0).max() <= 1e-6 * np.abs(forces0).max()
+        ipm_only = {"value": B / (ms2 * 1e-3), "unit": UNIT, "p50_batch_latency_ms": ms2, "mean_ipm_iters": it2}
+        m2.close()
+
     t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -284,6 +312,12 @@ def main():
                                  "bytes_per_solve": in_bytes + out_bytes}},
             "clocks": sampler.summary(),
         }
+        if ipm_only is not None:
+            f2 = alg_flops_per_solve(n_free, ipm_only["mean_ipm_iters"], n_free)
+            ipm_only["roofline_frac"] = f2 * B / (ipm_only["p50_batch_latency_ms"] * 1e-3) / 1e12 / fp64_peak
+            ipm_only["flops_per_solve"] = f2
+            line["ipm_only"] = ipm_only
+        line["config"]["presolve"] = args.presolve
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(pkg, cfg, st, ds, di)
         print(json.dumps(line))

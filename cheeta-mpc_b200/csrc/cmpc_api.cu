@@ -42,9 +42,14 @@ struct cmpc_handle {
     int W = 1, groups = 1, grid = 0, nbmax = 0, n4max = 0, m_in_smem = 1;
     size_t smem_bytes = 0, scratch_per_group = 0;
     double* d_scratch = nullptr;
+    // presolve kernel of the class (cmpc_presolve_kernel): more groups per CTA, H-only scratch
+    bool pre_used = false;
+    int pre_groups = 0;
+    size_t pre_smem_bytes = 0, pre_scratch_per_group = 0;
+    double* d_pre_scratch = nullptr;
   } cls[kNumClasses], exp_plan;
   int4 bounds = {0, 0, 0, 0};
-  int32_t *d_counts = nullptr, *d_perm = nullptr;  // counts[4] then work[4]
+  int32_t *d_counts = nullptr, *d_perm = nullptr;  // counts[4], work[4], then the presolve's deferred counts[4], work[4]; perm [2][4][B]
   std::string err;
 };
 
@@ -338,17 +343,46 @@ int launch_class(cmpc_handle* h, const cmpc_handle::ClassPlan& p, SolveArgs a) {
   return CMPC_OK;
 }
 
-// classify + one launch per used size class. Returns the number of kernels launched (<0: error).
+template <int W>
+cudaError_t launch_pre_w(cmpc_handle* h, const cmpc_handle::ClassPlan& p, const SolveArgs& a) {
+  cmpc_presolve_kernel<W><<<p.grid, 32 * W * p.pre_groups, p.pre_smem_bytes, h->stream>>>(h->dev, a);
+  return cudaGetLastError();
+}
+
+int launch_presolve(cmpc_handle* h, const cmpc_handle::ClassPlan& p, SolveArgs a) {
+  a.scratch = p.d_pre_scratch; a.scratch_per_group = p.pre_scratch_per_group;
+  a.nbmax = p.nbmax; a.n4max = p.n4max; a.m_in_smem = 1; a.groups = p.pre_groups;
+  a.plan = make_pre_plan(h->cfg.horizon, h->cfg.num_legs, p.W, p.nbmax, p.n4max);
+  const cudaError_t e = p.W == 1 ? launch_pre_w<1>(h, p, a) : p.W == 4 ? launch_pre_w<4>(h, p, a) : launch_pre_w<8>(h, p, a);
+  if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, std::string("presolve launch: ") + cudaGetErrorString(e));
+  return CMPC_OK;
+}
+
+// classify, then per used size class: the presolve kernel (one Cholesky of H settles the instances
+// whose unconstrained minimiser is feasible) and the interior-point kernel over what it deferred --
+// all on the stream, no host round trip.  Returns the number of kernels launched (<0: error).
 int launch_solve(cmpc_handle* h, SolveArgs a, int B) {
-  if (cudaMemsetAsync(h->d_counts, 0, 2 * kNumClasses * sizeof(int32_t), h->stream) != cudaSuccess)
+  if (cudaMemsetAsync(h->d_counts, 0, 4 * kNumClasses * sizeof(int32_t), h->stream) != cudaSuccess)
     return fail(h, CMPC_ERR_CUDA, "memset counts");
   classify_kernel<<<(B + 31) / 32, 1024, 0, h->stream>>>(h->dev, B, a.des_inputs, h->bounds, h->d_counts, h->d_perm);
   int launches = 1;
+  const bool presolve = h->cfg.presolve && h->cfg.polish;
   for (int c = 0; c < kNumClasses; ++c) {
     if (!h->cls[c].used) continue;
     a.perm = h->d_perm + (size_t)c * B;
     a.count = h->d_counts + c;
     a.work = h->d_counts + kNumClasses + c;
+    if (presolve && h->cls[c].pre_used) {
+      a.fail_perm = h->d_perm + (size_t)(kNumClasses + c) * h->max_batch;
+      a.fail_count = h->d_counts + 2 * kNumClasses + c;
+      int rc = launch_presolve(h, h->cls[c], a);
+      if (rc) return rc;
+      ++launches;
+      a.perm = a.fail_perm;
+      a.count = a.fail_count;
+      a.work = h->d_counts + 3 * kNumClasses + c;
+      a.fail_perm = nullptr; a.fail_count = nullptr;
+    }
     int rc = launch_class<0>(h, h->cls[c], a);
     if (rc) return rc;
     ++launches;
@@ -380,6 +414,23 @@ int plan_class(cmpc_handle* h, cmpc_handle::ClassPlan& p, int W, int nbmax, int 
   p.scratch_per_group = (size_t)mat_region_doubles(N, L, p.n4max) * (p.m_in_smem ? 1 : 2) + (size_t)((9 * p.nbmax + 1) & ~1);
   CUDA_TRY(h, cudaMalloc(&p.d_scratch, p.scratch_per_group * 8 * (size_t)p.grid * p.groups));
   p.used = true;
+  if (mode == 0 && p.m_in_smem) {  // presolve variant: matrix + three vectors per group
+    const SmemPlan pp = make_pre_plan(N, L, W, p.nbmax, p.n4max);
+    const int pgmax = (W == 1 ? 448 : 256) / (32 * W);
+    p.pre_groups = (int)std::min<size_t>((size_t)pgmax, kMaxSmem / ((size_t)pp.total * 8));
+    if (p.pre_groups >= 1) {
+      p.pre_smem_bytes = (size_t)pp.total * 8 * p.pre_groups;
+      p.pre_scratch_per_group = (size_t)mat_region_doubles(N, L, p.n4max);
+      CUDA_TRY(h, cudaMalloc(&p.d_pre_scratch, p.pre_scratch_per_group * 8 * (size_t)p.grid * p.pre_groups));
+      p.pre_used = true;
+    }
+  }
+  return CMPC_OK;
+}
+
+template <int W>
+int set_pre_smem_attr(cmpc_handle* h, size_t bytes) {
+  CUDA_TRY(h, cudaFuncSetAttribute(cmpc_presolve_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return CMPC_OK;
 }
 
@@ -419,7 +470,7 @@ int cmpc_config_init(cmpc_config* cfg, double mass, int num_legs, int horizon, d
   cfg->mass = mass; cfg->num_legs = num_legs; cfg->horizon = horizon; cfg->dt = dt;
   for (int i = 0; i < num_legs; ++i) cfg->mu[i] = mu[i];
   for (int i = 0; i < 9 + 9 * num_legs; ++i) cfg->weights[i] = weights[i];
-  cfg->disc_mode = 0; cfg->max_iter = 50; cfg->ipm_tol = 1e-9; cfg->polish = 1;
+  cfg->disc_mode = 0; cfg->max_iter = 50; cfg->ipm_tol = 1e-9; cfg->polish = 1; cfg->presolve = 1;
   return valid_config(cfg) ? CMPC_OK : CMPC_ERR_ARG;
 }
 
@@ -473,8 +524,8 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
   CUDA_TRY(h, cudaMalloc(&h->d_active, B * L * N * 2));
   CUDA_TRY(h, cudaMalloc(&h->d_stats, sizeof(DevStats)));
 
-  CUDA_TRY(h, cudaMalloc(&h->d_counts, 2 * kNumClasses * sizeof(int32_t)));
-  CUDA_TRY(h, cudaMalloc(&h->d_perm, (size_t)kNumClasses * B * sizeof(int32_t)));
+  CUDA_TRY(h, cudaMalloc(&h->d_counts, 4 * kNumClasses * sizeof(int32_t)));
+  CUDA_TRY(h, cudaMalloc(&h->d_perm, (size_t)2 * kNumClasses * B * sizeof(int32_t)));
   // size classes by number of free 3-blocks: n4 <= 64 -> one warp per instance, n4 <= 128 ->
   // four warps, larger -> a whole 256-thread CTA; the factor lives in shared memory whenever it fits
   {
@@ -495,9 +546,14 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
     h->bounds = make_int4(b[0], b[1], b[2], b[3]);
     int rc = plan_class(h, h->exp_plan, 8, nbfull, 1);
     if (rc) return rc;
-    size_t s1 = 0, s2 = 0, s4 = 0, s8 = 0, s8g = 0;
+    size_t s1 = 0, s2 = 0, s4 = 0, s8 = 0, s8g = 0, p1 = 0, p4 = 0, p8 = 0;
     for (int c = 0; c < kNumClasses; ++c) {
       if (!h->cls[c].used) continue;
+      if (h->cls[c].pre_used && h->cls[c].W == 2) h->cls[c].pre_used = false;  // no two-warp presolve variant
+      if (h->cls[c].pre_used) {
+        size_t& pref = h->cls[c].W == 1 ? p1 : h->cls[c].W == 4 ? p4 : p8;
+        pref = std::max(pref, h->cls[c].pre_smem_bytes);
+      }
       if (!h->cls[c].m_in_smem) h->cls[c].W = 8;  // the global-factor variant exists for W = 8 only
       size_t& sref = !h->cls[c].m_in_smem ? s8g : h->cls[c].W == 1 ? s1 : h->cls[c].W == 2 ? s2 : h->cls[c].W == 4 ? s4 : s8;
       sref = std::max(sref, h->cls[c].smem_bytes);
@@ -508,6 +564,9 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
     if (s8 && (rc = set_smem_attr<8, 0, true>(h, s8))) return rc;
     if (s8g && (rc = set_smem_attr<8, 0, false>(h, s8g))) return rc;
     if ((rc = set_smem_attr<8, 1, false>(h, h->exp_plan.smem_bytes))) return rc;
+    if (p1 && (rc = set_pre_smem_attr<1>(h, p1))) return rc;
+    if (p4 && (rc = set_pre_smem_attr<4>(h, p4))) return rc;
+    if (p8 && (rc = set_pre_smem_attr<8>(h, p8))) return rc;
   }
   h->max_batch = max_batch;
   h->ready = true;
@@ -907,7 +966,7 @@ void cmpc_destroy(cmpc_handle* h) {
   if (h->device >= 0) cudaSetDevice(h->device);
   cudaFree(h->d_state); cudaFree(h->d_ds); cudaFree(h->d_di); cudaFree(h->d_forces); cudaFree(h->d_kkt);
   cudaFree(h->d_lam); cudaFree(h->d_hip); cudaFree(h->d_counts); cudaFree(h->d_perm); cudaFree(h->exp_plan.d_scratch);
-  for (auto& c : h->cls) cudaFree(c.d_scratch);
+  for (auto& c : h->cls) { cudaFree(c.d_scratch); cudaFree(c.d_pre_scratch); }
   cudaFree(h->d_status); cudaFree(h->d_iters);
   cudaFree(h->d_iters_sum); cudaFree(h->d_status_or); cudaFree(h->d_active); cudaFree(h->d_stats);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);

@@ -73,6 +73,8 @@ struct SolveArgs {
   int m_in_smem;
   int groups;                // groups per CTA
   SmemPlan plan;             // shared-memory layout of one group, computed on the host
+  int32_t* fail_perm;        // presolve kernel only: instances it could not settle, for the IPM kernel
+  int32_t* fail_count;
 };
 
 // ------------------------------------------------------------------ BC4 layout
@@ -678,6 +680,217 @@ __global__ void __launch_bounds__(1024) classify_kernel(const DevConfig cfg, int
   if (valid) perm[(size_t)c * B + base + rank] = bb;
 }
 
+// ------------------------------------------------------------------ prologue and build (both kernels)
+// Shared-memory views of one group used while an instance is unpacked and its QP is built.
+struct BuildView {
+  double* Mm;   // the matrix buffer; stages the raw inputs [state | des_state | des_inputs] first
+  double *ce, *fz, *arm, *eq, *qz, *g;
+  int* misc;    // [0] = nb, [1] = invalid table
+  uint16_t* tb;
+  uint8_t *blk_j, *blk_i;
+  int8_t* blk_of;
+};
+
+// Inputs -> shared memory, contact table -> free blocks, zero-input rollout errors.  Returns
+// whether every input is finite (uniform over the group); ends with a group barrier.
+template <int W>
+__device__ __forceinline__ bool stage_inputs(const Group<W>& G, const DevConfig& cfg, const SolveArgs& args, int inst,
+                                             const BuildView& V) {
+  constexpr int GT = Group<W>::GT;
+  const int gtid = G.gtid;
+  const int N = cfg.N, L = cfg.L;
+  const int ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = L * (4 * N + 3);
+  const double dt = cfg.dt, mass = cfg.mass;
+  // ---- stage the raw inputs once, coalesced (CentroidalMPC.cpp:284-317 copies them blindly;
+  // here non-finite values are caught).  The buffers may be HBM or mapped pinned host memory
+  // (zero-copy end-to-end path): every input byte crosses the bus exactly once.  The staging
+  // area is the factor's buffer, which is dead until the build.
+  double* g_state = V.Mm;
+  double* g_ds = V.Mm + ns;
+  double* g_di = V.Mm + ns + nds;
+  bool finite = true;
+  {
+    const double* src = args.state + (size_t)inst * ns;
+    for (int t = gtid; t < ns; t += GT) { const double v = __ldg(src + t); g_state[t] = v; finite = finite && isfinite(v); }
+    src = args.des_state + (size_t)inst * nds;
+    for (int t = gtid; t < nds; t += GT) { const double v = __ldg(src + t); g_ds[t] = v; finite = finite && isfinite(v); }
+    src = args.des_inputs + (size_t)inst * ndi;
+    for (int t = gtid; t < ndi; t += GT) { const double v = __ldg(src + t); g_di[t] = v; finite = finite && isfinite(v); }
+  }
+  const double* g_dpos = g_ds;
+  const double* g_dvel = g_ds + 3 * (N + 1);
+  const double* g_dam = g_ds + 6 * (N + 1);
+  finite = G.all(finite);
+
+  // ---- contact table -> free blocks; validity (CentroidalMPC.cpp:328-330).  Lane j of the
+  // group's first warp owns step j (N <= 32): column sum, stance count, exclusive prefix by
+  // shuffles, then it numbers its own stance legs.
+  if (gtid < 32) {
+    const int j = gtid;
+    double colsum = 0.0;
+    int cnt = 0;
+    if (j < N)
+      for (int i = 0; i < L; ++i) { const double ce = g_di[i * (4 * N + 3) + j]; colsum += ce; cnt += ce > 0.0 ? 1 : 0; }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (gtid >= o) incl += v; }
+    const unsigned bad = __ballot_sync(0xffffffffu, j < N && !(colsum > 0.0));
+    const int total = __shfl_sync(0xffffffffu, incl, N - 1);
+    if (j < N) {
+      int b = incl - cnt;
+      for (int i = 0; i < L; ++i) {
+        const double ce = g_di[i * (4 * N + 3) + j];
+        if (ce > 0.0 && b < args.nbmax) {
+          V.blk_j[b] = j; V.blk_i[b] = i; V.blk_of[j * L + i] = b;
+          V.ce[b] = ce;
+          V.fz[b] = (colsum > 0.0) ? mass * kGrav / colsum : 0.0;  // desired fz, :331-333
+          ++b;
+        } else {
+          V.blk_of[j * L + i] = -1;
+        }
+      }
+    }
+    if (gtid == 0) { V.misc[0] = total < args.nbmax ? total : args.nbmax; V.misc[1] = bad != 0u; }
+  }
+  // zero-input rollout (closed form of x_k = A^k x0 + sum A^p d) and e = Q (x - x_ref), nodes 1..N
+  for (int k = gtid; k < N; k += GT) {
+    const int node = k + 1;
+    const double kk = (double)node;
+    const double gpos = cfg.zoh ? 0.5 * kk * kk : 0.5 * kk * (kk - 1.0);
+    double c[3], v[3];
+    for (int a = 0; a < 3; ++a) { c[a] = g_state[a] + kk * dt * g_state[3 + a]; v[a] = g_state[3 + a]; }
+    c[2] += gpos * dt * dt * (-kGrav);
+    v[2] += kk * dt * (-kGrav);
+    const double om = (cfg.w[2] * 0.5) * exp(-kk) + cfg.w[2] * 0.5;  // :205
+    const double qz = om * om;                                        // :210 (inside the square)
+    V.qz[k] = qz;
+    V.eq[9 * k + 0] = cfg.w[0] * (c[0] - g_dpos[3 * node + 0]);
+    V.eq[9 * k + 1] = cfg.w[1] * (c[1] - g_dpos[3 * node + 1]);
+    V.eq[9 * k + 2] = qz * (c[2] - g_dpos[3 * node + 2]);
+    for (int a = 0; a < 3; ++a) {
+      V.eq[9 * k + 3 + a] = cfg.w[3 + a] * (v[a] - g_dvel[3 * node + a]);
+      V.eq[9 * k + 6 + a] = cfg.w[6 + a] * (g_state[6 + a] - g_dam[3 * node + a]);
+    }
+  }
+  G.sync();
+  return finite;
+}
+
+// H = 2 (Bqp' L Bqp + K) in BC4 layout into Hb, g into V.g; reads the inputs staged in V.Mm (Hb may
+// be V.Mm itself: the staged inputs are consumed before the first tile is written).
+template <int W>
+__device__ __forceinline__ void build_qp(const Group<W>& G, const DevConfig& cfg, const BuildView& V, double* Hb, int nb) {
+  constexpr int GT = Group<W>::GT;
+  const int gtid = G.gtid;
+  const int N = cfg.N, L = cfg.L;
+  const int ns = 9 + 3 * L, nds = 9 * (N + 1);
+  const double dt = cfg.dt, mass = cfg.mass;
+  const double zeta = cfg.zoh ? 0.5 : 0.0;
+  const int n = 3 * nb, nblk = (n + 3) >> 2, n4 = nblk << 2;
+  const int matd = ((nblk * (nblk + 1)) >> 1) * kTS;
+  // lever arms r = des_foot_pos[:, j] - des_com_pos[:, j] (frozen), tile table
+  for (int b = gtid; b < nb; b += GT) {
+    const int j = V.blk_j[b], i = V.blk_i[b];
+    for (int q = 0; q < 3; ++q) V.arm[3 * b + q] = V.Mm[ns + nds + i * (4 * N + 3) + N + 3 * j + q] - V.Mm[ns + 3 * j + q];
+  }
+  for (int bj = gtid; bj < nblk; bj += GT) {
+    const int o = blkoff(bj, bj, nblk);
+    for (int bi = bj; bi < nblk; ++bi) V.tb[o + bi - bj] = (uint16_t)(bi | (bj << 8));
+  }
+  // ---- H = 2 (Bqp' L Bqp + K) on the free variables, one thread per block pair (b >= b2),
+  // assembled on chip (in the factor's buffer) and then streamed to the L2-resident copy.
+  // Column (j,i) of Bqp at row block k >= j is A_d^{k-j} B_j =
+  //   [ dt^2 (k-j+zeta) (c/m) I ; dt (c/m) I ; dt c [r]x ]   (a2/a3; Euler zeta=0, ZOH 1/2)
+    G.sync();  // all reads of the staged inputs (they live in the factor's buffer) are done
+    for (int t = gtid; t < matd; t += GT) Hb[t] = 0.0;
+    G.sync();
+    const int npairs = (nb * (nb + 1)) >> 1;
+    const double dt2 = dt * dt, dt4 = dt2 * dt2;
+    for (int idx = gtid; idx < npairs; idx += GT) {
+      int a = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
+      while (((a + 1) * (a + 2)) >> 1 <= idx) ++a;
+      while ((a * (a + 1)) >> 1 > idx) --a;
+      const int b2 = idx - ((a * (a + 1)) >> 1), b = a;  // b >= b2  => j >= j2
+      const int j = V.blk_j[b], i = V.blk_i[b], j2 = V.blk_j[b2], i2 = V.blk_i[b2];
+      const double ce = V.ce[b], ce2 = V.ce[b2];
+      const double r0 = V.arm[3 * b], r1 = V.arm[3 * b + 1], r2 = V.arm[3 * b + 2];
+      const double p0 = V.arm[3 * b2], p1 = V.arm[3 * b2 + 1], p2 = V.arm[3 * b2 + 2];
+      const double cm = ce / mass, cm2 = ce2 / mass;
+      // position rows: sum_k alpha_{k-j} alpha_{k-j2} Qp_k ; only the z weight depends on k
+      double s0 = 0.0, sz = 0.0;
+      for (int k = j; k < N; ++k) {
+        const double aa = ((double)(k - j) + zeta) * ((double)(k - j2) + zeta);
+        s0 += aa; sz += aa * V.qz[k];
+      }
+      const double cnt = (double)(N - j);
+      // angular rows: dt^2 c c2 [r]x' diag(ql) [r2]x summed over the N-j row blocks below;
+      // [r]x = [[0,-rz,ry],[rz,0,-rx],[-ry,rx,0]]
+      const double q0 = cfg.w[6], q1 = cfg.w[7], q2 = cfg.w[8];
+      const double sc = cnt * dt2 * ce * ce2;
+      double blk[3][3];
+      blk[0][0] = sc * (r2 * q1 * p2 + r1 * q2 * p1);
+      blk[0][1] = sc * (-r1 * q2 * p0);
+      blk[0][2] = sc * (-r2 * q1 * p0);
+      blk[1][0] = sc * (-r0 * q2 * p1);
+      blk[1][1] = sc * (r2 * q0 * p2 + r0 * q2 * p0);
+      blk[1][2] = sc * (-r2 * q0 * p1);
+      blk[2][0] = sc * (-r0 * q1 * p2);
+      blk[2][1] = sc * (-r1 * q0 * p2);
+      blk[2][2] = sc * (r1 * q0 * p1 + r0 * q1 * p0);
+      const double pos[3] = {cfg.w[0] * s0, cfg.w[1] * s0, sz};
+      for (int aa = 0; aa < 3; ++aa) blk[aa][aa] += cm * cm2 * (dt4 * pos[aa] + cnt * dt2 * cfg.w[3 + aa]);
+      // K = W_f + D' W_r D (CentroidalMPC.cpp:223-231): same leg, same component
+      if (i == i2) {
+        for (int aa = 0; aa < 3; ++aa) {
+          const double wr = cfg.w[9 + 6 * L + 3 * i + aa];
+          if (j == j2) {
+            const double nn = (j > 0 ? 1.0 : 0.0) + (j + 1 < N ? 1.0 : 0.0);
+            blk[aa][aa] += cfg.w[9 + 3 * L + 3 * i + aa] + nn * wr;
+          } else if (j == j2 + 1) {
+            blk[aa][aa] -= wr;
+          }
+        }
+      }
+      for (int aa = 0; aa < 3; ++aa)
+        for (int bb = 0; bb < 3; ++bb) {
+          const int gi = 3 * b + aa, gj = 3 * b2 + bb;
+          const double v = 2.0 * blk[aa][bb];
+          if (b != b2) {
+            Hb[midx(gi, gj, nblk)] = v;                              // gi > gj always here
+            if ((gi >> 2) == (gj >> 2)) Hb[midx(gj, gi, nblk)] = v;  // same diagonal tile: mirror
+          } else if ((gi >> 2) >= (gj >> 2)) {
+            // diagonal 3x3 block: all 9 (aa,bb) are visited, so both triangles of a
+            // diagonal tile get written; a straddling entry lands in the lower tile only
+            Hb[midx(gi, gj, nblk)] = v;
+          }
+        }
+    }
+    if (gtid < n4 - n) Hb[midx(n + gtid, n + gtid, nblk)] = 1.0;  // padding rows: identity
+    // ---- g = 2 Bqp' L (Aqp x0 + dqp - Xref) - 2 W_f Uref, one thread per block (adjoint sum)
+    for (int b = gtid; b < nb; b += GT) {
+      const int j = V.blk_j[b], i = V.blk_i[b];
+      const double ce = V.ce[b];
+      const double r[3] = {V.arm[3 * b], V.arm[3 * b + 1], V.arm[3 * b + 2]};
+      double sp[3] = {0, 0, 0}, sv[3] = {0, 0, 0}, sl3[3] = {0, 0, 0};
+      for (int k = j; k < N; ++k) {
+        const double al = (double)(k - j) + zeta;
+        for (int q = 0; q < 3; ++q) {
+          sp[q] += al * V.eq[9 * k + q]; sv[q] += V.eq[9 * k + 3 + q]; sl3[q] += V.eq[9 * k + 6 + q];
+        }
+      }
+      const double cm = ce / mass;
+      // [r]x' v = v x r
+      const double cr[3] = {sl3[1] * r[2] - sl3[2] * r[1], sl3[2] * r[0] - sl3[0] * r[2], sl3[0] * r[1] - sl3[1] * r[0]};
+      for (int q = 0; q < 3; ++q) {
+        double gq = 2.0 * (cm * (dt * dt * sp[q] + dt * sv[q]) + dt * ce * cr[q]);
+        if (q == 2) gq -= 2.0 * cfg.w[9 + 3 * L + 3 * i + 2] * V.fz[b];
+        V.g[3 * b + q] = gq;
+      }
+    }
+    if (gtid < n4 - n) V.g[n + gtid] = 0.0;
+    G.sync();
+}
+
 // ------------------------------------------------------------------ the fused kernel
 // MODE 0: solve.  MODE 1: build-export (H, g in the full 3LN layout to global memory).
 template <int W, int MODE, bool MS>
@@ -685,7 +898,7 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solv
   extern __shared__ __align__(128) double smem[];
   constexpr int GT = Group<W>::GT;
   const int N = cfg.N, L = cfg.L, nu = 3 * L;
-  const int ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = L * (4 * N + 3), nf = 3 * L * N;
+  const int nf = 3 * L * N;
   const int nbfull = L * N, mfull = 5 * nbfull;
   const int nbmax = args.nbmax, mmax = 5 * nbmax;
   const SmemPlan& P = args.plan;
@@ -728,8 +941,7 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solv
   // polish only: null-space bases, 9 doubles per leg-step, behind the matrices in the L2 slab
   double* g_Zt = Hm + (size_t)mat_region_doubles(N, L, args.n4max) * (MS ? 1 : 2);
 
-  const double dt = cfg.dt, mass = cfg.mass;
-  const double zeta = cfg.zoh ? 0.5 : 0.0;
+  const double mass = cfg.mass;
   const int count = args.count ? *args.count : args.count_imm;
 
   while (true) {
@@ -738,78 +950,10 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solv
     slot = G.bcast0(slot, s_misc + 2);
     if (slot >= count) break;
     const int inst = args.perm ? args.perm[slot] : slot;
-    // ---- stage the raw inputs once, coalesced (CentroidalMPC.cpp:284-317 copies them blindly;
-    // here non-finite values are caught).  The buffers may be HBM or mapped pinned host memory
-    // (zero-copy end-to-end path): every input byte crosses the bus exactly once.  The staging
-    // area is the factor's buffer, which is dead until the build.
-    double* g_state = Mm;
-    double* g_ds = Mm + ns;
-    double* g_di = Mm + ns + nds;
-    bool finite = true;
-    {
-      const double* src = args.state + (size_t)inst * ns;
-      for (int t = gtid; t < ns; t += GT) { const double v = __ldg(src + t); g_state[t] = v; finite = finite && isfinite(v); }
-      src = args.des_state + (size_t)inst * nds;
-      for (int t = gtid; t < nds; t += GT) { const double v = __ldg(src + t); g_ds[t] = v; finite = finite && isfinite(v); }
-      src = args.des_inputs + (size_t)inst * ndi;
-      for (int t = gtid; t < ndi; t += GT) { const double v = __ldg(src + t); g_di[t] = v; finite = finite && isfinite(v); }
-    }
-    const double* g_dpos = g_ds;
-    const double* g_dvel = g_ds + 3 * (N + 1);
-    const double* g_dam = g_ds + 6 * (N + 1);
-    finite = G.all(finite);
-
-    // ---- contact table -> free blocks; validity (CentroidalMPC.cpp:328-330).  Lane j of the
-    // group's first warp owns step j (N <= 32): column sum, stance count, exclusive prefix by
-    // shuffles, then it numbers its own stance legs.
-    if (gtid < 32) {
-      const int j = gtid;
-      double colsum = 0.0;
-      int cnt = 0;
-      if (j < N)
-        for (int i = 0; i < L; ++i) { const double ce = g_di[i * (4 * N + 3) + j]; colsum += ce; cnt += ce > 0.0 ? 1 : 0; }
-      int incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (gtid >= o) incl += v; }
-      const unsigned bad = __ballot_sync(0xffffffffu, j < N && !(colsum > 0.0));
-      const int total = __shfl_sync(0xffffffffu, incl, N - 1);
-      if (j < N) {
-        int b = incl - cnt;
-        for (int i = 0; i < L; ++i) {
-          const double ce = g_di[i * (4 * N + 3) + j];
-          if (ce > 0.0 && b < nbmax) {
-            s_blk_j[b] = j; s_blk_i[b] = i; s_blk_of[j * L + i] = b;
-            s_ce[b] = ce;
-            s_fz[b] = (colsum > 0.0) ? mass * kGrav / colsum : 0.0;  // desired fz, :331-333
-            ++b;
-          } else {
-            s_blk_of[j * L + i] = -1;
-          }
-        }
-      }
-      if (gtid == 0) { s_misc[0] = total < nbmax ? total : nbmax; s_misc[1] = bad != 0u; }
-    }
-    // zero-input rollout (closed form of x_k = A^k x0 + sum A^p d) and e = Q (x - x_ref), nodes 1..N
-    for (int k = gtid; k < N; k += GT) {
-      const int node = k + 1;
-      const double kk = (double)node;
-      const double gpos = cfg.zoh ? 0.5 * kk * kk : 0.5 * kk * (kk - 1.0);
-      double c[3], v[3];
-      for (int a = 0; a < 3; ++a) { c[a] = g_state[a] + kk * dt * g_state[3 + a]; v[a] = g_state[3 + a]; }
-      c[2] += gpos * dt * dt * (-kGrav);
-      v[2] += kk * dt * (-kGrav);
-      const double om = (cfg.w[2] * 0.5) * exp(-kk) + cfg.w[2] * 0.5;  // :205
-      const double qz = om * om;                                        // :210 (inside the square)
-      s_qz[k] = qz;
-      s_eq[9 * k + 0] = cfg.w[0] * (c[0] - g_dpos[3 * node + 0]);
-      s_eq[9 * k + 1] = cfg.w[1] * (c[1] - g_dpos[3 * node + 1]);
-      s_eq[9 * k + 2] = qz * (c[2] - g_dpos[3 * node + 2]);
-      for (int a = 0; a < 3; ++a) {
-        s_eq[9 * k + 3 + a] = cfg.w[3 + a] * (v[a] - g_dvel[3 * node + a]);
-        s_eq[9 * k + 6 + a] = cfg.w[6 + a] * (g_state[6 + a] - g_dam[3 * node + a]);
-      }
-    }
-    G.sync();
+    BuildView V;
+    V.Mm = Mm; V.ce = s_ce; V.fz = s_fz; V.arm = s_arm; V.eq = s_eq; V.qz = s_qz; V.g = s_g;
+    V.misc = s_misc; V.tb = s_tb; V.blk_j = s_blk_j; V.blk_i = s_blk_i; V.blk_of = s_blk_of;
+    const bool finite = stage_inputs<W>(G, cfg, args, inst, V);
     const int nb = s_misc[0];
     const int n = 3 * nb, nblk = (n + 3) >> 2, n4 = nblk << 2, m = 5 * nb;
     const int ntiles = (nblk * (nblk + 1)) >> 1;
@@ -829,112 +973,10 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solv
       continue;
     }
 
-    // lever arms r = des_foot_pos[:, j] - des_com_pos[:, j] (frozen), tile table
-    for (int b = gtid; b < nb; b += GT) {
-      const int j = s_blk_j[b], i = s_blk_i[b];
-      for (int q = 0; q < 3; ++q) s_arm[3 * b + q] = g_di[i * (4 * N + 3) + N + 3 * j + q] - g_dpos[3 * j + q];
-    }
-    for (int bj = gtid; bj < nblk; bj += GT) {
-      const int o = blkoff(bj, bj, nblk);
-      for (int bi = bj; bi < nblk; ++bi) s_tb[o + bi - bj] = (uint16_t)(bi | (bj << 8));
-    }
-    // ---- H = 2 (Bqp' L Bqp + K) on the free variables, one thread per block pair (b >= b2),
-    // assembled on chip (in the factor's buffer) and then streamed to the L2-resident copy.
-    // Column (j,i) of Bqp at row block k >= j is A_d^{k-j} B_j =
-    //   [ dt^2 (k-j+zeta) (c/m) I ; dt (c/m) I ; dt c [r]x ]   (a2/a3; Euler zeta=0, ZOH 1/2)
     double* Hb;
     if constexpr (MS) Hb = Mm; else Hb = Hm;
-    {
-      G.sync();  // all reads of the staged inputs (they live in the factor's buffer) are done
-      for (int t = gtid; t < matd; t += GT) Hb[t] = 0.0;
-      G.sync();
-      const int npairs = (nb * (nb + 1)) >> 1;
-      const double dt2 = dt * dt, dt4 = dt2 * dt2;
-      for (int idx = gtid; idx < npairs; idx += GT) {
-        int a = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
-        while (((a + 1) * (a + 2)) >> 1 <= idx) ++a;
-        while ((a * (a + 1)) >> 1 > idx) --a;
-        const int b2 = idx - ((a * (a + 1)) >> 1), b = a;  // b >= b2  => j >= j2
-        const int j = s_blk_j[b], i = s_blk_i[b], j2 = s_blk_j[b2], i2 = s_blk_i[b2];
-        const double ce = s_ce[b], ce2 = s_ce[b2];
-        const double r0 = s_arm[3 * b], r1 = s_arm[3 * b + 1], r2 = s_arm[3 * b + 2];
-        const double p0 = s_arm[3 * b2], p1 = s_arm[3 * b2 + 1], p2 = s_arm[3 * b2 + 2];
-        const double cm = ce / mass, cm2 = ce2 / mass;
-        // position rows: sum_k alpha_{k-j} alpha_{k-j2} Qp_k ; only the z weight depends on k
-        double s0 = 0.0, sz = 0.0;
-        for (int k = j; k < N; ++k) {
-          const double aa = ((double)(k - j) + zeta) * ((double)(k - j2) + zeta);
-          s0 += aa; sz += aa * s_qz[k];
-        }
-        const double cnt = (double)(N - j);
-        // angular rows: dt^2 c c2 [r]x' diag(ql) [r2]x summed over the N-j row blocks below;
-        // [r]x = [[0,-rz,ry],[rz,0,-rx],[-ry,rx,0]]
-        const double q0 = cfg.w[6], q1 = cfg.w[7], q2 = cfg.w[8];
-        const double sc = cnt * dt2 * ce * ce2;
-        double blk[3][3];
-        blk[0][0] = sc * (r2 * q1 * p2 + r1 * q2 * p1);
-        blk[0][1] = sc * (-r1 * q2 * p0);
-        blk[0][2] = sc * (-r2 * q1 * p0);
-        blk[1][0] = sc * (-r0 * q2 * p1);
-        blk[1][1] = sc * (r2 * q0 * p2 + r0 * q2 * p0);
-        blk[1][2] = sc * (-r2 * q0 * p1);
-        blk[2][0] = sc * (-r0 * q1 * p2);
-        blk[2][1] = sc * (-r1 * q0 * p2);
-        blk[2][2] = sc * (r1 * q0 * p1 + r0 * q1 * p0);
-        const double pos[3] = {cfg.w[0] * s0, cfg.w[1] * s0, sz};
-        for (int aa = 0; aa < 3; ++aa) blk[aa][aa] += cm * cm2 * (dt4 * pos[aa] + cnt * dt2 * cfg.w[3 + aa]);
-        // K = W_f + D' W_r D (CentroidalMPC.cpp:223-231): same leg, same component
-        if (i == i2) {
-          for (int aa = 0; aa < 3; ++aa) {
-            const double wr = cfg.w[9 + 6 * L + 3 * i + aa];
-            if (j == j2) {
-              const double nn = (j > 0 ? 1.0 : 0.0) + (j + 1 < N ? 1.0 : 0.0);
-              blk[aa][aa] += cfg.w[9 + 3 * L + 3 * i + aa] + nn * wr;
-            } else if (j == j2 + 1) {
-              blk[aa][aa] -= wr;
-            }
-          }
-        }
-        for (int aa = 0; aa < 3; ++aa)
-          for (int bb = 0; bb < 3; ++bb) {
-            const int gi = 3 * b + aa, gj = 3 * b2 + bb;
-            const double v = 2.0 * blk[aa][bb];
-            if (b != b2) {
-              Hb[midx(gi, gj, nblk)] = v;                              // gi > gj always here
-              if ((gi >> 2) == (gj >> 2)) Hb[midx(gj, gi, nblk)] = v;  // same diagonal tile: mirror
-            } else if ((gi >> 2) >= (gj >> 2)) {
-              // diagonal 3x3 block: all 9 (aa,bb) are visited, so both triangles of a
-              // diagonal tile get written; a straddling entry lands in the lower tile only
-              Hb[midx(gi, gj, nblk)] = v;
-            }
-          }
-      }
-      if (gtid < n4 - n) Hb[midx(n + gtid, n + gtid, nblk)] = 1.0;  // padding rows: identity
-      // ---- g = 2 Bqp' L (Aqp x0 + dqp - Xref) - 2 W_f Uref, one thread per block (adjoint sum)
-      for (int b = gtid; b < nb; b += GT) {
-        const int j = s_blk_j[b], i = s_blk_i[b];
-        const double ce = s_ce[b];
-        const double r[3] = {s_arm[3 * b], s_arm[3 * b + 1], s_arm[3 * b + 2]};
-        double sp[3] = {0, 0, 0}, sv[3] = {0, 0, 0}, sl3[3] = {0, 0, 0};
-        for (int k = j; k < N; ++k) {
-          const double al = (double)(k - j) + zeta;
-          for (int q = 0; q < 3; ++q) {
-            sp[q] += al * s_eq[9 * k + q]; sv[q] += s_eq[9 * k + 3 + q]; sl3[q] += s_eq[9 * k + 6 + q];
-          }
-        }
-        const double cm = ce / mass;
-        // [r]x' v = v x r
-        const double cr[3] = {sl3[1] * r[2] - sl3[2] * r[1], sl3[2] * r[0] - sl3[0] * r[2], sl3[0] * r[1] - sl3[1] * r[0]};
-        for (int q = 0; q < 3; ++q) {
-          double gq = 2.0 * (cm * (dt * dt * sp[q] + dt * sv[q]) + dt * ce * cr[q]);
-          if (q == 2) gq -= 2.0 * cfg.w[9 + 3 * L + 3 * i + 2] * s_fz[b];
-          s_g[3 * b + q] = gq;
-        }
-      }
-      if (gtid < n4 - n) s_g[n + gtid] = 0.0;
-      G.sync();
-      if constexpr (MS) store_mat<W>(G, Hm, Mm, matd);
-    }
+    build_qp<W>(G, cfg, V, Hb, nb);
+    if constexpr (MS) store_mat<W>(G, Hm, Mm, matd);
 
     if (MODE == 1) {
       // export H, g in the full 3LN step-major layout with pinned rows/cols = identity
@@ -1480,6 +1522,176 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solv
         if (args.iters) args.iters[inst] = it;
         if (args.kkt) args.kkt[inst] = 0.0;
       }
+    }
+    G.sync();
+  }
+}
+
+// ------------------------------------------------------------------ presolve kernel
+// Most ticks of a legged MPC have no friction or force-limit row active (the reference's weights make
+// force tracking dominate), and then the optimum is the unconstrained minimiser -H^-1 g.  This kernel
+// settles exactly those instances with ONE Cholesky of H: build, factor (forward substitution fused),
+// back-substitute, then verify on the original H -- stationarity |H u + g| <= 1e-9 gs and every row
+// of 0 <= F f <= ub satisfied to -1e-9 us, the polish's own acceptance test with an empty working
+// set -- and write the outputs (status OK, iters 0, multipliers 0).  Anything else (a violated row, a
+// warm-start guess with active rows, a failed pivot) is appended to fail_perm and goes through the
+// interior-point kernel.  Per group it needs the matrix and three vectors only, so more instances are
+// resident per SM than in the IPM kernel.  Shared-memory plan: make_pre_plan (fields of SmemPlan reused:
+// u = the solution, rhs = H u; rd..tv host eq/qz during the build).
+__host__ __device__ inline SmemPlan make_pre_plan(int N, int L, int W, int nbmax, int n4max) {
+  SmemPlan p;
+  int o = 0;
+  auto take = [&](int cnt) { int r = o; o += (cnt + 1) & ~1; return r; };
+  p.ce = take(nbmax);
+  p.dua = take(nbmax);      // desired fz
+  p.du = take(3 * nbmax);   // lever arms
+  p.g = take(n4max);
+  const int nv = (2 * n4max >= 10 * N + 2) ? n4max : (10 * N + 2 + 1) / 2;
+  p.u = take(nv); p.rhs = take(nv);  // eq[9N], qz[N] live here during the build
+  p.rd = p.u; p.tv = p.rhs;
+  p.zl = p.zu = 0;
+  p.red = take(W > 1 ? 3 * W : 2);
+  p.exch = take(8);
+  const int nbytes = 16 + 2 * nbmax + 2 * bc4_tiles(n4max) + 2 + 2 * nbmax + N * L;
+  p.ints = take((nbytes + 7) / 8);
+  o = (o + 1) & ~1;
+  p.Mm = o;
+  o += mat_region_doubles(N, L, n4max);
+  p.total = (o + 1) & ~1;
+  return p;
+}
+
+template <int W>
+__global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const DevConfig cfg, const SolveArgs args) {
+  extern __shared__ __align__(128) double smem[];
+  constexpr int GT = Group<W>::GT;
+  const int N = cfg.N, L = cfg.L;
+  const int nf = 3 * L * N, nbfull = L * N, mfull = 5 * nbfull;
+  const int nbmax = args.nbmax;
+  const SmemPlan& P = args.plan;
+  Group<W> G;
+  G.gtid = threadIdx.x % GT;
+  G.gid = threadIdx.x / GT;
+  const int gtid = G.gtid;
+  double* base = smem + (size_t)G.gid * P.total;
+  G.red = base + P.red;
+  double* s_exch = base + P.exch;
+  double* s_g = base + P.g;
+  double* s_x = base + P.u;
+  double* s_hx = base + P.rhs;
+  int* s_misc = reinterpret_cast<int*>(base + P.ints);  // [0]=nb, [1]=invalid, [2]=work slot
+  uint16_t* s_tb = reinterpret_cast<uint16_t*>(s_misc + 4);
+  uint8_t* s_blk_j = reinterpret_cast<uint8_t*>(s_tb + bc4_tiles(args.n4max) + (bc4_tiles(args.n4max) & 1));
+  uint8_t* s_blk_i = s_blk_j + nbmax;
+  int8_t* s_blk_of = reinterpret_cast<int8_t*>(s_blk_i + nbmax);
+  double* Mm = base + P.Mm;
+  double* Hm = args.scratch + (size_t)(blockIdx.x * args.groups + G.gid) * args.scratch_per_group;
+  BuildView V;
+  V.Mm = Mm; V.ce = base + P.ce; V.fz = base + P.dua; V.arm = base + P.du; V.eq = s_x; V.qz = s_x + 9 * N; V.g = s_g;
+  V.misc = s_misc; V.tb = s_tb; V.blk_j = s_blk_j; V.blk_i = s_blk_i; V.blk_of = s_blk_of;
+  const double mass = cfg.mass;
+  const int count = args.count ? *args.count : args.count_imm;
+
+  while (true) {
+    int slot = 0;
+    if (gtid == 0) slot = atomicAdd(args.work, 1);
+    slot = G.bcast0(slot, s_misc + 2);
+    if (slot >= count) break;
+    const int inst = args.perm ? args.perm[slot] : slot;
+    bool defer = false;
+    if (args.warm_active) {  // a warm-start guess with active rows belongs to the IPM kernel's polish
+      bool any = false;
+      const uint16_t* wa = args.warm_active + (size_t)inst * nbfull;
+      for (int t = gtid; t < nbfull; t += GT) { const unsigned a = wa[t]; any = any || (!(a & 0x8000u) && (a & 0x3ffu)); }
+      defer = !G.all(!any);
+    }
+    bool finite = true;
+    int nb = 0, n = 0, nblk = 0, n4 = 0, matd = 0;
+    if (!defer) {
+      finite = stage_inputs<W>(G, cfg, args, inst, V);
+      nb = s_misc[0];
+      n = 3 * nb; nblk = (n + 3) >> 2; n4 = nblk << 2;
+      matd = ((nblk * (nblk + 1)) >> 1) * kTS;
+      const bool invalid = s_misc[1] != 0;
+      if (!finite || invalid) {
+        for (int t = gtid; t < nf; t += GT) args.forces[(size_t)inst * nf + t] = 0.0;
+        if (args.lam) for (int t = gtid; t < 2 * mfull; t += GT) args.lam[(size_t)inst * 2 * mfull + t] = 0.0;
+        if (args.active) for (int t = gtid; t < nbfull; t += GT) args.active[(size_t)inst * nbfull + t] = 0;
+        if (gtid == 0) {
+          args.status[inst] = !finite ? CMPC_STATUS_NUMERICAL : CMPC_STATUS_INVALID_TABLE;
+          if (args.iters) args.iters[inst] = 0;
+          if (args.kkt) args.kkt[inst] = 0.0;
+        }
+        G.sync();
+        continue;
+      }
+      build_qp<W>(G, cfg, V, Mm, nb);
+      store_mat<W>(G, Hm, Mm, matd);  // the verification below needs H again: keep it in the L2 slab
+      for (int t = gtid; t < n4; t += GT) s_x[t] = t < n ? -s_g[t] : 0.0;  // (eq/qz are dead after the build)
+      G.sync();
+      bool ok = chol_bc4<W>(G, Mm, nblk, s_tb, s_x, s_exch);
+      if (ok) {
+        chol_bwd_bc4<W>(G, Mm, nblk, s_x, s_exch);
+        copy_mat<W>(G, Mm, Hm, matd);
+        G.sync();
+        symv_bc4<W>(G, Mm, n4, nblk, s_x, s_hx);
+      }
+      defer = !ok;
+    }
+    double gs = 1.0, usf = 1.0, stat = 0.0, prim = 0.0;
+    if (!defer) {
+      double gmax = 0.0, umax = 0.0;
+      bool fin = true;
+      for (int t = gtid; t < n; t += GT) {
+        gmax = fmax(gmax, fabs(s_g[t])); umax = fmax(umax, fabs(s_x[t]));
+        stat = fmax(stat, fabs(s_hx[t] + s_g[t]));
+        fin = fin && isfinite(s_x[t]) && isfinite(s_hx[t]);
+      }
+      for (int b = gtid; b < nb; b += GT) {
+        const double ce = V.ce[b];
+        const double ubxy = kFricUb * ce, ubz = mass * kGrav * (double)L * ce;
+        double y[5];
+        cmul5(cfg.mu[s_blk_i[b]], s_x + 3 * b, y);
+        for (int q = 0; q < 5; ++q) prim = fmax(prim, fmax(-y[q], y[q] - (q < 4 ? ubxy : ubz)));
+      }
+      gmax = G.max(gmax); umax = G.max(umax); stat = G.max(stat);
+      gs = 1.0 + gmax; usf = 1.0 + umax;
+      prim = G.max(prim);
+      defer = !(stat <= 1e-9 * gs && prim <= 1e-9 * usf);
+      defer = !G.all(!defer && fin);  // fmax drops NaNs: a non-finite candidate is caught here
+    }
+    if (defer) {
+      if (gtid == 0) args.fail_perm[atomicAdd(args.fail_count, 1)] = inst;
+      G.sync();
+      continue;
+    }
+    // ---- outputs of a verified unconstrained optimum (same conventions as the IPM kernel)
+    for (int t = gtid; t < nf; t += GT) {
+      const int i = t / (3 * N), j = (t % (3 * N)) / 3, q = t % 3;
+      const int b = s_blk_of[j * L + i];
+      args.forces[(size_t)inst * nf + t] = b < 0 ? 0.0 : s_x[3 * b + q];
+    }
+    if (args.lam) for (int t = gtid; t < 2 * mfull; t += GT) args.lam[(size_t)inst * 2 * mfull + t] = 0.0;
+    if (args.active) {
+      for (int t = gtid; t < nbfull; t += GT) {
+        const int b = s_blk_of[t];
+        uint16_t a = 0x8000;
+        if (b >= 0) {
+          const double ce = V.ce[b];
+          const double ubxy = kFricUb * ce, ubz = mass * kGrav * (double)L * ce;
+          double y[5];
+          cmul5(cfg.mu[s_blk_i[b]], s_x + 3 * b, y);
+          a = 0;
+          for (int q = 0; q < 5; ++q)
+            a |= (uint16_t)((y[q] <= 1e-9 * usf ? 1 : 0) << q | (((q < 4 ? ubxy : ubz) - y[q]) <= 1e-9 * usf ? 1 : 0) << (5 + q));
+        }
+        args.active[(size_t)inst * nbfull + t] = a;
+      }
+    }
+    if (gtid == 0) {
+      args.status[inst] = CMPC_STATUS_OK;
+      if (args.iters) args.iters[inst] = 0;
+      if (args.kkt) args.kkt[inst] = fmax(stat / gs, fmax(prim, 0.0) / usf);
     }
     G.sync();
   }

@@ -69,7 +69,10 @@ typedef struct cmpc_config {
   int32_t max_iter;                 /* IPM iteration cap (default 50) */
   double ipm_tol;                   /* scaled residual + gap tolerance (default 1e-9) */
   int32_t polish;                   /* 1 = active-set polish (default), 0 = IPM only */
-  int32_t reserved;
+  int32_t presolve;                 /* 1 (default, needs polish) = first try the unconstrained minimiser
+                                       -H^-1 g: one Cholesky of H; if it satisfies every friction /
+                                       force-limit row it is the optimum (status OK, iters 0), else
+                                       the instance goes through the interior-point iteration */
 } cmpc_config;
 
 typedef struct cmpc_stats {

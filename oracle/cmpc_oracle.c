@@ -481,7 +481,7 @@ static double kkt_scaled(const orc_compact* P, const double* u, const double* zl
  * verification, and up to 6 correction passes.  actl/actu: 5 nb flags in/out.
  * Returns 1 and overwrites u, zl, zu when a verified KKT point is found. */
 static int polish(const orc_compact* P, double gs, double us, unsigned char* actl,
-                  unsigned char* actu, double* u, double* zl, double* zu) {
+                  unsigned char* actu, double* u, double* zl, double* zu, int max_pass) {
   int n = P->n, nb = P->nb, m = 5 * nb;
   double* f0 = malloc((n + 1) * 8); double* Zt = malloc((9 * nb + 1) * 8); /* [b][col][3] */
   int* rk = malloc((nb + 1) * sizeof(int)); int* off = malloc((nb + 1) * sizeof(int));
@@ -489,7 +489,7 @@ static int polish(const orc_compact* P, double gs, double us, unsigned char* act
   double* y = malloc((m + 1) * 8); double* ll = malloc((m + 1) * 8); double* lu = malloc((m + 1) * 8);
   double* Mr = malloc(((size_t)n * n + 1) * 8); double* t = malloc((n + 1) * 8);
   int accepted = 0;
-  for (int pass = 0; pass < 6 && !accepted; ++pass) {
+  for (int pass = 0; pass < max_pass && !accepted; ++pass) {
     int ok_all = 1, nr = 0;
     for (int b = 0; b < nb; ++b) {
       double A[10][3], rhs[10]; int k = 0;
@@ -529,6 +529,7 @@ static int polish(const orc_compact* P, double gs, double us, unsigned char* act
     symv(P->H, n, up, r);
     for (int a = 0; a < n; ++a) r[a] += P->g[a];
     Cmul(P->mu, nb, up, y);
+    if (!(us > 0)) us = 1 + maxabs(up, n); /* presolve: scale of the candidate itself */
     int okm = 1, changed = 0;
     for (int b = 0; b < nb; ++b) {
       double Nrm[10][3], lam[10]; int idx[10], k = 0;
@@ -599,7 +600,10 @@ int cmpc_oracle_solve(const cmpc_config* c, const double* state, const double* d
   double mu0 = maxabs(rd, n); if (mu0 < 1e-2) mu0 = 1e-2;
   for (int t = 0; t < m; ++t) { zl[t] = mu0 / sl[t]; zu[t] = mu0 / su[t]; }
   int npolish = 0, numerical = 0, ipm_ok = 0;
-  for (it = 0; it <= c->max_iter; ++it) {
+  /* Presolve: the unconstrained minimiser -H^-1 g is the optimum whenever it is feasible (no row
+   * active).  One factorisation of H, verified like any polish; otherwise the IPM runs cold. */
+  if (c->polish && c->presolve && polish(&P, gs, 0.0, actl, actu, u, zl, zu, 1)) status = CMPC_STATUS_OK;
+  for (it = 0; status != CMPC_STATUS_OK && it <= c->max_iter; ++it) {
     symv(P.H, n, u, rd);
     for (int a = 0; a < n; ++a) rd[a] += P.g[a];
     CTmul_add(P.mu, nb, zl, -1.0, rd);
@@ -619,7 +623,7 @@ int cmpc_oracle_solve(const cmpc_config* c, const double* state, const double* d
     if (c->polish && ready && npolish < 3) {
       ++npolish;
       for (int t = 0; t < m; ++t) { actl[t] = zl[t] * us > sl[t] * gs; actu[t] = zu[t] * us > su[t] * gs; }
-      if (polish(&P, gs, us, actl, actu, u, zl, zu)) { status = CMPC_STATUS_OK; break; }
+      if (polish(&P, gs, us, actl, actu, u, zl, zu, 6)) { status = CMPC_STATUS_OK; break; }
     }
     if (strict && (!c->polish || npolish >= 3)) break;
     if (mu <= 1e-8 * c->ipm_tol * gs * us) break; /* far past convergence: stop before 0/0 */

@@ -56,10 +56,10 @@ def advance_reference(orc, ccfg, cfg, st, ds, di, hip, forces):
     return st, ds, di
 
 
-@pytest.mark.parametrize("warm", [0, 1])
-def test_rollout_matches_tickwise_oracle(pkg, orc, wl, warm):
+@pytest.mark.parametrize("warm,presolve", [(0, 1), (1, 1), (0, 0), (1, 0)])
+def test_rollout_matches_tickwise_oracle(pkg, orc, wl, warm, presolve):
     from conftest import hard_config
-    for cfg in (wl.default_config(10), hard_config(wl, 10, 0.3)):
+    for cfg in (dict(wl.default_config(10), presolve=presolve), dict(hard_config(wl, 10, 0.3), presolve=presolve)):
         B, ticks = 40, 14
         st, ds, di = wl.make_batch(cfg, B, gaits=wl.GAITS)
         m = pkg.CentroidalMPC.from_dict(cfg)
@@ -79,8 +79,8 @@ def test_rollout_matches_tickwise_oracle(pkg, orc, wl, warm):
         assert np.array_equal(out["des_inputs"][:, :10], rdi[:, :10])
         assert np.abs(out["des_inputs"] - rdi).max() <= 1e-9 and np.abs(out["des_state"] - rds).max() <= 1e-9
         assert (out["status_or"] == 1).all()          # only CMPC_STATUS_OK seen
-        if warm:
-            assert out["iters_sum"].sum() < cold_iters.sum()   # verified guesses skip the interior-point iterations
+        if warm:   # verified guesses skip the interior-point iterations (nothing left to skip when the presolve settles every tick)
+            assert out["iters_sum"].sum() < cold_iters.sum() or cold_iters.sum() == 0
         else:
             assert out["stats"]["launches"] >= 3 * ticks
         m.close()
