@@ -55,6 +55,50 @@ struct cmpc_handle {
 
 namespace {
 
+// ------------------------------------------------------------------ classification
+// Number of free blocks -> size class -> permutation slot.  One 1024-thread block handles 32
+// instances: warp w counts the contact flags of instance 32*blockIdx + w (coalesced reads, all
+// misses in flight at once; the flags may sit in mapped host memory), then warp 0 assigns the
+// slots, bumping each class counter once per block via __match_any_sync -- one atomic per
+// instance on the same address would serialise in L2.
+// bounds = largest nb of classes 0..2 (ascending); class 3 takes the rest.
+__global__ void __launch_bounds__(1024) classify_kernel(const DevConfig cfg, int B, const double* des_inputs, int4 bounds,
+                                                        int32_t* counts, int32_t* perm) {
+  __shared__ int s_nb[32];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 32 + w;
+  const int N = cfg.N, L = cfg.L;
+  if (b < B) {
+    const double* di = des_inputs + (size_t)b * L * (4 * N + 3);
+    int nb = 0;
+    for (int e = lane; e < L * N; e += 32) {
+      const int i = e / N, j = e - i * N;
+      nb += __ldg(di + i * (4 * N + 3) + j) > 0.0 ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nb += __shfl_xor_sync(0xffffffffu, nb, o);
+    if (lane == 0) s_nb[w] = nb;
+  }
+  __syncthreads();
+  if (w != 0) return;
+  const int bb = blockIdx.x * 32 + lane;
+  const bool valid = bb < B;
+  const int mine = valid ? s_nb[lane] : 0;
+  int c = 3;
+  if (mine <= bounds.x) c = 0;
+  else if (mine <= bounds.y) c = 1;
+  else if (mine <= bounds.z) c = 2;
+  if (!valid) c = 4;  // lanes past the end form their own group and do nothing
+  const unsigned peers = __match_any_sync(0xffffffffu, c);
+  const int leader = __ffs(peers) - 1;
+  const int rank = __popc(peers & ((1u << lane) - 1u));
+  int base = 0;
+  if (lane == leader && valid) base = atomicAdd(&counts[c], __popc(peers));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (valid) perm[(size_t)c * B + base + rank] = bb;
+}
+
+
 constexpr size_t kMaxSmem = 232448;  // 227 KB opt-in per CTA on sm_100
 
 struct DevStats {
@@ -324,36 +368,22 @@ void fill_dev(cmpc_handle* h) {
   for (int i = 0; i < CMPC_NUM_WEIGHTS; ++i) d.w[i] = c.weights[i];
 }
 
-template <int W, int MODE, bool MS>
-cudaError_t launch_w(cmpc_handle* h, const cmpc_handle::ClassPlan& p, const SolveArgs& a) {
-  cmpc_solve_kernel<W, MODE, MS><<<p.grid, 32 * W * p.groups, p.smem_bytes, h->stream>>>(h->dev, a);
-  return cudaGetLastError();
-}
-
 template <int MODE>
 int launch_class(cmpc_handle* h, const cmpc_handle::ClassPlan& p, SolveArgs a) {
   a.scratch = p.d_scratch; a.scratch_per_group = p.scratch_per_group;
   a.nbmax = p.nbmax; a.n4max = p.n4max; a.m_in_smem = p.m_in_smem; a.groups = p.groups;
   a.plan = make_plan(h->cfg.horizon, h->cfg.num_legs, p.m_in_smem ? p.W : 8, p.nbmax, p.n4max, p.m_in_smem);
-  cudaError_t e;
-  if (MODE == 1 || !p.m_in_smem) e = launch_w<8, MODE, false>(h, p, a);
-  else if constexpr (MODE == 0) e = p.W == 1 ? launch_w<1, 0, true>(h, p, a) : p.W == 2 ? launch_w<2, 0, true>(h, p, a) : p.W == 4 ? launch_w<4, 0, true>(h, p, a) : launch_w<8, 0, true>(h, p, a);
-  else e = cudaErrorInvalidValue;
+  const int W = (MODE == 1 || !p.m_in_smem) ? 8 : p.W;
+  const cudaError_t e = launch_solve_kernel(W, MODE, p.m_in_smem != 0, p.grid, 32 * W * p.groups, p.smem_bytes, h->stream, h->dev, a);
   if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
   return CMPC_OK;
-}
-
-template <int W>
-cudaError_t launch_pre_w(cmpc_handle* h, const cmpc_handle::ClassPlan& p, const SolveArgs& a) {
-  cmpc_presolve_kernel<W><<<p.grid, 32 * W * p.pre_groups, p.pre_smem_bytes, h->stream>>>(h->dev, a);
-  return cudaGetLastError();
 }
 
 int launch_presolve(cmpc_handle* h, const cmpc_handle::ClassPlan& p, SolveArgs a) {
   a.scratch = p.d_pre_scratch; a.scratch_per_group = p.pre_scratch_per_group;
   a.nbmax = p.nbmax; a.n4max = p.n4max; a.m_in_smem = 1; a.groups = p.pre_groups;
-  a.plan = make_pre_plan(h->cfg.horizon, h->cfg.num_legs, p.W, p.nbmax, p.n4max);
-  const cudaError_t e = p.W == 1 ? launch_pre_w<1>(h, p, a) : p.W == 4 ? launch_pre_w<4>(h, p, a) : launch_pre_w<8>(h, p, a);
+  a.pre = make_pre_plan(h->cfg.horizon, h->cfg.num_legs, p.W, p.nbmax, p.n4max);
+  const cudaError_t e = launch_presolve_kernel(p.W, p.grid, 32 * p.W * p.pre_groups, p.pre_smem_bytes, h->stream, h->dev, a);
   if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, std::string("presolve launch: ") + cudaGetErrorString(e));
   return CMPC_OK;
 }
@@ -414,13 +444,14 @@ int plan_class(cmpc_handle* h, cmpc_handle::ClassPlan& p, int W, int nbmax, int 
   p.scratch_per_group = (size_t)mat_region_doubles(N, L, p.n4max) * (p.m_in_smem ? 1 : 2) + (size_t)((9 * p.nbmax + 1) & ~1);
   CUDA_TRY(h, cudaMalloc(&p.d_scratch, p.scratch_per_group * 8 * (size_t)p.grid * p.groups));
   p.used = true;
-  if (mode == 0 && p.m_in_smem) {  // presolve variant: matrix + three vectors per group
-    const SmemPlan pp = make_pre_plan(N, L, W, p.nbmax, p.n4max);
+  if (mode == 0 && p.m_in_smem) {  // presolve variant: the matrix and one vector per group (make_pre_plan)
+    const PrePlan pp = make_pre_plan(N, L, W, p.nbmax, p.n4max);
     const int pgmax = (W == 1 ? 448 : 256) / (32 * W);
-    p.pre_groups = (int)std::min<size_t>((size_t)pgmax, kMaxSmem / ((size_t)pp.total * 8));
+    const size_t room = kMaxSmem / 8 > (size_t)pp.cta ? kMaxSmem / 8 - pp.cta : 0;
+    p.pre_groups = (int)std::min<size_t>((size_t)pgmax, room / (size_t)pp.total);
     if (p.pre_groups >= 1) {
-      p.pre_smem_bytes = (size_t)pp.total * 8 * p.pre_groups;
-      p.pre_scratch_per_group = (size_t)mat_region_doubles(N, L, p.n4max);
+      p.pre_smem_bytes = ((size_t)pp.cta + (size_t)pp.total * p.pre_groups) * 8;
+      p.pre_scratch_per_group = (size_t)pp.mat;
       CUDA_TRY(h, cudaMalloc(&p.d_pre_scratch, p.pre_scratch_per_group * 8 * (size_t)p.grid * p.pre_groups));
       p.pre_used = true;
     }
@@ -428,15 +459,12 @@ int plan_class(cmpc_handle* h, cmpc_handle::ClassPlan& p, int W, int nbmax, int 
   return CMPC_OK;
 }
 
-template <int W>
-int set_pre_smem_attr(cmpc_handle* h, size_t bytes) {
-  CUDA_TRY(h, cudaFuncSetAttribute(cmpc_presolve_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+int set_smem_attr(cmpc_handle* h, int W, int mode, bool ms, size_t bytes) {
+  CUDA_TRY(h, set_solve_kernel_smem(W, mode, ms, bytes));
   return CMPC_OK;
 }
-
-template <int W, int MODE, bool MS>
-int set_smem_attr(cmpc_handle* h, size_t bytes) {
-  CUDA_TRY(h, cudaFuncSetAttribute(cmpc_solve_kernel<W, MODE, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+int set_pre_smem_attr(cmpc_handle* h, int W, size_t bytes) {
+  CUDA_TRY(h, set_presolve_kernel_smem(W, bytes));
   return CMPC_OK;
 }
 
@@ -558,15 +586,15 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
       size_t& sref = !h->cls[c].m_in_smem ? s8g : h->cls[c].W == 1 ? s1 : h->cls[c].W == 2 ? s2 : h->cls[c].W == 4 ? s4 : s8;
       sref = std::max(sref, h->cls[c].smem_bytes);
     }
-    if (s1 && (rc = set_smem_attr<1, 0, true>(h, s1))) return rc;
-    if (s2 && (rc = set_smem_attr<2, 0, true>(h, s2))) return rc;
-    if (s4 && (rc = set_smem_attr<4, 0, true>(h, s4))) return rc;
-    if (s8 && (rc = set_smem_attr<8, 0, true>(h, s8))) return rc;
-    if (s8g && (rc = set_smem_attr<8, 0, false>(h, s8g))) return rc;
-    if ((rc = set_smem_attr<8, 1, false>(h, h->exp_plan.smem_bytes))) return rc;
-    if (p1 && (rc = set_pre_smem_attr<1>(h, p1))) return rc;
-    if (p4 && (rc = set_pre_smem_attr<4>(h, p4))) return rc;
-    if (p8 && (rc = set_pre_smem_attr<8>(h, p8))) return rc;
+    if (s1 && (rc = set_smem_attr(h, 1, 0, true, s1))) return rc;
+    if (s2 && (rc = set_smem_attr(h, 2, 0, true, s2))) return rc;
+    if (s4 && (rc = set_smem_attr(h, 4, 0, true, s4))) return rc;
+    if (s8 && (rc = set_smem_attr(h, 8, 0, true, s8))) return rc;
+    if (s8g && (rc = set_smem_attr(h, 8, 0, false, s8g))) return rc;
+    if ((rc = set_smem_attr(h, 8, 1, false, h->exp_plan.smem_bytes))) return rc;
+    if (p1 && (rc = set_pre_smem_attr(h, 1, p1))) return rc;
+    if (p4 && (rc = set_pre_smem_attr(h, 4, p4))) return rc;
+    if (p8 && (rc = set_pre_smem_attr(h, 8, p8))) return rc;
   }
   h->max_batch = max_batch;
   h->ready = true;

@@ -41,6 +41,12 @@ struct DevConfig {
   int L, N, zoh, max_iter, polish;
 };
 
+struct PrePlan {  // presolve kernel, see make_pre_plan
+  int T, cta;
+  int x, ce, red, exch, ints, M;  // per-group offsets (doubles)
+  int mat, total;
+};
+
 struct SmemPlan {
   // offsets in doubles from the start of the group's slab
   int ce, g, u, rd, tv, rhs, du, dua;
@@ -73,6 +79,7 @@ struct SolveArgs {
   int m_in_smem;
   int groups;                // groups per CTA
   SmemPlan plan;             // shared-memory layout of one group, computed on the host
+  PrePlan pre;               // presolve kernel: its own shared-memory layout
   int32_t* fail_perm;        // presolve kernel only: instances it could not settle, for the IPM kernel
   int32_t* fail_count;
 };
@@ -488,7 +495,7 @@ __device__ __forceinline__ void ctmul5(double mu, const double* w, double* o) {
 }
 
 // Null space of the active rows of one leg-step block (Gram-Schmidt). Returns rank.
-__device__ __noinline__ int block_nullspace(int k, const double (*A)[3], const double* b, double* f0, double (*Z)[3], bool* ok) {
+static __device__ __noinline__ int block_nullspace(int k, const double (*A)[3], const double* b, double* f0, double (*Z)[3], bool* ok) {
   double Q[3][3];
   int r = 0;
   *ok = true;
@@ -535,7 +542,7 @@ __device__ __noinline__ int block_nullspace(int k, const double (*A)[3], const d
 }
 
 // least squares S' lam = rb for k (<=3) independent normals via normal equations
-__device__ __noinline__ double small_lsq(int k, const double (*S)[3], const double* rb, double* lam) {
+static __device__ __noinline__ double small_lsq(int k, const double (*S)[3], const double* rb, double* lam) {
   double G[3][3], y[3];
   for (int a = 0; a < k; ++a) {
     y[a] = S[a][0] * rb[0] + S[a][1] * rb[1] + S[a][2] * rb[2];
@@ -570,7 +577,7 @@ __device__ __noinline__ double small_lsq(int k, const double (*S)[3], const doub
 }
 
 // lam >= 0 with sum lam_t Nrm_t = rb; enumerates independent subsets (degenerate apex).
-__device__ __noinline__ bool block_multipliers(int k, const double (*Nrm)[3], const double* rb, double tol, double* lam) {
+static __device__ __noinline__ bool block_multipliers(int k, const double (*Nrm)[3], const double* rb, double tol, double* lam) {
   for (int t = 0; t < k; ++t) lam[t] = 0.0;
   if (k == 0) return fmax(fabs(rb[0]), fmax(fabs(rb[1]), fabs(rb[2]))) <= tol;
   double Q[3][3];
@@ -635,49 +642,6 @@ __host__ __device__ inline SmemPlan make_plan(int N, int L, int W, int nbmax, in
   if (m_in_smem) o += mat_region_doubles(N, L, n4max);
   p.total = (o + 1) & ~1;
   return p;
-}
-
-// ------------------------------------------------------------------ classification
-// Number of free blocks -> size class -> permutation slot.  One 1024-thread block handles 32
-// instances: warp w counts the contact flags of instance 32*blockIdx + w (coalesced reads, all
-// misses in flight at once; the flags may sit in mapped host memory), then warp 0 assigns the
-// slots, bumping each class counter once per block via __match_any_sync -- one atomic per
-// instance on the same address would serialise in L2.
-// bounds = largest nb of classes 0..2 (ascending); class 3 takes the rest.
-__global__ void __launch_bounds__(1024) classify_kernel(const DevConfig cfg, int B, const double* des_inputs, int4 bounds,
-                                                        int32_t* counts, int32_t* perm) {
-  __shared__ int s_nb[32];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * 32 + w;
-  const int N = cfg.N, L = cfg.L;
-  if (b < B) {
-    const double* di = des_inputs + (size_t)b * L * (4 * N + 3);
-    int nb = 0;
-    for (int e = lane; e < L * N; e += 32) {
-      const int i = e / N, j = e - i * N;
-      nb += __ldg(di + i * (4 * N + 3) + j) > 0.0 ? 1 : 0;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nb += __shfl_xor_sync(0xffffffffu, nb, o);
-    if (lane == 0) s_nb[w] = nb;
-  }
-  __syncthreads();
-  if (w != 0) return;
-  const int bb = blockIdx.x * 32 + lane;
-  const bool valid = bb < B;
-  const int mine = valid ? s_nb[lane] : 0;
-  int c = 3;
-  if (mine <= bounds.x) c = 0;
-  else if (mine <= bounds.y) c = 1;
-  else if (mine <= bounds.z) c = 2;
-  if (!valid) c = 4;  // lanes past the end form their own group and do nothing
-  const unsigned peers = __match_any_sync(0xffffffffu, c);
-  const int leader = __ffs(peers) - 1;
-  const int rank = __popc(peers & ((1u << lane) - 1u));
-  int base = 0;
-  if (lane == leader && valid) base = atomicAdd(&counts[c], __popc(peers));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (valid) perm[(size_t)c * B + base + rank] = bb;
 }
 
 // ------------------------------------------------------------------ prologue and build (both kernels)
@@ -891,810 +855,46 @@ __device__ __forceinline__ void build_qp(const Group<W>& G, const DevConfig& cfg
     G.sync();
 }
 
-// ------------------------------------------------------------------ the fused kernel
-// MODE 0: solve.  MODE 1: build-export (H, g in the full 3LN layout to global memory).
-template <int W, int MODE, bool MS>
-__global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solve_kernel(const DevConfig cfg, const SolveArgs args) {
-  extern __shared__ __align__(128) double smem[];
-  constexpr int GT = Group<W>::GT;
-  const int N = cfg.N, L = cfg.L, nu = 3 * L;
-  const int nf = 3 * L * N;
-  const int nbfull = L * N, mfull = 5 * nbfull;
-  const int nbmax = args.nbmax, mmax = 5 * nbmax;
-  const SmemPlan& P = args.plan;
-  Group<W> G;
-  G.gtid = threadIdx.x % GT;
-  G.gid = threadIdx.x / GT;
-  const int gtid = G.gtid;
-  double* base = smem + (size_t)G.gid * P.total;
-  G.red = base + P.red;
-  double* s_exch = base + P.exch;
-  double* s_ce = base + P.ce;
-  double* s_g = base + P.g;
-  double* s_u = base + P.u;
-  double* s_rd = base + P.rd;
-  double* s_f0 = s_rd;   // polish only; rd is recomputed after a rejected polish
-  double* s_rhs = base + P.rhs;
-  double* s_fz = s_rhs;  // desired fz: build + start point only
-  double* s_du = base + P.du;
-  double* s_arm = s_du;  // lever arms: build only
-  double* s_tv = base + P.tv;
-  double* s_up = s_du;   // polish only: candidate point (du is dead there; chol's rhs is tv)
-  double* s_eq = s_rd;   // build only: 9N weighted errors then N z-weights, spanning rd..tv
-  double* s_qz = s_rd + 9 * N;
-  double* s_dua = base + P.dua;  // copy of the affine (predictor) direction
-  double* s_zl = base + P.zl;
-  double* s_zu = base + P.zu;
-  int* s_misc = reinterpret_cast<int*>(base + P.ints);  // [0]=nb, [1]=invalid, [2]=work slot, [3]=nr
-  uint16_t* s_off = reinterpret_cast<uint16_t*>(s_misc + 4);
-  uint16_t* s_tb = s_off + nbmax + (nbmax & 1);
-  uint8_t* s_blk_j = reinterpret_cast<uint8_t*>(s_tb + bc4_tiles(args.n4max) + (bc4_tiles(args.n4max) & 1));
-  uint8_t* s_blk_i = s_blk_j + nbmax;
-  uint8_t* s_rk = s_blk_i + nbmax;
-  int8_t* s_blk_of = reinterpret_cast<int8_t*>(s_rk + nbmax);  // [N*L] free block index or -1 (nb <= 127)
-  unsigned char* s_actl = reinterpret_cast<unsigned char*>(s_blk_of + nbfull);
-  unsigned char* s_actu = s_actl + mmax;
-  const int group_global = blockIdx.x * args.groups + G.gid;
-  double* Hm = args.scratch + (size_t)group_global * args.scratch_per_group;
-  double* Mm;
-  if constexpr (MS) Mm = base + P.Mm; else Mm = Hm + mat_region_doubles(N, L, args.n4max);
-  // polish only: null-space bases, 9 doubles per leg-step, behind the matrices in the L2 slab
-  double* g_Zt = Hm + (size_t)mat_region_doubles(N, L, args.n4max) * (MS ? 1 : 2);
-
-  const double mass = cfg.mass;
-  const int count = args.count ? *args.count : args.count_imm;
-
-  while (true) {
-    int slot = 0;
-    if (gtid == 0) slot = atomicAdd(args.work, 1);
-    slot = G.bcast0(slot, s_misc + 2);
-    if (slot >= count) break;
-    const int inst = args.perm ? args.perm[slot] : slot;
-    BuildView V;
-    V.Mm = Mm; V.ce = s_ce; V.fz = s_fz; V.arm = s_arm; V.eq = s_eq; V.qz = s_qz; V.g = s_g;
-    V.misc = s_misc; V.tb = s_tb; V.blk_j = s_blk_j; V.blk_i = s_blk_i; V.blk_of = s_blk_of;
-    const bool finite = stage_inputs<W>(G, cfg, args, inst, V);
-    const int nb = s_misc[0];
-    const int n = 3 * nb, nblk = (n + 3) >> 2, n4 = nblk << 2, m = 5 * nb;
-    const int ntiles = (nblk * (nblk + 1)) >> 1;
-    const int matd = ntiles * kTS;
-    const bool invalid = s_misc[1] != 0;
-
-    if (MODE == 0 && (!finite || invalid)) {
-      for (int t = gtid; t < nf; t += GT) args.forces[(size_t)inst * nf + t] = 0.0;
-      if (args.lam) for (int t = gtid; t < 2 * mfull; t += GT) args.lam[(size_t)inst * 2 * mfull + t] = 0.0;
-      if (args.active) for (int t = gtid; t < nbfull; t += GT) args.active[(size_t)inst * nbfull + t] = 0;
-      if (gtid == 0) {
-        args.status[inst] = !finite ? CMPC_STATUS_NUMERICAL : CMPC_STATUS_INVALID_TABLE;
-        if (args.iters) args.iters[inst] = 0;
-        if (args.kkt) args.kkt[inst] = 0.0;
-      }
-      G.sync();
-      continue;
-    }
-
-    double* Hb;
-    if constexpr (MS) Hb = Mm; else Hb = Hm;
-    build_qp<W>(G, cfg, V, Hb, nb);
-    if constexpr (MS) store_mat<W>(G, Hm, Mm, matd);
-
-    if (MODE == 1) {
-      // export H, g in the full 3LN step-major layout with pinned rows/cols = identity
-      const int p = nf;
-      double* Ho = args.Hout + (size_t)inst * p * p;
-      double* go = args.gout + (size_t)inst * p;
-      for (int t = gtid; t < p * p; t += GT) {
-        const int a = t / p, c = t % p;
-        const int ba = s_blk_of[(a / nu) * L + (a % nu) / 3], bc = s_blk_of[(c / nu) * L + (c % nu) / 3];
-        double v;
-        if (ba < 0 || bc < 0) v = (a == c) ? 1.0 : 0.0;
-        else v = Hb[sidx(3 * ba + a % 3, 3 * bc + c % 3, nblk)];
-        Ho[t] = v;
-      }
-      for (int t = gtid; t < p; t += GT) {
-        const int ba = s_blk_of[(t / nu) * L + (t % nu) / 3];
-        go[t] = ba < 0 ? 0.0 : s_g[3 * ba + t % 3];
-      }
-      if (gtid == 0) args.status[inst] = !finite ? CMPC_STATUS_NUMERICAL : (invalid ? CMPC_STATUS_INVALID_TABLE : CMPC_STATUS_OK);
-      G.sync();
-      continue;
-    }
-
-    // ---- strictly feasible start f = (0, 0, fz0); centred duals
-    for (int b = gtid; b < nb; b += GT) {
-      const double mub = cfg.mu[s_blk_i[b]];
-      double fz = s_fz[b];
-      fz = fmin(fz, 0.5 * mass * kGrav * (double)L * s_ce[b]);
-      fz = fmin(fz, 0.5 * kFricUb * s_ce[b] / mub);
-      s_u[3 * b] = 0.0; s_u[3 * b + 1] = 0.0; s_u[3 * b + 2] = fz;
-    }
-    if (gtid < n4 - n) s_u[n + gtid] = 0.0;
-    if constexpr (!MS) copy_mat<W>(G, Mm, Hm, matd);
-    G.sync();
-    // (s_fz aliases s_rhs, s_arm aliases s_du, s_eq aliases s_rd/s_tv: all dead from here on)
-    if (gtid < n4 - n) { s_rhs[n + gtid] = 0.0; s_du[n + gtid] = 0.0; s_dua[n + gtid] = 0.0; s_rd[n + gtid] = 0.0; s_tv[n + gtid] = 0.0; }
-    symv_bc4<W>(G, Mm, n4, nblk, s_u, s_rd);
-    double gmax = 0.0, r0max = 0.0;
-    for (int t = gtid; t < n; t += GT) { gmax = fmax(gmax, fabs(s_g[t])); r0max = fmax(r0max, fabs(s_rd[t] + s_g[t])); }
-    gmax = G.max(gmax);
-    r0max = G.max(r0max);
-    const double gs = 1.0 + gmax;
-    const double mu0 = fmax(1e-2, r0max);
-    for (int b = gtid; b < nb; b += GT) {
-      const double mub = cfg.mu[s_blk_i[b]];
-      const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];  // :183,199
-      double y[5];
-      cmul5(mub, s_u + 3 * b, y);
-      for (int q = 0; q < 5; ++q) {
-        const double ub = q < 4 ? ubxy : ubz;
-        s_zl[5 * b + q] = mu0 / y[q]; s_zu[5 * b + q] = mu0 / (ub - y[q]);
-      }
-    }
-    G.sync();
-
-    int status = CMPC_STATUS_MAX_ITER, it = 0, npolish = 0;
-    bool numerical = false, ipm_ok = false, m_is_h = true, warm_done = false;
-    double us = 1.0;
-    for (it = 0; it <= cfg.max_iter; ++it) {
-      // ---- residuals (M holds a fresh copy of H here)
-      if (!m_is_h) { copy_mat<W>(G, Mm, Hm, matd); G.sync(); m_is_h = true; }
-      if (it > 0) symv_bc4<W>(G, Mm, n4, nblk, s_u, s_rd);  // it == 0: rd still holds H u0 from the start point
-      double rmax = 0.0, umax = 0.0, gap = 0.0;
-      for (int b = gtid; b < nb; b += GT) {
-        const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
-        double w[5], o[3], ys[5];
-        cmul5(cfg.mu[s_blk_i[b]], s_u + 3 * b, ys);
-        for (int q = 0; q < 5; ++q) {
-          const int t = 5 * b + q;
-          const double sl = ys[q], su = (q < 4 ? ubxy : ubz) - sl;
-          w[q] = s_zl[t] - s_zu[t];
-          gap += sl * s_zl[t] + su * s_zu[t];
-        }
-        ctmul5(cfg.mu[s_blk_i[b]], w, o);
-        for (int q = 0; q < 3; ++q) {
-          const double rr = s_rd[3 * b + q] + s_g[3 * b + q] - o[q];
-          s_rd[3 * b + q] = rr;
-          rmax = fmax(rmax, fabs(rr)); umax = fmax(umax, fabs(s_u[3 * b + q]));
-        }
-      }
-      G.max2_sum(rmax, umax, gap);
-      const double mu = gap / (2.0 * (double)m);
-      us = 1.0 + umax;
-      // Convergence. The dual residual has a round-off floor ~ eps * cond(H + C'SC) once the
-      // gap is small, so the polish (which verifies the KKT conditions itself) is attempted
-      // as soon as the gap is converged and the residual is merely small.
-      const bool conv_mu = mu <= cfg.tol * gs * us;
-      const bool strict = conv_mu && rmax <= cfg.tol * gs;
-      const bool ready = conv_mu && rmax <= 1e4 * cfg.tol * gs;
-      ipm_ok = conv_mu && rmax <= 10.0 * cfg.tol * gs;
-      // Warm start (closed loop): before the first factorisation, try the previous tick's
-      // active set, shifted by one step, as the polish's guess. The polish verifies the KKT
-      // conditions, so a wrong guess only costs its correction passes and the IPM runs cold.
-      const bool warm_now = cfg.polish && args.warm_active != nullptr && it == 0 && !warm_done;
-      if (cfg.polish && ((ready && npolish < 3) || warm_now)) {
-        bool any_act = false;
-        if (warm_now) {
-          warm_done = true;
-          const uint16_t* wa = args.warm_active + (size_t)inst * nbfull;
-          for (int b = gtid; b < nb; b += GT) {
-            const int j = s_blk_j[b], i = s_blk_i[b];
-            const int jj = j + 1 < N ? j + 1 : j;
-            const unsigned a = wa[jj * L + i];
-            for (int q = 0; q < 5; ++q) {
-              const bool al = !(a & 0x8000u) && ((a >> q) & 1u), au = !(a & 0x8000u) && ((a >> (5 + q)) & 1u);
-              s_actl[5 * b + q] = al; s_actu[5 * b + q] = au;
-              any_act = any_act || al || au;
-            }
-          }
-        } else {
-          ++npolish;
-          for (int b = gtid; b < nb; b += GT) {
-            const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
-            double ys[5];
-            cmul5(cfg.mu[s_blk_i[b]], s_u + 3 * b, ys);
-            for (int q = 0; q < 5; ++q) {
-              const int t = 5 * b + q;
-              const double sl = ys[q], su = (q < 4 ? ubxy : ubz) - sl;
-              const bool al = s_zl[t] * us > sl * gs, au = s_zu[t] * us > su * gs;
-              s_actl[t] = al; s_actu[t] = au;
-              any_act = any_act || al || au;
-            }
-          }
-        }
-        bool none_active = G.all(!any_act);
-        // ---- active-set polish with correction passes
-        bool accepted = false;
-        for (int pass = 0; pass < 6 && !accepted; ++pass) {
-          int nr, nblk_r;
-          if (none_active) {
-            // no active row: Z = I, f0 = 0, the reduced system is (H, -g) itself
-            nr = n; nblk_r = nblk;
-            for (int b = gtid; b < nb; b += GT) { s_rk[b] = 0; s_off[b] = 3 * b; }
-            for (int t = gtid; t < n4; t += GT) { s_f0[t] = 0.0; s_tv[t] = t < n ? -s_g[t] : 0.0; }
-            if (!m_is_h) copy_mat<W>(G, Mm, Hm, matd);
-            G.sync();
-          } else {
-            bool ok_all = true;
-            for (int b = gtid; b < nb; b += GT) {
-              const double mub = cfg.mu[s_blk_i[b]];
-              const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
-              double A[10][3], rhsb[10], Z[3][3], f0[3];
-              int k = 0;
-              for (int q = 0; q < 5; ++q) if (s_actl[5 * b + q]) { row_vec(mub, q, A[k]); rhsb[k++] = 0.0; }
-              for (int q = 0; q < 5; ++q) if (s_actu[5 * b + q]) { row_vec(mub, q, A[k]); rhsb[k++] = q < 4 ? ubxy : ubz; }
-              bool okb;
-              const int rk = block_nullspace(k, A, rhsb, f0, Z, &okb);
-              ok_all = ok_all && okb;
-              s_rk[b] = rk;
-              for (int q = 0; q < 3; ++q) s_f0[3 * b + q] = f0[q];
-              for (int cc = 0; cc < 3 - rk; ++cc)
-                for (int q = 0; q < 3; ++q) g_Zt[9 * b + 3 * cc + q] = Z[cc][q];
-            }
-            if (gtid < n4 - n) s_f0[n + gtid] = 0.0;
-            ok_all = G.all(ok_all);
-            if (!ok_all) break;
-            if (gtid == 0) {
-              int o = 0;
-              for (int b = 0; b < nb; ++b) { s_off[b] = o; o += 3 - s_rk[b]; }
-              s_misc[3] = o;
-            }
-            if (!m_is_h) copy_mat<W>(G, Mm, Hm, matd);
-            G.sync();
-            nr = s_misc[3];
-            nblk_r = (nr + 3) >> 2;
-            const int nr4 = nblk_r << 2;
-            // r = H f0 + g   (H read from the shared copy)
-            symv_bc4<W>(G, Mm, n4, nblk, s_f0, s_rhs);
-            for (int t = gtid; t < n; t += GT) s_rhs[t] += s_g[t];
-            G.sync();
-            // reduced system Z'HZ t = -Z'(H f0 + g); H is read from the global copy, the
-            // reduced matrix is assembled in M
-            {
-              const int matr = bc4_doubles(nr4);
-              for (int t = gtid; t < matr; t += GT) Mm[t] = 0.0;
-            }
-            for (int b = gtid; b < nb; b += GT)
-              for (int cc = 0; cc < 3 - s_rk[b]; ++cc) {
-                const double* z = g_Zt + 9 * b + 3 * cc;
-                s_tv[s_off[b] + cc] = -(__ldcg(z) * s_rhs[3 * b] + __ldcg(z + 1) * s_rhs[3 * b + 1] + __ldcg(z + 2) * s_rhs[3 * b + 2]);
-              }
-            G.sync();
-            if (gtid < nr4 - nr) { s_tv[nr + gtid] = 0.0; Mm[midx(nr + gtid, nr + gtid, nblk_r)] = 1.0; }
-            const int npairs = (nb * (nb + 1)) >> 1;
-            for (int idx = gtid; idx < npairs; idx += GT) {
-              int a = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
-              while (((a + 1) * (a + 2)) >> 1 <= idx) ++a;
-              while ((a * (a + 1)) >> 1 > idx) --a;
-              const int b2 = idx - ((a * (a + 1)) >> 1), b = a;
-              const int d1 = 3 - s_rk[b], d2 = 3 - s_rk[b2];
-              if (d1 == 0 || d2 == 0) continue;
-              double Hb3[3][3], Za[3][3], Zb[3][3];
-              for (int aa = 0; aa < 3; ++aa)
-                for (int bb = 0; bb < 3; ++bb) {
-                  Hb3[aa][bb] = __ldcg(Hm + sidx(3 * b + aa, 3 * b2 + bb, nblk));
-                  Za[aa][bb] = aa < d1 ? __ldcg(g_Zt + 9 * b + 3 * aa + bb) : 0.0;
-                  Zb[aa][bb] = aa < d2 ? __ldcg(g_Zt + 9 * b2 + 3 * aa + bb) : 0.0;
-                }
-              for (int cc = 0; cc < d1; ++cc)
-                for (int c2 = 0; c2 < d2; ++c2) {
-                  if (b == b2 && c2 > cc) continue;  // lower part of the diagonal block; mirrored below
-                  const double* z = Za[cc];
-                  const double* z2 = Zb[c2];
-                  double sacc = 0.0;
-                  for (int aa = 0; aa < 3; ++aa)
-                    for (int bb = 0; bb < 3; ++bb) sacc += z[aa] * Hb3[aa][bb] * z2[bb];
-                  const int gi = s_off[b] + cc, gj = s_off[b2] + c2;  // gi >= gj
-                  Mm[midx(gi, gj, nblk_r)] = sacc;
-                  if ((gi >> 2) == (gj >> 2)) Mm[midx(gj, gi, nblk_r)] = sacc;
-                }
-            }
-            G.sync();
-            if (nr > 0) {
-              for (int bj = gtid; bj < nblk_r; bj += GT) {
-                const int o = blkoff(bj, bj, nblk_r);
-                for (int bi = bj; bi < nblk_r; ++bi) s_tb[o + bi - bj] = (uint16_t)(bi | (bj << 8));
-              }
-              G.sync();
-            }
-          }
-          m_is_h = false;
-          bool fact_ok = true;
-          if (nr > 0) {
-            fact_ok = chol_bc4<W>(G, Mm, nblk_r, s_tb, s_tv, s_exch);  // forward pass fused
-            if (fact_ok) chol_bwd_bc4<W>(G, Mm, nblk_r, s_tv, s_exch);
-          }
-          if (!none_active && nr > 0) {  // restore the tile table of the full system
-            for (int bj = gtid; bj < nblk; bj += GT) {
-              const int o = blkoff(bj, bj, nblk);
-              for (int bi = bj; bi < nblk; ++bi) s_tb[o + bi - bj] = (uint16_t)(bi | (bj << 8));
-            }
-          }
-          if (!fact_ok) break;
-          for (int b = gtid; b < nb; b += GT) {
-            double f[3] = {s_f0[3 * b], s_f0[3 * b + 1], s_f0[3 * b + 2]};
-            if (none_active) {
-              for (int q = 0; q < 3; ++q) f[q] = s_tv[3 * b + q];
-            } else {
-              for (int cc = 0; cc < 3 - s_rk[b]; ++cc) {
-                const double tv = s_tv[s_off[b] + cc];
-                for (int q = 0; q < 3; ++q) f[q] += __ldcg(g_Zt + 9 * b + 3 * cc + q) * tv;
-              }
-            }
-            for (int q = 0; q < 3; ++q) s_up[3 * b + q] = f[q];
-          }
-          if (gtid < n4 - n) s_up[n + gtid] = 0.0;
-          copy_mat<W>(G, Mm, Hm, matd);
-          m_is_h = true;
-          G.sync();
-          symv_bc4<W>(G, Mm, n4, nblk, s_up, s_rhs);
-          // multipliers, verification, correction; when the pass verifies, the same loop runs a
-          // second time to commit the multipliers (nothing is stored per row in between)
-          bool good = false;
-          for (int commit = 0; commit < 2; ++commit) {
-            bool okm = true, changed = false, any_act2 = false;
-            for (int b = gtid; b < nb; b += GT) {
-              const double mub = cfg.mu[s_blk_i[b]];
-              const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
-              double rb[3], y[5], ll[5] = {0, 0, 0, 0, 0}, lu[5] = {0, 0, 0, 0, 0};
-              for (int q = 0; q < 3; ++q) rb[q] = s_rhs[3 * b + q] + s_g[3 * b + q];
-              if (none_active) {
-                okm = okm && fmax(fabs(rb[0]), fmax(fabs(rb[1]), fabs(rb[2]))) <= 1e-9 * gs;
-              } else {
-                double Nrm[10][3], lam[10];
-                int idx[10], k = 0;
-                for (int q = 0; q < 5; ++q) if (s_actl[5 * b + q]) { row_vec(mub, q, Nrm[k]); idx[k++] = q; }
-                for (int q = 0; q < 5; ++q) if (s_actu[5 * b + q]) {
-                  row_vec(mub, q, Nrm[k]);
-                  Nrm[k][0] = -Nrm[k][0]; Nrm[k][1] = -Nrm[k][1]; Nrm[k][2] = -Nrm[k][2];
-                  idx[k++] = 5 + q;
-                }
-                okm = block_multipliers(k, Nrm, rb, 1e-9 * gs, lam) && okm;
-                for (int sI = 0; sI < k; ++sI) { if (idx[sI] < 5) ll[idx[sI]] = lam[sI]; else lu[idx[sI] - 5] = lam[sI]; }
-              }
-              if (commit) {
-                for (int q = 0; q < 5; ++q) { s_zl[5 * b + q] = ll[q]; s_zu[5 * b + q] = lu[q]; }
-                continue;
-              }
-              cmul5(mub, s_up + 3 * b, y);
-              for (int q = 0; q < 5; ++q) {
-                const double ub = q < 4 ? ubxy : ubz;
-                const double sl = y[q], su = ub - y[q];
-                const bool vl = sl < -1e-9 * us, vu = su < -1e-9 * us;
-                const bool nl = ll[q] < -1e-9 * gs, nuu = lu[q] < -1e-9 * gs;
-                if (vl || vu || nl || nuu) changed = true;
-                const bool al = (s_actl[5 * b + q] || vl) && !nl, au = (s_actu[5 * b + q] || vu) && !nuu;
-                s_actl[5 * b + q] = al; s_actu[5 * b + q] = au;
-                any_act2 = any_act2 || al || au;
-              }
-            }
-            if (commit) break;
-            good = G.all(okm && !changed);
-            none_active = G.all(!any_act2);  // unchanged when the pass verified (flags did not move)
-            if (!good) break;
-          }
-          if (good) accepted = true;
-        }
-        if (accepted) {
-          for (int t = gtid; t < n; t += GT) s_u[t] = s_up[t];
-          G.sync();
-          status = CMPC_STATUS_OK;
-          break;
-        }
-        G.sync();
-        // polish not accepted: rd was used as f0 scratch -> recompute the residual
-        if (!m_is_h) { copy_mat<W>(G, Mm, Hm, matd); G.sync(); m_is_h = true; }
-        symv_bc4<W>(G, Mm, n4, nblk, s_u, s_rd);
-        for (int b = gtid; b < nb; b += GT) {
-          double w[5], o[3];
-          for (int q = 0; q < 5; ++q) w[q] = s_zl[5 * b + q] - s_zu[5 * b + q];
-          ctmul5(cfg.mu[s_blk_i[b]], w, o);
-          for (int q = 0; q < 3; ++q) s_rd[3 * b + q] += s_g[3 * b + q] - o[q];
-        }
-        G.sync();
-      }
-      if (strict && (!cfg.polish || npolish >= 3)) break;
-      if (mu <= 1e-8 * cfg.tol * gs * us) break;  // far past convergence: stop before 0/0
-      if (it == cfg.max_iter) break;
-
-      // ---- M = H + C' diag(zl/sl + zu/su) C  (only the 3x3 diagonal blocks change), and the
-      // affine (predictor) right-hand side  -rd + C'(rcl/sl - rcu/su)  with rc = -s z
-      for (int b = gtid; b < nb; b += GT) {
-        const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
-        double sg[5], tq[5], o[3], ys[5];
-        cmul5(cfg.mu[s_blk_i[b]], s_u + 3 * b, ys);
-        for (int q = 0; q < 5; ++q) {
-          const int t = 5 * b + q;
-          const double sl = ys[q], su = (q < 4 ? ubxy : ubz) - sl;
-          const double isl = fast_rcp(sl), isu = fast_rcp(su);
-          sg[q] = s_zl[t] * isl + s_zu[t] * isu;
-          tq[q] = s_zu[t] - s_zl[t];
-        }
-        const double mb = cfg.mu[s_blk_i[b]], sx = sg[0] + sg[1], sy = sg[2] + sg[3];
-        const int g0 = 3 * b, g1 = g0 + 1, g2 = g0 + 2;
-        Mm[midx(g0, g0, nblk)] += sx;
-        Mm[midx(g1, g1, nblk)] += sy;
-        Mm[midx(g2, g2, nblk)] += mb * mb * (sx + sy) + sg[4];
-        Mm[midx(g2, g0, nblk)] += mb * (sg[1] - sg[0]);
-        Mm[midx(g2, g1, nblk)] += mb * (sg[3] - sg[2]);
-        ctmul5(mb, tq, o);
-        for (int q = 0; q < 3; ++q) s_du[3 * b + q] = -s_rd[3 * b + q] + o[q];
-      }
-      m_is_h = false;
-      G.sync();
-      // factor; the predictor's forward substitution is fused into the sweep
-      if (!chol_bc4<W>(G, Mm, nblk, s_tb, s_du, s_exch)) { numerical = true; break; }
-
-      // Per-row step quantities are recomputed where needed instead of stored: with s = slack,
-      // z = multiplier, cd = a_r . du:  dz_l = (rc_l - z_l cd) / s_l,  dz_u = (rc_u + z_u cd) / s_u,
-      // rc = -s z  (+ sigma mu -/+ cdA dzA in the corrector, A = affine step kept in dua).
-      double tmax = 0.0, sigma = 0.0;
-      for (int phase = 0; phase < 2; ++phase) {
-        // phase 0: affine predictor; phase 1: centred corrector (Mehrotra)
-        if (phase) {
-          for (int t = gtid; t < n4; t += GT) s_dua[t] = s_du[t];
-          G.sync();
-          for (int b = gtid; b < nb; b += GT) {
-            const double mub = cfg.mu[s_blk_i[b]];
-            const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
-            double tq[5], o[3], ys[5], ya[5];
-            cmul5(mub, s_u + 3 * b, ys);
-            cmul5(mub, s_dua + 3 * b, ya);
-            for (int q = 0; q < 5; ++q) {
-              const int t = 5 * b + q;
-              const double sl = ys[q], su = (q < 4 ? ubxy : ubz) - sl, zl = s_zl[t], zu = s_zu[t];
-              const double isl = fast_rcp(sl), isu = fast_rcp(su);
-              const double dla = (-sl * zl - zl * ya[q]) * isl, dua_ = (-su * zu + zu * ya[q]) * isu;
-              const double rcl = -sl * zl + sigma * mu - ya[q] * dla;
-              const double rcu = -su * zu + sigma * mu + ya[q] * dua_;
-              tq[q] = rcl * isl - rcu * isu;
-            }
-            ctmul5(mub, tq, o);
-            for (int q = 0; q < 3; ++q) s_du[3 * b + q] = -s_rd[3 * b + q] + o[q];
-          }
-          G.sync();
-          chol_fwd_bc4<W>(G, Mm, nblk, s_du, s_exch);
-        }
-        chol_bwd_bc4<W>(G, Mm, nblk, s_du, s_exch);
-        // step to the boundary: alpha_max = 1 / max_i(-ds_i/s_i, -dz_i/z_i)
-        double tloc = 0.0;
-        for (int b = gtid; b < nb; b += GT) {
-          const double mub = cfg.mu[s_blk_i[b]];
-          const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
-          double ys[5], yd[5], ya[5];
-          cmul5(mub, s_u + 3 * b, ys);
-          cmul5(mub, s_du + 3 * b, yd);
-          if (phase) cmul5(mub, s_dua + 3 * b, ya);
-          for (int q = 0; q < 5; ++q) {
-            const int t = 5 * b + q;
-            const double sl = ys[q], su = (q < 4 ? ubxy : ubz) - sl, zl = s_zl[t], zu = s_zu[t];
-            const double isl = fast_rcp(sl), isu = fast_rcp(su);
-            double rcl = -sl * zl, rcu = -su * zu;
-            if (phase) {
-              const double dla = (rcl - zl * ya[q]) * isl, dua_ = (rcu + zu * ya[q]) * isu;
-              rcl += sigma * mu - ya[q] * dla; rcu += sigma * mu + ya[q] * dua_;
-            }
-            const double cd = yd[q];
-            const double dl = (rcl - zl * cd) * isl;
-            const double du_ = (rcu + zu * cd) * isu;
-            tloc = fmax(tloc, fmax(-cd * isl, cd * isu));
-            tloc = fmax(tloc, fmax(-dl * fast_rcp(zl), -du_ * fast_rcp(zu)));
-          }
-        }
-        tmax = G.max(tloc);
-        if (!phase) {
-          const double alpha = tmax > 1.0 ? 1.0 / tmax : 1.0;
-          double ga = 0.0;
-          for (int b = gtid; b < nb; b += GT) {
-            const double mub = cfg.mu[s_blk_i[b]];
-            const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
-            double ys[5], yd[5];
-            cmul5(mub, s_u + 3 * b, ys);
-            cmul5(mub, s_du + 3 * b, yd);
-            for (int q = 0; q < 5; ++q) {
-              const int t = 5 * b + q;
-              const double sl = ys[q], su = (q < 4 ? ubxy : ubz) - sl, zl = s_zl[t], zu = s_zu[t];
-              const double cd = yd[q];
-              const double dl = (-sl * zl - zl * cd) * fast_rcp(sl), du_ = (-su * zu + zu * cd) * fast_rcp(su);
-              ga += (sl + alpha * cd) * (zl + alpha * dl) + (su - alpha * cd) * (zu + alpha * du_);
-            }
-          }
-          ga = G.sum(ga);
-          const double ratio = ga / gap;
-          sigma = ratio * ratio * ratio;
-        }
-      }
-      // fraction to the boundary tau -> 1 as the gap closes (superlinear tail)
-      const double tau = fmax(0.995, 1.0 - mu / (gs * us));
-      const double alpha = fmin(1.0, tau / fmax(tmax, 1e-300));
-      bool fin = true;
-      for (int b = gtid; b < nb; b += GT) {
-        const double mub = cfg.mu[s_blk_i[b]];
-        const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
-        double ys[5], yd[5], ya[5];
-        cmul5(mub, s_u + 3 * b, ys);       // slacks at the current point (before the update)
-        cmul5(mub, s_du + 3 * b, yd);
-        cmul5(mub, s_dua + 3 * b, ya);
-        for (int q = 0; q < 5; ++q) {
-          const int t = 5 * b + q;
-          const double sl = ys[q], su = (q < 4 ? ubxy : ubz) - sl, zl = s_zl[t], zu = s_zu[t];
-          const double isl = fast_rcp(sl), isu = fast_rcp(su);
-          const double dla = (-sl * zl - zl * ya[q]) * isl, dua_ = (-su * zu + zu * ya[q]) * isu;
-          const double rcl = -sl * zl + sigma * mu - ya[q] * dla;
-          const double rcu = -su * zu + sigma * mu + ya[q] * dua_;
-          s_zl[t] = zl + alpha * (rcl - zl * yd[q]) * isl;
-          s_zu[t] = zu + alpha * (rcu + zu * yd[q]) * isu;
-        }
-        for (int q = 0; q < 3; ++q) {
-          const double v = s_u[3 * b + q] + alpha * s_du[3 * b + q];
-          s_u[3 * b + q] = v; fin = fin && isfinite(v);
-        }
-      }
-      fin = G.all(fin);
-      if (!fin) { numerical = true; break; }
-    }
-    if (numerical) status = CMPC_STATUS_NUMERICAL;
-    else if (status != CMPC_STATUS_OK) status = ipm_ok ? CMPC_STATUS_OK_IPM : CMPC_STATUS_MAX_ITER;
-
-    // ---- outputs
-    if (!numerical) {
-      // scaled KKT residual (same definition as the oracle)
-      if (status != CMPC_STATUS_OK) {  // an accepted polish left H u in s_rhs already
-        if (!m_is_h) { copy_mat<W>(G, Mm, Hm, matd); G.sync(); m_is_h = true; }
-        symv_bc4<W>(G, Mm, n4, nblk, s_u, s_rhs);
-      }
-      double stat = 0.0, umax = 0.0, prim = 0.0, dual = 0.0, comp = 0.0;
-      for (int b = gtid; b < nb; b += GT) {
-        const double mub = cfg.mu[s_blk_i[b]];
-        const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
-        double w[5], o[3], y[5];
-        for (int q = 0; q < 5; ++q) w[q] = s_zl[5 * b + q] - s_zu[5 * b + q];
-        ctmul5(mub, w, o);
-        cmul5(mub, s_u + 3 * b, y);
-        for (int q = 0; q < 3; ++q) {
-          stat = fmax(stat, fabs(s_rhs[3 * b + q] + s_g[3 * b + q] - o[q]));
-          umax = fmax(umax, fabs(s_u[3 * b + q]));
-        }
-        for (int q = 0; q < 5; ++q) {
-          const double ub = q < 4 ? ubxy : ubz;
-          const double sl = y[q], su = ub - y[q], zl = s_zl[5 * b + q], zu = s_zu[5 * b + q];
-          prim = fmax(prim, fmax(-sl, -su));
-          dual = fmax(dual, fmax(-zl, -zu));
-          comp = fmax(comp, fmax(fabs(zl * sl), fabs(zu * su)));
-        }
-      }
-      stat = G.max(stat);
-      umax = G.max(umax);
-      prim = G.max(prim);
-      dual = G.max(dual);
-      comp = G.max(comp);
-      const double usf = 1.0 + umax;
-      const double kkt = fmax(fmax(stat / gs, prim / usf), fmax(dual / gs, comp / (gs * usf)));
-      // reported active set. Polished: the rows with zero slack at the KKT point (primal
-      // definition, unique because the optimum is unique -- the polish's working set can omit
-      // redundant rows at the degenerate apex f = 0). Otherwise: the IPM guess.
-      for (int b = gtid; b < nb; b += GT) {
-        const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
-        double ys[5];
-        cmul5(cfg.mu[s_blk_i[b]], s_u + 3 * b, ys);
-        for (int q = 0; q < 5; ++q) {
-          const int t = 5 * b + q;
-          const double sl = ys[q], su = (q < 4 ? ubxy : ubz) - sl;
-          if (status == CMPC_STATUS_OK) { s_actl[t] = sl <= 1e-9 * usf; s_actu[t] = su <= 1e-9 * usf; }
-          else { s_actl[t] = s_zl[t] * usf > sl * gs; s_actu[t] = s_zu[t] * usf > su * gs; }
-        }
-      }
-      G.sync();
-      // forces in the reference's per-leg order [L][N][3] (CentroidalMPC.cpp:270)
-      for (int t = gtid; t < nf; t += GT) {
-        const int i = t / (3 * N), j = (t % (3 * N)) / 3, q = t % 3;
-        const int b = s_blk_of[j * L + i];
-        args.forces[(size_t)inst * nf + t] = b < 0 ? 0.0 : s_u[3 * b + q];
-      }
-      if (args.lam) {
-        for (int t = gtid; t < 2 * mfull; t += GT) {
-          const int side = t / mfull, rem = t % mfull, ji = rem / 5, q = rem % 5;
-          const int b = s_blk_of[ji];
-          args.lam[(size_t)inst * 2 * mfull + t] = b < 0 ? 0.0 : (side ? s_zu[5 * b + q] : s_zl[5 * b + q]);
-        }
-      }
-      if (args.active) {
-        for (int t = gtid; t < nbfull; t += GT) {
-          const int b = s_blk_of[t];
-          uint16_t a = 0x8000;
-          if (b >= 0) {
-            a = 0;
-            for (int q = 0; q < 5; ++q) a |= (uint16_t)((s_actl[5 * b + q] ? 1 : 0) << q | (s_actu[5 * b + q] ? 1 : 0) << (5 + q));
-          }
-          args.active[(size_t)inst * nbfull + t] = a;
-        }
-      }
-      if (gtid == 0) {
-        args.status[inst] = status;
-        if (args.iters) args.iters[inst] = it;
-        if (args.kkt) args.kkt[inst] = kkt;
-      }
-    } else {
-      for (int t = gtid; t < nf; t += GT) args.forces[(size_t)inst * nf + t] = 0.0;
-      if (args.lam) for (int t = gtid; t < 2 * mfull; t += GT) args.lam[(size_t)inst * 2 * mfull + t] = 0.0;
-      if (args.active) for (int t = gtid; t < nbfull; t += GT) args.active[(size_t)inst * nbfull + t] = 0;
-      if (gtid == 0) {
-        args.status[inst] = status;
-        if (args.iters) args.iters[inst] = it;
-        if (args.kkt) args.kkt[inst] = 0.0;
-      }
-    }
-    G.sync();
-  }
-}
-
-// ------------------------------------------------------------------ presolve kernel
-// Most ticks of a legged MPC have no friction or force-limit row active (the reference's weights make
-// force tracking dominate), and then the optimum is the unconstrained minimiser -H^-1 g.  This kernel
-// settles exactly those instances with ONE Cholesky of H: build, factor (forward substitution fused),
-// back-substitute, then verify on the original H -- stationarity |H u + g| <= 1e-9 gs and every row
-// of 0 <= F f <= ub satisfied to -1e-9 us, the polish's own acceptance test with an empty working
-// set -- and write the outputs (status OK, iters 0, multipliers 0).  Anything else (a violated row, a
-// warm-start guess with active rows, a failed pivot) is appended to fail_perm and goes through the
-// interior-point kernel.  Per group it needs the matrix and three vectors only, so more instances are
-// resident per SM than in the IPM kernel.  Shared-memory plan: make_pre_plan (fields of SmemPlan reused:
-// u = the solution, rhs = H u; rd..tv host eq/qz during the build).
-__host__ __device__ inline SmemPlan make_pre_plan(int N, int L, int W, int nbmax, int n4max) {
-  SmemPlan p;
+// ------------------------------------------------------------------ presolve kernel: shared-memory plan
+// Chunk-major tile layout of the presolve kernel (cmpc_presolve.cu): tile t of the BC4 ordering is
+// eight 16-byte chunks (row a, column pair h -> chunk 2a + h) stored at double2 index  chunk * T + t
+// with T odd.  Lanes that walk consecutive tiles, or the four rows of one tile, then fall into
+// distinct 16-byte bank groups WITHOUT the padding of the kTS = 18 layout -- 1936 instead of 2160
+// doubles at n = 60, which is what lets 14 instances share an SM (two waves for a 4096 batch).
+__host__ __device__ inline PrePlan make_pre_plan(int N, int L, int W, int nbmax, int n4max) {
+  PrePlan p;
+  const int tiles = bc4_tiles(n4max);
+  p.T = tiles | 1;
+  // CTA-shared tables: z1[N], z2[N] (z-weighted power-stacking sums), wf[3L], wr[3L]
+  p.cta = (2 * N + 6 * L + 1) & ~1;
   int o = 0;
   auto take = [&](int cnt) { int r = o; o += (cnt + 1) & ~1; return r; };
+  p.x = take(n4max);          // rhs staging, lever arms during the build, then y and the solution
   p.ce = take(nbmax);
-  p.dua = take(nbmax);      // desired fz
-  p.du = take(3 * nbmax);   // lever arms
-  p.g = take(n4max);
-  const int nv = (2 * n4max >= 10 * N + 2) ? n4max : (10 * N + 2 + 1) / 2;
-  p.u = take(nv); p.rhs = take(nv);  // eq[9N], qz[N] live here during the build
-  p.rd = p.u; p.tv = p.rhs;
-  p.zl = p.zu = 0;
-  p.red = take(W > 1 ? 3 * W : 2);
+  p.red = take(W > 1 ? 3 * W : 0);
   p.exch = take(8);
-  const int nbytes = 16 + 2 * nbmax + 2 * bc4_tiles(n4max) + 2 + 2 * nbmax + N * L;
+  // misc int32[4]; tile table uint16[tiles]; blk_j, blk_i uint8[nbmax]; blk_of int8[N L]
+  const int nbytes = 16 + 2 * (tiles + (tiles & 1)) + 2 * nbmax + N * L;
   p.ints = take((nbytes + 7) / 8);
-  o = (o + 1) & ~1;
-  p.Mm = o;
-  o += mat_region_doubles(N, L, n4max);
-  p.total = (o + 1) & ~1;
+  p.M = o;
+  // the matrix region also stages [inputs | eq (9N) | qz (N) | fz (nbmax)] before the build
+  const int nin = (9 + 3 * L) + 9 * (N + 1) + L * (4 * N + 3);
+  const int stage = ((nin + 1) & ~1) + 10 * N + nbmax + 2;
+  p.mat = 16 * p.T > stage ? 16 * p.T : stage;
+  p.mat = (p.mat + 1) & ~1;
+  o += p.mat;
+  p.total = o;
   return p;
 }
 
-template <int W>
-__global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const DevConfig cfg, const SolveArgs args) {
-  extern __shared__ __align__(128) double smem[];
-  constexpr int GT = Group<W>::GT;
-  const int N = cfg.N, L = cfg.L;
-  const int nf = 3 * L * N, nbfull = L * N, mfull = 5 * nbfull;
-  const int nbmax = args.nbmax;
-  const SmemPlan& P = args.plan;
-  Group<W> G;
-  G.gtid = threadIdx.x % GT;
-  G.gid = threadIdx.x / GT;
-  const int gtid = G.gtid;
-  double* base = smem + (size_t)G.gid * P.total;
-  G.red = base + P.red;
-  double* s_exch = base + P.exch;
-  double* s_g = base + P.g;
-  double* s_x = base + P.u;
-  double* s_hx = base + P.rhs;
-  int* s_misc = reinterpret_cast<int*>(base + P.ints);  // [0]=nb, [1]=invalid, [2]=work slot
-  uint16_t* s_tb = reinterpret_cast<uint16_t*>(s_misc + 4);
-  uint8_t* s_blk_j = reinterpret_cast<uint8_t*>(s_tb + bc4_tiles(args.n4max) + (bc4_tiles(args.n4max) & 1));
-  uint8_t* s_blk_i = s_blk_j + nbmax;
-  int8_t* s_blk_of = reinterpret_cast<int8_t*>(s_blk_i + nbmax);
-  double* Mm = base + P.Mm;
-  double* Hm = args.scratch + (size_t)(blockIdx.x * args.groups + G.gid) * args.scratch_per_group;
-  BuildView V;
-  V.Mm = Mm; V.ce = base + P.ce; V.fz = base + P.dua; V.arm = base + P.du; V.eq = s_x; V.qz = s_x + 9 * N; V.g = s_g;
-  V.misc = s_misc; V.tb = s_tb; V.blk_j = s_blk_j; V.blk_i = s_blk_i; V.blk_of = s_blk_of;
-  const double mass = cfg.mass;
-  const int count = args.count ? *args.count : args.count_imm;
-
-  while (true) {
-    int slot = 0;
-    if (gtid == 0) slot = atomicAdd(args.work, 1);
-    slot = G.bcast0(slot, s_misc + 2);
-    if (slot >= count) break;
-    const int inst = args.perm ? args.perm[slot] : slot;
-    bool defer = false;
-    if (args.warm_active) {  // a warm-start guess with active rows belongs to the IPM kernel's polish
-      bool any = false;
-      const uint16_t* wa = args.warm_active + (size_t)inst * nbfull;
-      for (int t = gtid; t < nbfull; t += GT) { const unsigned a = wa[t]; any = any || (!(a & 0x8000u) && (a & 0x3ffu)); }
-      defer = !G.all(!any);
-    }
-    bool finite = true;
-    int nb = 0, n = 0, nblk = 0, n4 = 0, matd = 0;
-    if (!defer) {
-      finite = stage_inputs<W>(G, cfg, args, inst, V);
-      nb = s_misc[0];
-      n = 3 * nb; nblk = (n + 3) >> 2; n4 = nblk << 2;
-      matd = ((nblk * (nblk + 1)) >> 1) * kTS;
-      const bool invalid = s_misc[1] != 0;
-      if (!finite || invalid) {
-        for (int t = gtid; t < nf; t += GT) args.forces[(size_t)inst * nf + t] = 0.0;
-        if (args.lam) for (int t = gtid; t < 2 * mfull; t += GT) args.lam[(size_t)inst * 2 * mfull + t] = 0.0;
-        if (args.active) for (int t = gtid; t < nbfull; t += GT) args.active[(size_t)inst * nbfull + t] = 0;
-        if (gtid == 0) {
-          args.status[inst] = !finite ? CMPC_STATUS_NUMERICAL : CMPC_STATUS_INVALID_TABLE;
-          if (args.iters) args.iters[inst] = 0;
-          if (args.kkt) args.kkt[inst] = 0.0;
-        }
-        G.sync();
-        continue;
-      }
-      build_qp<W>(G, cfg, V, Mm, nb);
-      store_mat<W>(G, Hm, Mm, matd);  // the verification below needs H again: keep it in the L2 slab
-      for (int t = gtid; t < n4; t += GT) s_x[t] = t < n ? -s_g[t] : 0.0;  // (eq/qz are dead after the build)
-      G.sync();
-      bool ok = chol_bc4<W>(G, Mm, nblk, s_tb, s_x, s_exch);
-      if (ok) {
-        chol_bwd_bc4<W>(G, Mm, nblk, s_x, s_exch);
-        copy_mat<W>(G, Mm, Hm, matd);
-        G.sync();
-        symv_bc4<W>(G, Mm, n4, nblk, s_x, s_hx);
-      }
-      defer = !ok;
-    }
-    double gs = 1.0, usf = 1.0, stat = 0.0, prim = 0.0;
-    if (!defer) {
-      double gmax = 0.0, umax = 0.0;
-      bool fin = true;
-      for (int t = gtid; t < n; t += GT) {
-        gmax = fmax(gmax, fabs(s_g[t])); umax = fmax(umax, fabs(s_x[t]));
-        stat = fmax(stat, fabs(s_hx[t] + s_g[t]));
-        fin = fin && isfinite(s_x[t]) && isfinite(s_hx[t]);
-      }
-      for (int b = gtid; b < nb; b += GT) {
-        const double ce = V.ce[b];
-        const double ubxy = kFricUb * ce, ubz = mass * kGrav * (double)L * ce;
-        double y[5];
-        cmul5(cfg.mu[s_blk_i[b]], s_x + 3 * b, y);
-        for (int q = 0; q < 5; ++q) prim = fmax(prim, fmax(-y[q], y[q] - (q < 4 ? ubxy : ubz)));
-      }
-      gmax = G.max(gmax); umax = G.max(umax); stat = G.max(stat);
-      gs = 1.0 + gmax; usf = 1.0 + umax;
-      prim = G.max(prim);
-      defer = !(stat <= 1e-9 * gs && prim <= 1e-9 * usf);
-      defer = !G.all(!defer && fin);  // fmax drops NaNs: a non-finite candidate is caught here
-    }
-    if (defer) {
-      if (gtid == 0) args.fail_perm[atomicAdd(args.fail_count, 1)] = inst;
-      G.sync();
-      continue;
-    }
-    // ---- outputs of a verified unconstrained optimum (same conventions as the IPM kernel)
-    for (int t = gtid; t < nf; t += GT) {
-      const int i = t / (3 * N), j = (t % (3 * N)) / 3, q = t % 3;
-      const int b = s_blk_of[j * L + i];
-      args.forces[(size_t)inst * nf + t] = b < 0 ? 0.0 : s_x[3 * b + q];
-    }
-    if (args.lam) for (int t = gtid; t < 2 * mfull; t += GT) args.lam[(size_t)inst * 2 * mfull + t] = 0.0;
-    if (args.active) {
-      for (int t = gtid; t < nbfull; t += GT) {
-        const int b = s_blk_of[t];
-        uint16_t a = 0x8000;
-        if (b >= 0) {
-          const double ce = V.ce[b];
-          const double ubxy = kFricUb * ce, ubz = mass * kGrav * (double)L * ce;
-          double y[5];
-          cmul5(cfg.mu[s_blk_i[b]], s_x + 3 * b, y);
-          a = 0;
-          for (int q = 0; q < 5; ++q)
-            a |= (uint16_t)((y[q] <= 1e-9 * usf ? 1 : 0) << q | (((q < 4 ? ubxy : ubz) - y[q]) <= 1e-9 * usf ? 1 : 0) << (5 + q));
-        }
-        args.active[(size_t)inst * nbfull + t] = a;
-      }
-    }
-    if (gtid == 0) {
-      args.status[inst] = CMPC_STATUS_OK;
-      if (args.iters) args.iters[inst] = 0;
-      if (args.kkt) args.kkt[inst] = fmax(stat / gs, fmax(prim, 0.0) / usf);
-    }
-    G.sync();
-  }
-}
+// ------------------------------------------------------------------ kernel launchers (one translation unit per kernel family)
+// cmpc_solve.cu: W in {1, 2, 4, 8}; mode 0 = solve, 1 = build-export; ms = factor in shared memory
+cudaError_t launch_solve_kernel(int W, int mode, bool ms, int grid, int block, size_t smem, cudaStream_t stream,
+                                const DevConfig& cfg, const SolveArgs& args);
+cudaError_t set_solve_kernel_smem(int W, int mode, bool ms, size_t bytes);
+// cmpc_presolve.cu: W in {1, 4, 8}
+cudaError_t launch_presolve_kernel(int W, int grid, int block, size_t smem, cudaStream_t stream, const DevConfig& cfg,
+                                   const SolveArgs& args);
+cudaError_t set_presolve_kernel_smem(int W, size_t bytes);
 
 }  // namespace cmpc

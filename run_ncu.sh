@@ -1,12 +1,14 @@
 #!/bin/bash
-# ncu capture of the solve kernel on one headline-config batch (B=4096, device-resident: one launch), source-level
+# ncu capture of one kernel on one headline-config batch (B=4096, device-resident), source-level.
+# KERN=cmpc_presolve_kernel (default, the headline's dominant kernel) or cmpc_solve_kernel with PRESOLVE=0; OUT=report name
+KERN=${KERN:-cmpc_presolve_kernel}; OUT=${OUT:-prof}; export PRESOLVE=${PRESOLVE:-1}
 mkdir -p gpurun_out
 cat > /tmp/ncu_case.py <<'PY'
 import sys; sys.path.insert(0, '.')
-import numpy as np, torch, __graft_entry__ as ge
+import os, numpy as np, torch, __graft_entry__ as ge
 pkg = ge.load_package(); wl = pkg.workloads
 B = 4096
-cfg = wl.default_config(10); st, ds, di = wl.make_batch(cfg, B)
+cfg = dict(wl.default_config(10), presolve=int(os.environ.get('PRESOLVE', '1'))); st, ds, di = wl.make_batch(cfg, B)
 dev = torch.device('cuda', 0)
 m = pkg.CentroidalMPC.from_dict(cfg); m.SetupMPC(B)
 d = [torch.from_numpy(a).to(dev) for a in (st, ds, di)]
@@ -18,5 +20,5 @@ for _ in range(3):
 print(stats.as_dict())
 PY
 python /tmp/ncu_case.py > gpurun_out/ncu_plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:cmpc_solve_kernel -s 4 -c 1 -f -o gpurun_out/prof python /tmp/ncu_case.py > gpurun_out/ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:$KERN -s 4 -c 1 -f -o gpurun_out/$OUT python /tmp/ncu_case.py > gpurun_out/ncu.log 2>&1
 tail -n 3 gpurun_out/ncu_plain.log gpurun_out/ncu.log
