@@ -49,6 +49,11 @@ struct cmpc_handle {
     double* d_pre_scratch = nullptr;
   } cls[kNumClasses], exp_plan;
   int4 bounds = {0, 0, 0, 0};
+  int32_t* d_ready = nullptr;        // chunks of inputs landed (written by the copy stream, polled by the router kernel)
+  int32_t* h_ready_vals = nullptr;   // pinned {1, 2, ...}: the values the copy stream writes into d_ready
+  int32_t* h_error_dev = nullptr;    // device alias of h_error
+  int32_t* h_error = nullptr;        // pinned + mapped: set by a kernel whose wait on d_ready timed out
+  int e2e_mode = 0;                  // CMPC_E2E_MODE: 0 (default) zero-copy reads of pinned inputs, 2 staged copies, 3 progressive copies
   int32_t *d_counts = nullptr, *d_perm = nullptr;  // counts[4], work[4], then the presolve's deferred counts[4], work[4]; perm [2][4][B]
   std::string err;
 };
@@ -388,23 +393,41 @@ int launch_presolve(cmpc_handle* h, const cmpc_handle::ClassPlan& p, SolveArgs a
   return CMPC_OK;
 }
 
-// classify, then per used size class: the presolve kernel (one Cholesky of H settles the instances
-// whose unconstrained minimiser is feasible) and the interior-point kernel over what it deferred --
-// all on the stream, no host round trip.  Returns the number of kernels launched (<0: error).
-int launch_solve(cmpc_handle* h, SolveArgs a, int B) {
+// One batch on the handle's stream, no host round trip.  Returns the number of kernels launched
+// (< 0: error).
+//  * presolve on (default): the presolve kernel of size class 0 walks all B instances itself -- it
+//    forwards those with more free blocks to their class lists (no classify launch), settles the
+//    ones whose unconstrained minimiser is feasible with one Cholesky of H, and defers the rest to
+//    the interior-point kernel; then the same pair of kernels per larger class that is in use.
+//    ready != nullptr: the inputs are still arriving (copy stream bumps *ready per chunk of
+//    ready_chunk instances) and the router waits per instance for its chunk.
+//  * presolve off: classify kernel, then one interior-point kernel per class.
+int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = nullptr, int ready_chunk = 0) {
   if (cudaMemsetAsync(h->d_counts, 0, 4 * kNumClasses * sizeof(int32_t), h->stream) != cudaSuccess)
     return fail(h, CMPC_ERR_CUDA, "memset counts");
-  classify_kernel<<<(B + 31) / 32, 1024, 0, h->stream>>>(h->dev, B, a.des_inputs, h->bounds, h->d_counts, h->d_perm);
-  int launches = 1;
+  int launches = 0;
   const bool presolve = h->cfg.presolve && h->cfg.polish;
+  const bool router = presolve && h->cls[0].used && h->cls[0].pre_used;
+  if (!router) {
+    if (ready) return fail(h, CMPC_ERR_STATE, "progressive inputs need the presolve router");
+    classify_kernel<<<(B + 31) / 32, 1024, 0, h->stream>>>(h->dev, B, a.des_inputs, h->bounds, h->d_counts, h->d_perm);
+    ++launches;
+  }
   for (int c = 0; c < kNumClasses; ++c) {
     if (!h->cls[c].used) continue;
     a.perm = h->d_perm + (size_t)c * B;
     a.count = h->d_counts + c;
     a.work = h->d_counts + kNumClasses + c;
+    a.route = 0; a.ready = nullptr;
     if (presolve && h->cls[c].pre_used) {
       a.fail_perm = h->d_perm + (size_t)(kNumClasses + c) * h->max_batch;
       a.fail_count = h->d_counts + 2 * kNumClasses + c;
+      if (router && c == 0) {
+        a.perm = nullptr; a.count = nullptr; a.count_imm = B;
+        a.route = 1; a.route_b1 = h->bounds.y; a.route_b2 = h->bounds.z;
+        a.route_perm = h->d_perm; a.route_counts = h->d_counts; a.route_stride = B;
+        a.ready = ready; a.ready_chunk = ready_chunk; a.error_flag = h->h_error_dev;
+      }
       int rc = launch_presolve(h, h->cls[c], a);
       if (rc) return rc;
       ++launches;
@@ -412,6 +435,7 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B) {
       a.count = a.fail_count;
       a.work = h->d_counts + 3 * kNumClasses + c;
       a.fail_perm = nullptr; a.fail_count = nullptr;
+      a.route = 0; a.ready = nullptr;
     }
     int rc = launch_class<0>(h, h->cls[c], a);
     if (rc) return rc;
@@ -552,6 +576,13 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
   CUDA_TRY(h, cudaMalloc(&h->d_active, B * L * N * 2));
   CUDA_TRY(h, cudaMalloc(&h->d_stats, sizeof(DevStats)));
 
+  CUDA_TRY(h, cudaMalloc(&h->d_ready, 4 * sizeof(int32_t)));
+  CUDA_TRY(h, cudaHostAlloc(&h->h_ready_vals, cmpc_handle::kMaxChunks * sizeof(int32_t), cudaHostAllocDefault));
+  for (int c = 0; c < cmpc_handle::kMaxChunks; ++c) h->h_ready_vals[c] = c + 1;
+  CUDA_TRY(h, cudaHostAlloc(&h->h_error, sizeof(int32_t), cudaHostAllocMapped));
+  *h->h_error = 0;
+  CUDA_TRY(h, cudaHostGetDevicePointer((void**)&h->h_error_dev, h->h_error, 0));
+  if (const char* m = getenv("CMPC_E2E_MODE")) h->e2e_mode = atoi(m);
   CUDA_TRY(h, cudaMalloc(&h->d_counts, 4 * kNumClasses * sizeof(int32_t)));
   CUDA_TRY(h, cudaMalloc(&h->d_perm, (size_t)2 * kNumClasses * B * sizeof(int32_t)));
   // size classes by number of free 3-blocks: n4 <= 64 -> one warp per instance, n4 <= 128 ->
@@ -666,95 +697,101 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
   const int N = h->cfg.horizon, L = h->cfg.num_legs;
   const size_t ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = (size_t)L * (4 * N + 3), nf = (size_t)3 * L * N;
   cudaStream_t s = h->stream;
-  // Zero-copy path: when every buffer is pinned (page-locked, hence device-mapped under UVA) the
-  // kernels read the inputs and write the outputs in place over PCIe/C2C -- each byte crosses the
-  // bus once, overlapped with the other resident instances' compute, and no staging copy runs.
-  {
-    void* dp[9] = {nullptr};
-    const void* hp[9] = {state, des_state, des_inputs, forces, status, iters, kkt, lam, active};
-    bool all_mapped = h->zero_copy;
-    for (int q = 0; q < 9 && all_mapped; ++q) {
-      if (!hp[q]) continue;
-      dp[q] = mapped_device_pointer(hp[q]);
-      all_mapped = dp[q] != nullptr;
-    }
-    if (all_mapped) {
-      SolveArgs a = base_args(h, B);
-      a.state = (const double*)dp[0]; a.des_state = (const double*)dp[1]; a.des_inputs = (const double*)dp[2];
-      a.forces = (double*)dp[3]; a.status = (int32_t*)dp[4];
-      a.iters = iters ? (int32_t*)dp[5] : (stats ? h->d_iters : nullptr);
-      a.kkt = kkt ? (double*)dp[6] : (stats ? h->d_kkt : nullptr);
-      a.lam = (double*)dp[7]; a.active = (uint16_t*)dp[8];
-      CUDA_TRY(h, cudaEventRecord(h->ev[0], s));
-      int rc = launch_solve(h, a, B);
-      if (rc < 0) return rc;
-      const int launches = rc;
-      CUDA_TRY(h, cudaEventRecord(h->ev[1], s));
-      CUDA_TRY(h, cudaStreamSynchronize(s));
-      if (stats) {
-        std::memset(stats, 0, sizeof(*stats));
-        rc = collect_stats(h, B, a.status, a.iters, a.kkt, stats, launches);
-        if (rc) return rc;
-        float t1 = 0;
-        CUDA_TRY(h, cudaEventElapsedTime(&t1, h->ev[0], h->ev[1]));
-        stats->kernel_ms = t1;
-      }
-      return CMPC_OK;
-    }
+  const bool router = h->cfg.presolve && h->cfg.polish && h->cls[0].used && h->cls[0].pre_used;
+  // device aliases of pinned (page-locked, hence mapped under UVA) caller buffers
+  void* dp[9] = {nullptr};
+  const void* hp[9] = {state, des_state, des_inputs, forces, status, iters, kkt, lam, active};
+  bool in_mapped = h->zero_copy, out_mapped = h->zero_copy;
+  for (int q = 0; q < 9; ++q) {
+    if (!hp[q]) continue;
+    dp[q] = mapped_device_pointer(hp[q]);
+    if (!dp[q]) (q < 3 ? in_mapped : out_mapped) = false;
   }
-  // Staged path, pipelined in chunks of one resident wave: the copy-in of chunk c+1 and the
-  // copy-out of chunk c-1 run on their own streams (both DMA directions) while chunk c computes.
-  const int wave = std::max(1, h->cls[0].used ? h->cls[0].grid * h->cls[0].groups : h->num_sms);
-  int nch = (B + wave - 1) / wave;
-  if (nch > cmpc_handle::kMaxChunks) nch = cmpc_handle::kMaxChunks;
-  const int per = ((B + nch - 1) / nch + 31) & ~31;
-  nch = (B + per - 1) / per;
+  // Inputs (pinned buffers).  Default: the kernels read them in place over the bus -- every byte
+  // crosses once, overlapped with the other resident instances' compute, no staging copy; measured
+  // 0.36-0.40 ms per 4096-instance step, stable.  CMPC_E2E_MODE=3 ("progressive"): DMA copies in chunks
+  // on a copy stream while the router kernel, launched at the same time, waits per instance for its
+  // chunk; the DMA engine moves the bytes twice as fast (54 GB/s), but the step measured 0.34-0.70 ms
+  // (the copies slow down erratically while 2000 warps poll), so it is not the default.
+  // CMPC_E2E_MODE=2, or pageable buffers: copy in, compute, copy out.
+  const bool zc_in = in_mapped && h->e2e_mode != 2 && h->e2e_mode != 3;
+  // (progressive needs pinned inputs: a pageable cudaMemcpyAsync is staged by the driver and can
+  // serialise behind the running kernel, which would then wait for its chunk until the time-out)
+  const bool progressive = in_mapped && !zc_in && router && h->e2e_mode == 3 && B >= 256;
+  // Outputs: written in place over the bus when every output buffer is pinned (posted writes,
+  // overlapped with the remaining compute); otherwise device buffers and one copy back.
+  const bool zc_out = out_mapped && h->e2e_mode != 2;
+  SolveArgs a = base_args(h, B);
+  a.state = zc_in ? (const double*)dp[0] : h->d_state;
+  a.des_state = zc_in ? (const double*)dp[1] : h->d_ds;
+  a.des_inputs = zc_in ? (const double*)dp[2] : h->d_di;
+  if (zc_out) {
+    a.forces = (double*)dp[3]; a.status = (int32_t*)dp[4];
+    a.iters = iters ? (int32_t*)dp[5] : (stats ? h->d_iters : nullptr);
+    a.kkt = kkt ? (double*)dp[6] : (stats ? h->d_kkt : nullptr);
+    a.lam = (double*)dp[7]; a.active = (uint16_t*)dp[8];
+  } else {
+    a.forces = h->d_forces; a.status = h->d_status; a.iters = h->d_iters; a.kkt = h->d_kkt;
+    a.lam = lam ? h->d_lam : nullptr; a.active = active ? h->d_active : nullptr;
+  }
+  int nch = 1, per = B;
+  if (progressive) {
+    per = getenv("CMPC_E2E_CHUNK") ? std::max(32, atoi(getenv("CMPC_E2E_CHUNK")) & ~31) : 1024;
+    if ((B + per - 1) / per > cmpc_handle::kMaxChunks) per = (((B + cmpc_handle::kMaxChunks - 1) / cmpc_handle::kMaxChunks) + 31) & ~31;
+    nch = (B + per - 1) / per;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_ready, 0, 4 * sizeof(int32_t), s));
+  }
   CUDA_TRY(h, cudaEventRecord(h->ev_span[0], s));
-  CUDA_TRY(h, cudaStreamWaitEvent(h->s_in, h->ev_span[0], 0));   // order behind earlier work of the caller's stream
-  CUDA_TRY(h, cudaStreamWaitEvent(h->s_out, h->ev_span[0], 0));
   int launches = 0;
-  for (int c = 0; c < nch; ++c) {
-    const size_t o = (size_t)c * per;
-    const size_t nbc = std::min<size_t>(per, (size_t)B - o);
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_state + o * ns, state + o * ns, nbc * ns * 8, cudaMemcpyHostToDevice, h->s_in));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_ds + o * nds, des_state + o * nds, nbc * nds * 8, cudaMemcpyHostToDevice, h->s_in));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_di + o * ndi, des_inputs + o * ndi, nbc * ndi * 8, cudaMemcpyHostToDevice, h->s_in));
-    CUDA_TRY(h, cudaEventRecord(h->ev_in[c], h->s_in));
+  if (!zc_in) {
+    // pinned sources when progressive: these calls only enqueue (chunk c of the three arrays, then
+    // the chunk counter); the router kernel launched below polls the counter
+    cudaStream_t sc[1] = {progressive ? h->s_in : s};
+    if (progressive) CUDA_TRY(h, cudaStreamWaitEvent(sc[0], h->ev_span[0], 0));
+    for (int c = 0; c < nch; ++c) {
+      const size_t o = (size_t)c * per;
+      const size_t nbc = std::min<size_t>(per, (size_t)B - o);
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_state + o * ns, state + o * ns, nbc * ns * 8, cudaMemcpyHostToDevice, sc[0]));
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_ds + o * nds, des_state + o * nds, nbc * nds * 8, cudaMemcpyHostToDevice, sc[0]));
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_di + o * ndi, des_inputs + o * ndi, nbc * ndi * 8, cudaMemcpyHostToDevice, sc[0]));
+      if (progressive)
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_ready, h->h_ready_vals + c, sizeof(int32_t), cudaMemcpyHostToDevice, sc[0]));
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev_span[1], sc[0]));
+  } else {
+    CUDA_TRY(h, cudaEventRecord(h->ev_span[1], s));
   }
-  CUDA_TRY(h, cudaEventRecord(h->ev_span[1], h->s_in));
-  for (int c = 0; c < nch; ++c) {
-    const size_t o = (size_t)c * per;
-    const int nbc = (int)std::min<size_t>(per, (size_t)B - o);
-    CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_in[c], 0));
-    SolveArgs a = base_args(h, nbc);
-    a.state = h->d_state + o * ns; a.des_state = h->d_ds + o * nds; a.des_inputs = h->d_di + o * ndi;
-    a.forces = h->d_forces + o * nf; a.status = h->d_status + o; a.iters = h->d_iters + o; a.kkt = h->d_kkt + o;
-    a.lam = lam ? h->d_lam + o * 10 * L * N : nullptr; a.active = active ? h->d_active + o * L * N : nullptr;
-    int rc = launch_solve(h, a, nbc);
+  if (progressive) {
+    int rc = launch_solve(h, a, B, h->d_ready, per);
     if (rc < 0) return rc;
-    launches += rc;
-    CUDA_TRY(h, cudaEventRecord(h->ev_k[c], s));
-    CUDA_TRY(h, cudaStreamWaitEvent(h->s_out, h->ev_k[c], 0));
-    CUDA_TRY(h, cudaMemcpyAsync(forces + o * nf, h->d_forces + o * nf, (size_t)nbc * nf * 8, cudaMemcpyDeviceToHost, h->s_out));
-    CUDA_TRY(h, cudaMemcpyAsync(status + o, h->d_status + o, (size_t)nbc * 4, cudaMemcpyDeviceToHost, h->s_out));
-    if (iters) CUDA_TRY(h, cudaMemcpyAsync(iters + o, h->d_iters + o, (size_t)nbc * 4, cudaMemcpyDeviceToHost, h->s_out));
-    if (kkt) CUDA_TRY(h, cudaMemcpyAsync(kkt + o, h->d_kkt + o, (size_t)nbc * 8, cudaMemcpyDeviceToHost, h->s_out));
-    if (lam) CUDA_TRY(h, cudaMemcpyAsync(lam + o * 10 * L * N, h->d_lam + o * 10 * L * N, (size_t)nbc * 10 * L * N * 8, cudaMemcpyDeviceToHost, h->s_out));
-    if (active) CUDA_TRY(h, cudaMemcpyAsync(active + o * L * N, h->d_active + o * L * N, (size_t)nbc * L * N * 2, cudaMemcpyDeviceToHost, h->s_out));
+    launches = rc;
+  }
+  if (!progressive) {
+    int rc = launch_solve(h, a, B);
+    if (rc < 0) return rc;
+    launches = rc;
   }
   CUDA_TRY(h, cudaEventRecord(h->ev_span[2], s));
-  CUDA_TRY(h, cudaEventRecord(h->ev_span[3], h->s_out));
-  CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_span[3], 0));  // the caller's stream observes completion
-  CUDA_TRY(h, cudaStreamSynchronize(h->s_out));
+  if (!zc_out) {
+    CUDA_TRY(h, cudaMemcpyAsync(forces, h->d_forces, (size_t)B * nf * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(status, h->d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    if (iters) CUDA_TRY(h, cudaMemcpyAsync(iters, h->d_iters, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    if (kkt) CUDA_TRY(h, cudaMemcpyAsync(kkt, h->d_kkt, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+    if (lam) CUDA_TRY(h, cudaMemcpyAsync(lam, h->d_lam, (size_t)B * 10 * L * N * 8, cudaMemcpyDeviceToHost, s));
+    if (active) CUDA_TRY(h, cudaMemcpyAsync(active, h->d_active, (size_t)B * L * N * 2, cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(h, cudaEventRecord(h->ev_span[3], s));
+  if (progressive) CUDA_TRY(h, cudaStreamSynchronize(h->s_in));
   CUDA_TRY(h, cudaStreamSynchronize(s));
+  if (*h->h_error) { *h->h_error = 0; return fail(h, CMPC_ERR_CUDA, "cmpc_solve_batch: input chunk did not arrive (copy stream stalled)"); }
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
-    int rc = collect_stats(h, B, h->d_status, h->d_iters, h->d_kkt, stats, launches);
+    int rc = collect_stats(h, B, a.status, a.iters, a.kkt, stats, launches);
     if (rc) return rc;
     float t0 = 0, t1 = 0, t2 = 0;
-    CUDA_TRY(h, cudaEventElapsedTime(&t0, h->ev_span[0], h->ev_span[1]));  // copy-in pipeline span
     CUDA_TRY(h, cudaEventElapsedTime(&t1, h->ev_span[0], h->ev_span[2]));  // until the last kernel ended
     CUDA_TRY(h, cudaEventElapsedTime(&t2, h->ev_span[2], h->ev_span[3]));  // copy-out tail after it
+    if (!zc_in) CUDA_TRY(h, cudaEventElapsedTime(&t0, h->ev_span[0], h->ev_span[1]));  // copy-in span (overlaps the kernels when progressive)
     stats->h2d_ms = t0; stats->kernel_ms = t1; stats->d2h_ms = t2;
   }
   return CMPC_OK;
@@ -995,6 +1032,7 @@ void cmpc_destroy(cmpc_handle* h) {
   cudaFree(h->d_state); cudaFree(h->d_ds); cudaFree(h->d_di); cudaFree(h->d_forces); cudaFree(h->d_kkt);
   cudaFree(h->d_lam); cudaFree(h->d_hip); cudaFree(h->d_counts); cudaFree(h->d_perm); cudaFree(h->exp_plan.d_scratch);
   for (auto& c : h->cls) { cudaFree(c.d_scratch); cudaFree(c.d_pre_scratch); }
+  cudaFree(h->d_ready); cudaFreeHost(h->h_ready_vals); cudaFreeHost(h->h_error);
   cudaFree(h->d_status); cudaFree(h->d_iters);
   cudaFree(h->d_iters_sum); cudaFree(h->d_status_or); cudaFree(h->d_active); cudaFree(h->d_stats);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);

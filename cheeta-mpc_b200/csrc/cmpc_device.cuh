@@ -82,6 +82,18 @@ struct SolveArgs {
   PrePlan pre;               // presolve kernel: its own shared-memory layout
   int32_t* fail_perm;        // presolve kernel only: instances it could not settle, for the IPM kernel
   int32_t* fail_count;
+  // presolve kernel of size class 0 as the batch's router (no classify launch): it walks all B
+  // instances in order and forwards those with more than nbmax free blocks to their class lists
+  int route;                 // 0: perm / count describe this class only
+  int route_b1, route_b2;    // largest nb of classes 1 and 2 (class 3 takes the rest)
+  int32_t* route_perm;       // [class][route_stride]
+  int32_t* route_counts;     // [class]
+  int route_stride;
+  // progressive input arrival (cmpc_solve_batch, host buffers): instance id / ready_chunk is its
+  // copy chunk; *ready = number of chunks whose H2D copy has completed (written by the copy stream)
+  const int32_t* ready;
+  int ready_chunk;
+  int32_t* error_flag;       // set when a wait on *ready times out
 };
 
 // ------------------------------------------------------------------ BC4 layout
@@ -649,7 +661,7 @@ __host__ __device__ inline SmemPlan make_plan(int N, int L, int W, int nbmax, in
 struct BuildView {
   double* Mm;   // the matrix buffer; stages the raw inputs [state | des_state | des_inputs] first
   double *ce, *fz, *arm, *eq, *qz, *g;
-  int* misc;    // [0] = nb, [1] = invalid table
+  int* misc;    // [0] = nb (clamped to the class bound), [1] = invalid table, [3] = nb unclamped
   uint16_t* tb;
   uint8_t *blk_j, *blk_i;
   int8_t* blk_of;
@@ -666,7 +678,8 @@ __device__ __forceinline__ bool stage_inputs(const Group<W>& G, const DevConfig&
   const int ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = L * (4 * N + 3);
   const double dt = cfg.dt, mass = cfg.mass;
   // ---- stage the raw inputs once, coalesced (CentroidalMPC.cpp:284-317 copies them blindly;
-  // here non-finite values are caught).  The buffers may be HBM or mapped pinned host memory
+  // here non-finite values are caught).  L2-only loads (ld.global.cg): each value is read once, and
+  // in the progressive host-buffer path the copy engine writes these buffers while the kernel runs.  The buffers may be HBM or mapped pinned host memory
   // (zero-copy end-to-end path): every input byte crosses the bus exactly once.  The staging
   // area is the factor's buffer, which is dead until the build.
   double* g_state = V.Mm;
@@ -675,11 +688,11 @@ __device__ __forceinline__ bool stage_inputs(const Group<W>& G, const DevConfig&
   bool finite = true;
   {
     const double* src = args.state + (size_t)inst * ns;
-    for (int t = gtid; t < ns; t += GT) { const double v = __ldg(src + t); g_state[t] = v; finite = finite && isfinite(v); }
+    for (int t = gtid; t < ns; t += GT) { const double v = __ldcg(src + t); g_state[t] = v; finite = finite && isfinite(v); }
     src = args.des_state + (size_t)inst * nds;
-    for (int t = gtid; t < nds; t += GT) { const double v = __ldg(src + t); g_ds[t] = v; finite = finite && isfinite(v); }
+    for (int t = gtid; t < nds; t += GT) { const double v = __ldcg(src + t); g_ds[t] = v; finite = finite && isfinite(v); }
     src = args.des_inputs + (size_t)inst * ndi;
-    for (int t = gtid; t < ndi; t += GT) { const double v = __ldg(src + t); g_di[t] = v; finite = finite && isfinite(v); }
+    for (int t = gtid; t < ndi; t += GT) { const double v = __ldcg(src + t); g_di[t] = v; finite = finite && isfinite(v); }
   }
   const double* g_dpos = g_ds;
   const double* g_dvel = g_ds + 3 * (N + 1);
@@ -714,7 +727,7 @@ __device__ __forceinline__ bool stage_inputs(const Group<W>& G, const DevConfig&
         }
       }
     }
-    if (gtid == 0) { V.misc[0] = total < args.nbmax ? total : args.nbmax; V.misc[1] = bad != 0u; }
+    if (gtid == 0) { V.misc[0] = total < args.nbmax ? total : args.nbmax; V.misc[1] = bad != 0u; V.misc[3] = total; }
   }
   // zero-input rollout (closed form of x_k = A^k x0 + sum A^p d) and e = Q (x - x_ref), nodes 1..N
   for (int k = gtid; k < N; k += GT) {

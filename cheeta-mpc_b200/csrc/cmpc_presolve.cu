@@ -13,6 +13,8 @@
 // layout (cmpc_device.cuh, make_pre_plan), ONE n-vector and a few tables; right-hand side, gradient
 // and residual live in registers (one or two rows per lane).  2066 doubles per instance at n = 60:
 // 14 instances per SM, so a 4096-instance batch runs in two waves.
+#include <type_traits>
+
 #include "cmpc_device.cuh"
 
 namespace cmpc {
@@ -184,6 +186,14 @@ __device__ __forceinline__ void symv_cm(const Group<W>& G, const CM<TT>& cm, con
   }
 }
 
+__device__ __forceinline__ int ld_acquire(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+constexpr int kOutMap = 4;  // force-output slots per thread whose (step, leg, component) is precomputed
+
 }  // namespace
 
 template <int W, int TT>
@@ -228,6 +238,15 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
   const double zeta = cfg.zoh ? 0.5 : 0.0;
   const int count = args.count ? *args.count : args.count_imm;
 
+  // forces leave in the reference's per-leg order [L][N][3] (CentroidalMPC.cpp:270): output t reads
+  // component q of free block blk_of[j L + i]; the map is the same for every instance
+  int omap[kOutMap];
+#pragma unroll
+  for (int k = 0; k < kOutMap; ++k) {
+    const int t = gtid + k * GT;
+    const int i = t / (3 * N), rem = t - i * 3 * N, j = rem / 3;
+    omap[k] = ((j * L + i) << 2) | (rem - 3 * j);
+  }
   if ((int)threadIdx.x < N) {
     const int j = threadIdx.x;
     double z1 = 0.0, z2 = 0.0;
@@ -250,21 +269,36 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
     slot = G.bcast0(slot, s_misc + 2);
     if (slot >= count) break;
     const int inst = args.perm ? args.perm[slot] : slot;
-    bool defer = false;
-    if (args.warm_active) {  // a warm-start guess with active rows belongs to the IPM kernel's polish
-      bool any = false;
-      const uint16_t* wa = args.warm_active + (size_t)inst * nbfull;
-      for (int t = gtid; t < nbfull; t += GT) { const unsigned a = wa[t]; any = any || (!(a & 0x8000u) && (a & 0x3ffu)); }
-      defer = !G.all(!any);
+    if (args.ready) {
+      // progressive arrival: the copy stream bumps *ready after each chunk of inputs has landed
+      const int chunk = inst / args.ready_chunk;
+      if (gtid == 0) {
+        const long long t0 = clock64();
+        while (ld_acquire(args.ready) <= chunk) {
+          __nanosleep(1000);
+          if (clock64() - t0 > 6000000000LL) { atomicExch(args.error_flag, 1); break; }  // ~3 s: never hang the GPU
+        }
+      }
+      G.sync();
     }
+    bool defer = false;
     int nb = 0, n = 0, nblk = 0, n4 = 0;
     double gr[2] = {0.0, 0.0};  // gradient rows gtid, gtid + GT
     double xr[2] = {0.0, 0.0};
-    if (!defer) {
+    {
       const bool finite = stage_inputs<W>(G, cfg, args, inst, V);
       nb = s_misc[0];
       n = 3 * nb; nblk = (n + 3) >> 2; n4 = nblk << 2;
       const bool invalid = s_misc[1] != 0;
+      if (args.route && s_misc[3] > nbmax) {  // belongs to a larger size class: forward it
+        if (gtid == 0) {
+          const int tot = s_misc[3];
+          const int c = tot <= args.route_b1 ? 1 : (tot <= args.route_b2 ? 2 : 3);
+          args.route_perm[(size_t)c * args.route_stride + atomicAdd(args.route_counts + c, 1)] = inst;
+        }
+        G.sync();
+        continue;
+      }
       if (!finite || invalid) {
         for (int t = gtid; t < nf; t += GT) args.forces[(size_t)inst * nf + t] = 0.0;
         if (args.lam) for (int t = gtid; t < 2 * mfull; t += GT) args.lam[(size_t)inst * 2 * mfull + t] = 0.0;
@@ -277,6 +311,14 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
         G.sync();
         continue;
       }
+      if (args.warm_active) {  // a warm-start guess with active rows belongs to the IPM kernel's polish
+        bool any = false;
+        const uint16_t* wa = args.warm_active + (size_t)inst * nbfull;
+        for (int t = gtid; t < nbfull; t += GT) { const unsigned a = wa[t]; any = any || (!(a & 0x8000u) && (a & 0x3ffu)); }
+        defer = !G.all(!any);
+      }
+    }
+    if (!defer) {
       // ---- g = 2 Bqp' L (Aqp x0 + dqp - Xref) - 2 W_f Uref: thread b owns block b (nb <= GT), adjoint
       // sums over the staged errors; the lever arm stays in registers until the staged inputs are dead
       double arm[3] = {0.0, 0.0, 0.0};
@@ -322,17 +364,17 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
       //   R = 4 (gi & 3) T + 2 (gi >> 2),  C = 2 T ((gj & 3) >> 1) + 2 colbase(gj >> 2) + (gj & 1).
       {
         const int T = cm.T();
-        const int npairs = (nb * (nb + 1)) >> 1;
         const double dt2 = dt * dt, dt4 = dt2 * dt2;
         const double q0 = cfg.w[6], q1 = cfg.w[7], q2 = cfg.w[8];
         const double im2 = 1.0 / (mass * mass);
         auto Rof = [&](int g) { return 4 * (g & 3) * T + 2 * (g >> 2); };
         auto Cof = [&](int g) { const int tj = g >> 2; return 2 * T * ((g & 3) >> 1) + 2 * (tj * nblk - ((tj * (tj + 1)) >> 1)) + (g & 1); };
-        for (int idx = gtid; idx < npairs; idx += GT) {
-          int a = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
-          while (((a + 1) * (a + 2)) >> 1 <= idx) ++a;
-          while ((a * (a + 1)) >> 1 > idx) --a;
-          const int b2 = idx - ((a * (a + 1)) >> 1), b = a;
+        // One block pair.  FAR (b2 <= b - 2): all nine elements lie strictly below the diagonal tiles,
+        // separable addressing.  Near pairs (b2 = b or b - 1) may touch a diagonal tile: lower tiles get
+        // (gi, gj) and an element inside a diagonal tile is mirrored so the tile holds both triangles.
+        // The two kinds run in separate loops so that no warp executes both store paths.
+        auto do_pair = [&](int b, int b2, auto far_tag) {
+          constexpr bool FAR = decltype(far_tag)::value;
           const int j = s_blk_j[b], i = s_blk_i[b], j2 = s_blk_j[b2], i2 = s_blk_i[b2];
           const double ce = s_ce[b], ce2 = s_ce[b2];
           const double r0 = s_x[3 * b], r1 = s_x[3 * b + 1], r2 = s_x[3 * b + 2];
@@ -362,8 +404,7 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
             }
           }
           const int g0 = 3 * b, h0 = 3 * b2;
-          if (h0 + 2 < (g0 & ~3)) {
-            // every element strictly below the diagonal tiles: plain separable addressing
+          if constexpr (FAR) {
             int R[3], C[3];
 #pragma unroll
             for (int aa = 0; aa < 3; ++aa) { R[aa] = Rof(g0 + aa); C[aa] = Cof(h0 + aa); }
@@ -372,9 +413,9 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
 #pragma unroll
               for (int bb = 0; bb < 3; ++bb) Mm[R[aa] + C[bb]] = 2.0 * blk[aa][bb];
           } else {
-            // the pair touches a diagonal tile (b2 = b or b - 1): lower tiles get (gi, gj), an element
-            // inside a diagonal tile is mirrored so that the tile holds both triangles
+#pragma unroll
             for (int aa = 0; aa < 3; ++aa)
+#pragma unroll
               for (int bb = 0; bb < 3; ++bb) {
                 const int gi = g0 + aa, gj = h0 + bb;
                 const double v = 2.0 * blk[aa][bb];
@@ -382,6 +423,17 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
                 if (b != b2 && (gi >> 2) == (gj >> 2)) Mm[Rof(gj) + Cof(gi)] = v;
               }
           }
+        };
+        const int nfar = nb >= 3 ? ((nb - 1) * (nb - 2)) >> 1 : 0;
+        for (int idx = gtid; idx < nfar; idx += GT) {
+          int a = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
+          while (((a + 1) * (a + 2)) >> 1 <= idx) ++a;
+          while ((a * (a + 1)) >> 1 > idx) --a;
+          do_pair(a + 2, idx - ((a * (a + 1)) >> 1), std::true_type{});
+        }
+        for (int idx = gtid; idx < 2 * nb - 1; idx += GT) {
+          const int b = (idx + 1) >> 1;
+          do_pair(b, b - (idx & 1), std::false_type{});
         }
         // padding rows (n .. n4-1): identity
         for (int e = gtid; e < (n4 - n) * n4; e += GT) {
@@ -444,10 +496,18 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
       continue;
     }
     // ---- outputs of a verified unconstrained optimum (same conventions as the IPM kernel)
-    for (int t = gtid; t < nf; t += GT) {
-      const int i = t / (3 * N), j = (t % (3 * N)) / 3, q = t % 3;
-      const int b = s_blk_of[j * L + i];
-      args.forces[(size_t)inst * nf + t] = b < 0 ? 0.0 : s_x[3 * b + q];
+    {
+      double* fo = args.forces + (size_t)inst * nf;
+#pragma unroll
+      for (int k = 0; k < kOutMap; ++k) {
+        const int t = gtid + k * GT;
+        if (t < nf) { const int b = s_blk_of[omap[k] >> 2]; fo[t] = b < 0 ? 0.0 : s_x[3 * b + (omap[k] & 3)]; }
+      }
+      for (int t = gtid + kOutMap * GT; t < nf; t += GT) {
+        const int i = t / (3 * N), j = (t % (3 * N)) / 3, q = t % 3;
+        const int b = s_blk_of[j * L + i];
+        fo[t] = b < 0 ? 0.0 : s_x[3 * b + q];
+      }
     }
     if (args.lam) for (int t = gtid; t < 2 * mfull; t += GT) args.lam[(size_t)inst * 2 * mfull + t] = 0.0;
     if (args.active) {
