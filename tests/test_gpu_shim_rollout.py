@@ -163,11 +163,11 @@ def test_weights_update_and_zoh_mode(pkg, orc, wl):
     mz.close()
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 2, 3])
 def test_host_buffer_paths_agree(pkg, wl, mode, monkeypatch):
-    """cmpc_solve_batch with host buffers: mode 0 = progressive (chunked DMA copy-in overlapped with
-    the router kernel that polls for its chunk; outputs written in place when pinned), mode 1 =
-    zero-copy reads of pinned inputs, mode 2 = copy in / compute / copy out.  Pageable and pinned
+    """cmpc_solve_batch with host buffers: mode 0 = zero-copy reads of pinned inputs (default; outputs
+    written in place when pinned), mode 2 = copy in / compute / copy out, mode 3 = progressive (chunked
+    DMA copy-in overlapped with the router kernel that polls for its chunk).  Pageable and pinned
     buffers, every mode: bit-identical results (mixed gaits, so the router also forwards the stand
     instances to their size class)."""
     import ctypes as C
