@@ -60,17 +60,21 @@ def main():
     ms, s, its, kk = timed_device(pkg, cfg, st, ds, di)
     out.append(dict(config="hard: tracking-heavy weights, mu=0.3, mixed gaits, N=10", batch=B, p50_ms=ms, solves_per_s=B / ms * 1e3,
                     mean_iters=float(its.mean()), status=np.bincount(s, minlength=5).tolist(), max_kkt=float(kk[s <= 1].max())))
-    # config 3: horizon 30
-    cfg = wl.default_config(30)
-    B = 1024
-    st, ds, di = wl.make_batch(cfg, B, gaits=("trot",))
+    # config 3: horizon 30.  qp_backend 0 = automatic (stage-wise Riccati presolve above 42 free leg-steps),
+    # 1 = condensed dense for every class (stand: n = 360, factor in L2, interior-point kernel only)
+    for backend, tag in ((0, "Riccati presolve"), (1, "dense")):
+        cfg = dict(wl.default_config(30), qp_backend=backend)
+        for gait, B, n in (("trot", 1024, 180), ("stand", 1024 if backend == 0 else 256, 360)):
+            st, ds, di = wl.make_batch(cfg, B, gaits=(gait,))
+            ms, s, its, kk = timed_device(pkg, cfg, st, ds, di, steps=5 if B > 256 else 3, warmup=2)
+            out.append(dict(config=f"3: N=30 {gait} (n={n}), {tag}", batch=B, p50_ms=ms, solves_per_s=B / ms * 1e3,
+                            mean_iters=float(its.mean()), status=np.bincount(s, minlength=5).tolist(), max_kkt=float(kk.max())))
+    cfg = dict(wl.default_config(30), qp_backend=0)
+    B = 8192
+    st, ds, di = wl.make_batch(cfg, B, gaits=wl.GAITS)
     ms, s, its, kk = timed_device(pkg, cfg, st, ds, di, steps=5, warmup=2)
-    out.append(dict(config="3: N=30 trot (n=180)", batch=B, p50_ms=ms, solves_per_s=B / ms * 1e3, mean_iters=float(its.mean()),
-                    status=np.bincount(s, minlength=5).tolist(), max_kkt=float(kk.max())))
-    st, ds, di = wl.make_batch(cfg, 256, gaits=("stand",))
-    ms, s, its, kk = timed_device(pkg, cfg, st, ds, di, steps=3, warmup=1)
-    out.append(dict(config="3: N=30 stand (n=360, factor in L2)", batch=256, p50_ms=ms, solves_per_s=256 / ms * 1e3, mean_iters=float(its.mean()),
-                    status=np.bincount(s, minlength=5).tolist(), max_kkt=float(kk.max())))
+    out.append(dict(config="3: N=30 mixed gaits, batch 8192, Riccati presolve", batch=B, p50_ms=ms, solves_per_s=B / ms * 1e3,
+                    mean_iters=float(its.mean()), status=np.bincount(s, minlength=5).tolist(), max_kkt=float(kk.max())))
     # config 5: closed loop
     cfg = wl.default_config(10)
     B, ticks = 4096, 1000

@@ -21,7 +21,7 @@ class CmpcConfig(C.Structure):
                 ("dt", C.c_double), ("mu", C.c_double * MAX_LEGS),
                 ("weights", C.c_double * NUM_WEIGHTS), ("disc_mode", C.c_int32),
                 ("max_iter", C.c_int32), ("ipm_tol", C.c_double), ("polish", C.c_int32),
-                ("presolve", C.c_int32)]
+                ("presolve", C.c_int32), ("qp_backend", C.c_int32), ("reserved", C.c_int32)]
 
 
 class CmpcStats(C.Structure):
@@ -69,6 +69,7 @@ def make_config(cfg: dict, max_iter=50, ipm_tol=1e-9, polish=1, presolve=1) -> C
     c.disc_mode = int(cfg.get("disc_mode", 0))
     c.max_iter, c.ipm_tol, c.polish = int(cfg.get("max_iter", max_iter)), float(cfg.get("ipm_tol", ipm_tol)), int(cfg.get("polish", polish))
     c.presolve = int(cfg.get("presolve", presolve))
+    c.qp_backend = int(cfg.get("qp_backend", 0))
     return c
 
 
@@ -144,7 +145,7 @@ class CentroidalMPC:
 
     @classmethod
     def from_dict(cls, cfg, device=0, **knobs):
-        kn = {k: cfg[k] for k in ("disc_mode", "max_iter", "ipm_tol", "polish", "presolve") if k in cfg}
+        kn = {k: cfg[k] for k in ("disc_mode", "max_iter", "ipm_tol", "polish", "presolve", "qp_backend") if k in cfg}
         kn.update(knobs)
         return cls(cfg["mass"], cfg["num_legs"], cfg["horizon"], cfg["dt"], cfg["weights"], cfg["mu"],
                    device=device, **kn)

@@ -49,6 +49,11 @@ struct cmpc_handle {
     double* d_pre_scratch = nullptr;
   } cls[kNumClasses], exp_plan;
   int4 bounds = {0, 0, 0, 0};
+  // Riccati presolve kernel (one plan for every size class: its working set does not depend on n)
+  bool ric_used = false;
+  int ric_groups = 0;
+  size_t ric_smem_bytes = 0;
+  double* d_ric_scratch = nullptr;
   int32_t* d_ready = nullptr;        // chunks of inputs landed (written by the copy stream, polled by the router kernel)
   int32_t* h_ready_vals = nullptr;   // pinned {1, 2, ...}: the values the copy stream writes into d_ready
   int32_t* h_error_dev = nullptr;    // device alias of h_error
@@ -361,6 +366,7 @@ bool valid_config(const cmpc_config* c) {
     if (!(c->weights[9 + 3 * c->num_legs + i] > 0)) return false;
   if (c->disc_mode != 0 && c->disc_mode != 1) return false;
   if (c->max_iter < 1 || !(c->ipm_tol > 0)) return false;
+  if (c->qp_backend < 0 || c->qp_backend > 2) return false;
   return true;
 }
 
@@ -393,6 +399,26 @@ int launch_presolve(cmpc_handle* h, const cmpc_handle::ClassPlan& p, SolveArgs a
   return CMPC_OK;
 }
 
+int launch_riccati(cmpc_handle* h, SolveArgs a) {
+  a.scratch = h->d_ric_scratch;
+  a.ric = make_ric_plan(h->cfg.horizon, h->cfg.num_legs);
+  a.scratch_per_group = (size_t)a.ric.slab;
+  a.nbmax = h->cfg.horizon * h->cfg.num_legs; a.n4max = 0; a.m_in_smem = 1; a.groups = h->ric_groups;
+  const cudaError_t e = launch_riccati_kernel(h->num_sms, 32 * h->ric_groups, h->ric_smem_bytes, h->stream, h->dev, a);
+  if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, std::string("riccati launch: ") + cudaGetErrorString(e));
+  return CMPC_OK;
+}
+
+// which presolve kernel settles size class c: 0 none, 1 dense (cmpc_presolve.cu), 2 Riccati (cmpc_riccati.cu)
+int presolve_kind(const cmpc_handle* h, int c) {
+  if (!(h->cfg.presolve && h->cfg.polish)) return 0;
+  const bool dense_ok = h->cls[c].pre_used, ric_ok = h->ric_used;
+  if (h->cfg.qp_backend == 1) return dense_ok ? 1 : 0;
+  if (h->cfg.qp_backend == 2) return ric_ok ? 2 : (dense_ok ? 1 : 0);
+  if (c >= 2 && ric_ok) return 2;  // more than 42 free leg-steps
+  return dense_ok ? 1 : (ric_ok ? 2 : 0);
+}
+
 // One batch on the handle's stream, no host round trip.  Returns the number of kernels launched
 // (< 0: error).
 //  * presolve on (default): the presolve kernel of size class 0 walks all B instances itself -- it
@@ -407,7 +433,7 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
     return fail(h, CMPC_ERR_CUDA, "memset counts");
   int launches = 0;
   const bool presolve = h->cfg.presolve && h->cfg.polish;
-  const bool router = presolve && h->cls[0].used && h->cls[0].pre_used;
+  const bool router = presolve && h->cls[0].used && presolve_kind(h, 0) == 1;
   if (!router) {
     if (ready) return fail(h, CMPC_ERR_STATE, "progressive inputs need the presolve router");
     classify_kernel<<<(B + 31) / 32, 1024, 0, h->stream>>>(h->dev, B, a.des_inputs, h->bounds, h->d_counts, h->d_perm);
@@ -419,7 +445,8 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
     a.count = h->d_counts + c;
     a.work = h->d_counts + kNumClasses + c;
     a.route = 0; a.ready = nullptr;
-    if (presolve && h->cls[c].pre_used) {
+    const int kind = presolve_kind(h, c);
+    if (kind) {
       a.fail_perm = h->d_perm + (size_t)(kNumClasses + c) * h->max_batch;
       a.fail_count = h->d_counts + 2 * kNumClasses + c;
       if (router && c == 0) {
@@ -428,7 +455,7 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
         a.route_perm = h->d_perm; a.route_counts = h->d_counts; a.route_stride = B;
         a.ready = ready; a.ready_chunk = ready_chunk; a.error_flag = h->h_error_dev;
       }
-      int rc = launch_presolve(h, h->cls[c], a);
+      int rc = kind == 1 ? launch_presolve(h, h->cls[c], a) : launch_riccati(h, a);
       if (rc) return rc;
       ++launches;
       a.perm = a.fail_perm;
@@ -623,6 +650,16 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
     if (s8 && (rc = set_smem_attr(h, 8, 0, true, s8))) return rc;
     if (s8g && (rc = set_smem_attr(h, 8, 0, false, s8g))) return rc;
     if ((rc = set_smem_attr(h, 8, 1, false, h->exp_plan.smem_bytes))) return rc;
+    {
+      const RicPlan rp = make_ric_plan(N, L);
+      h->ric_groups = (int)std::min<size_t>(14, kMaxSmem / ((size_t)rp.total * 8));
+      if (h->ric_groups >= 1) {
+        h->ric_smem_bytes = (size_t)rp.total * 8 * h->ric_groups;
+        CUDA_TRY(h, cudaMalloc(&h->d_ric_scratch, (size_t)rp.slab * 8 * (size_t)h->num_sms * h->ric_groups));
+        CUDA_TRY(h, set_riccati_kernel_smem(h->ric_smem_bytes));
+        h->ric_used = true;
+      }
+    }
     if (p1 && (rc = set_pre_smem_attr(h, 1, p1))) return rc;
     if (p4 && (rc = set_pre_smem_attr(h, 4, p4))) return rc;
     if (p8 && (rc = set_pre_smem_attr(h, 8, p8))) return rc;
@@ -697,7 +734,7 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
   const int N = h->cfg.horizon, L = h->cfg.num_legs;
   const size_t ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = (size_t)L * (4 * N + 3), nf = (size_t)3 * L * N;
   cudaStream_t s = h->stream;
-  const bool router = h->cfg.presolve && h->cfg.polish && h->cls[0].used && h->cls[0].pre_used;
+  const bool router = h->cls[0].used && presolve_kind(h, 0) == 1;
   // device aliases of pinned (page-locked, hence mapped under UVA) caller buffers
   void* dp[9] = {nullptr};
   const void* hp[9] = {state, des_state, des_inputs, forces, status, iters, kkt, lam, active};
@@ -1032,6 +1069,7 @@ void cmpc_destroy(cmpc_handle* h) {
   cudaFree(h->d_state); cudaFree(h->d_ds); cudaFree(h->d_di); cudaFree(h->d_forces); cudaFree(h->d_kkt);
   cudaFree(h->d_lam); cudaFree(h->d_hip); cudaFree(h->d_counts); cudaFree(h->d_perm); cudaFree(h->exp_plan.d_scratch);
   for (auto& c : h->cls) { cudaFree(c.d_scratch); cudaFree(c.d_pre_scratch); }
+  cudaFree(h->d_ric_scratch);
   cudaFree(h->d_ready); cudaFreeHost(h->h_ready_vals); cudaFreeHost(h->h_error);
   cudaFree(h->d_status); cudaFree(h->d_iters);
   cudaFree(h->d_iters_sum); cudaFree(h->d_status_or); cudaFree(h->d_active); cudaFree(h->d_stats);

@@ -47,6 +47,14 @@ struct PrePlan {  // presolve kernel, see make_pre_plan
   int mat, total;
 };
 
+struct RicPlan {  // Riccati presolve kernel (cmpc_riccati.cu), see make_ric_plan
+  int nz;                                  // 9 + 3L: augmented state [x; F_prev]
+  int in, ce, P, p, t, Bb, T1, G, M, m0, xc, ints;  // per-group offsets (doubles)
+  int X, F;                                // trajectory x_1..x_N and forces (alias P / T1..M when they fit)
+  int total;
+  int slab;                                // doubles of L2 scratch per group: N (12 nz + 12) gains
+};
+
 struct SmemPlan {
   // offsets in doubles from the start of the group's slab
   int ce, g, u, rd, tv, rhs, du, dua;
@@ -80,6 +88,7 @@ struct SolveArgs {
   int groups;                // groups per CTA
   SmemPlan plan;             // shared-memory layout of one group, computed on the host
   PrePlan pre;               // presolve kernel: its own shared-memory layout
+  RicPlan ric;               // Riccati presolve kernel: its own shared-memory layout
   int32_t* fail_perm;        // presolve kernel only: instances it could not settle, for the IPM kernel
   int32_t* fail_count;
   // presolve kernel of size class 0 as the batch's router (no classify launch): it walks all B
@@ -900,6 +909,32 @@ __host__ __device__ inline PrePlan make_pre_plan(int N, int L, int W, int nbmax,
   return p;
 }
 
+// ------------------------------------------------------------------ Riccati presolve kernel: shared-memory plan
+// Per group: the staged inputs stay resident (the backward sweep reads arms, contacts and references
+// stage by stage), the 21x21 cost-to-go, the per-stage products, and -- aliased onto those once the
+// sweep is done -- the state trajectory and the forces.  Gains go to an L2 slab.
+__host__ __device__ inline RicPlan make_ric_plan(int N, int L) {
+  RicPlan p;
+  const int nz = 9 + 3 * L, nbfull = L * N;
+  p.nz = nz;
+  int o = 0;
+  auto take = [&](int cnt) { int r = o; o += (cnt + 1) & ~1; return r; };
+  const int nin = (9 + 3 * L) + 9 * (N + 1) + L * (4 * N + 3);
+  p.in = take(((nin + 1) & ~1) + 10 * N + nbfull + 2);  // [inputs | eq 9N | qz N | fz nbfull]
+  p.ce = take(nbfull);
+  p.P = take(nz * nz);
+  p.Bb = take(nz * 12); p.T1 = take(nz * 12); p.G = take(12 * 13); p.M = take(12 * nz + 12);
+  // once the backward sweep is done P and T1..M are dead: the trajectory x_1..x_N and the forces go there
+  p.X = (9 * N <= nz * nz) ? p.P : take(9 * N);
+  p.F = (3 * L * N <= o - p.T1) ? p.T1 : take(3 * L * N);
+  p.p = take(nz); p.t = take(nz); p.m0 = take(12); p.xc = take(2 * nz + 4 * 9 + 12);
+  const int nbytes = 16 + 2 * nbfull + nbfull + 64;  // misc, blk_j, blk_i, blk_of, comp tables
+  p.ints = take((nbytes + 7) / 8);
+  p.total = o;
+  p.slab = N * (12 * nz + 12);
+  return p;
+}
+
 // ------------------------------------------------------------------ kernel launchers (one translation unit per kernel family)
 // cmpc_solve.cu: W in {1, 2, 4, 8}; mode 0 = solve, 1 = build-export; ms = factor in shared memory
 cudaError_t launch_solve_kernel(int W, int mode, bool ms, int grid, int block, size_t smem, cudaStream_t stream,
@@ -909,5 +944,9 @@ cudaError_t set_solve_kernel_smem(int W, int mode, bool ms, size_t bytes);
 cudaError_t launch_presolve_kernel(int W, int grid, int block, size_t smem, cudaStream_t stream, const DevConfig& cfg,
                                    const SolveArgs& args);
 cudaError_t set_presolve_kernel_smem(int W, size_t bytes);
+// cmpc_riccati.cu: stage-wise (Riccati) presolve, one warp per instance
+cudaError_t launch_riccati_kernel(int grid, int block, size_t smem, cudaStream_t stream, const DevConfig& cfg,
+                                  const SolveArgs& args);
+cudaError_t set_riccati_kernel_smem(size_t bytes);
 
 }  // namespace cmpc

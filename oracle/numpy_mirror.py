@@ -379,3 +379,104 @@ def foot_cost_and_feasible(cfg, state, des_inputs, p):
         dlt = p[i, 1:] - pd[1:]
         ok &= bool((dlt >= STEP_LB - 1e-12).all() and (dlt <= STEP_UB + 1e-12).all())
     return cost, ok
+
+
+# ------------------------------------------------------------------ stage-wise (Riccati) form
+def stage_data(cfg, state, des_state, des_inputs):
+    """The un-condensed optimal-control form of the same QP (the stage-wise A, B, b, Q, R, q, r
+    interface of the reference's HPIPM adapter, ocs2_sqp/hpipm_catkin/src/HpipmInterface.cpp:166-301):
+      x_{j+1} = A x_j + Bf_j F_j + d,  F_j in R^{3L} with swing-leg entries pinned to zero,
+      cost = sum_{k=1..N} (x_k - xr_k)' Q_k (x_k - xr_k) + sum_j (F_j - Fr_j)' Wf (F_j - Fr_j)
+             + sum_{j<=N-2} (F_{j+1} - F_j)' Wr (F_{j+1} - F_j)          (CentroidalMPC.cpp:203-232)."""
+    N, L, m = cfg["horizon"], cfg["num_legs"], cfg["mass"]
+    w = np.asarray(cfg["weights"], float)
+    x0, feet, dc, dv, dl, contact, dfoot = unpack(cfg, state, des_state, des_inputs)
+    colsum = contact.sum(axis=0)
+    A = None
+    Bf, Q, xr, Fr, free = [], [], [], [], []
+    for j in range(N):
+        A, Bj, d = discretize(cfg, contact[:, j], dfoot[:, j, :] - dc[j][None, :])
+        Bf.append(Bj)
+        node = j + 1
+        om = (w[2] / 2.0) * np.exp(-float(node)) + w[2] / 2.0
+        Q.append(np.diag([w[0], w[1], om * om, w[3], w[4], w[5], w[6], w[7], w[8]]))
+        xr.append(np.concatenate([dc[node], dv[node], dl[node]]))
+        fr = np.zeros(3 * L)
+        fj = []
+        for i in range(L):
+            if contact[i, j] > 0:
+                fr[3 * i + 2] = m * GRAV / colsum[j]
+                fj += [3 * i, 3 * i + 1, 3 * i + 2]
+        Fr.append(fr)
+        free.append(np.array(fj, int))
+    Wf = np.diag(w[9 + 3 * L:9 + 6 * L])
+    Wr = np.diag(w[9 + 6 * L:9 + 9 * L])
+    return dict(A=A, d=d, Bf=Bf, Q=Q, xr=xr, Fr=Fr, free=free, Wf=Wf, Wr=Wr, x0=x0, N=N, L=L)
+
+
+def riccati_unconstrained(cfg, state, des_state, des_inputs):
+    """Unconstrained minimiser of the QP by a backward Riccati sweep over the augmented state
+    z_k = [x_k; F_{k-1}] (the force-rate term couples consecutive inputs) and a forward roll-out:
+    O(N (9 + 3L)^3) instead of O((3LN)^3).  Returns U (3LN, step-major, zeros on pinned entries)."""
+    S = stage_data(cfg, state, des_state, des_inputs)
+    N, L = S["N"], S["L"]
+    nx, nf = 9, 3 * L
+    nz = nx + nf
+    A, d, Wf, Wr = S["A"], S["d"], S["Wf"], S["Wr"]
+    Abar = np.zeros((nz, nz)); Abar[:nx, :nx] = A
+    dbar = np.concatenate([d, np.zeros(nf)])
+    P = np.zeros((nz, nz)); p = np.zeros(nz)
+    P[:nx, :nx] = S["Q"][N - 1]; p[:nx] = -S["Q"][N - 1] @ S["xr"][N - 1]      # V_N
+    gains = [None] * N
+    for k in range(N - 1, -1, -1):
+        fr = S["free"][k]
+        Sk = np.zeros((nf, len(fr))); Sk[fr, np.arange(len(fr))] = 1.0
+        Bbar = np.vstack([S["Bf"][k] @ Sk, Sk])
+        rate = 1.0 if k >= 1 else 0.0
+        G = Sk.T @ (Wf + rate * Wr) @ Sk + Bbar.T @ P @ Bbar
+        M = Bbar.T @ P @ Abar
+        M[:, nx:] -= rate * (Sk.T @ Wr)
+        m0 = Bbar.T @ (P @ dbar + p) - Sk.T @ Wf @ S["Fr"][k]
+        Kk = np.linalg.solve(G, M); kff = np.linalg.solve(G, m0)
+        gains[k] = (Kk, kff, Sk)
+        if k >= 1:
+            Pn = Abar.T @ P @ Abar - M.T @ Kk
+            Pn[:nx, :nx] += S["Q"][k - 1]
+            Pn[nx:, nx:] += Wr
+            pn = Abar.T @ (P @ dbar + p) - M.T @ kff
+            pn[:nx] -= S["Q"][k - 1] @ S["xr"][k - 1]
+            P, p = 0.5 * (Pn + Pn.T), pn
+    x = S["x0"].copy(); Fp = np.zeros(nf)
+    U = np.zeros(nf * N)
+    for k in range(N):
+        Kk, kff, Sk = gains[k]
+        u = -Kk @ np.concatenate([x, Fp]) - kff
+        F = Sk @ u
+        U[nf * k:nf * (k + 1)] = F
+        x = A @ x + S["Bf"][k] @ F + d
+        Fp = F
+    return U
+
+
+def stage_gradient(cfg, state, des_state, des_inputs, U):
+    """(H U + g) on the free entries by one roll-out and one adjoint (costate) sweep -- independent
+    of both the condensed H and the Riccati recursion."""
+    S = stage_data(cfg, state, des_state, des_inputs)
+    N, L = S["N"], S["L"]
+    nf = 3 * L
+    F = U.reshape(N, nf)
+    xs = [S["x0"]]
+    for k in range(N):
+        xs.append(S["A"] @ xs[-1] + S["Bf"][k] @ F[k] + S["d"])
+    lam = np.zeros(9)
+    grad = np.zeros((N, nf))
+    for k in range(N - 1, -1, -1):
+        lam = 2.0 * S["Q"][k] @ (xs[k + 1] - S["xr"][k]) + S["A"].T @ lam     # costate of x_{k+1}
+        gk = 2.0 * S["Wf"] @ (F[k] - S["Fr"][k]) + S["Bf"][k].T @ lam
+        if k >= 1:
+            gk += 2.0 * S["Wr"] @ (F[k] - F[k - 1])
+        if k <= N - 2:
+            gk -= 2.0 * S["Wr"] @ (F[k + 1] - F[k])
+        mask = np.zeros(nf); mask[S["free"][k]] = 1.0
+        grad[k] = gk * mask
+    return grad.reshape(-1)

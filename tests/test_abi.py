@@ -36,8 +36,9 @@ def test_library_exports_every_declared_symbol(pkg):
 
 
 def test_config_struct_layout_matches_header(pkg):
-    # 8+4+4+8+32+360+4+4+8+4+4
-    assert C.sizeof(pkg.CmpcConfig) == 440
+    # 8+4+4+8+32+360+4+4+8+4+4 (polish, presolve) +4+4 (qp_backend, reserved)
+    assert C.sizeof(pkg.CmpcConfig) == 448
+    assert pkg.CmpcConfig.presolve.offset == 436 and pkg.CmpcConfig.qp_backend.offset == 440
     assert pkg.CmpcConfig.weights.offset == 56 and pkg.CmpcConfig.ipm_tol.offset == 424
     lib = pkg.load_library()
     cfg = pkg.CmpcConfig()

@@ -220,3 +220,23 @@ def test_batch_threads_agree(pkg, orc, wl):
     a = orc.solve_batch(cc, st, ds, di, nthreads=1)
     b = orc.solve_batch(cc, st, ds, di, nthreads=5)
     assert np.array_equal(a["forces"], b["forces"]) and np.array_equal(a["status"], b["status"])
+
+
+@pytest.mark.parametrize("N,disc", [(6, 0), (10, 0), (10, 1), (30, 0)])
+def test_stage_wise_riccati_equals_condensed_solve(pkg, wl, N, disc):
+    """the un-condensed (stage-wise, Riccati over [x; F_prev]) form has the same
+    unconstrained minimiser as the condensed dense H, and its adjoint gradient equals H U + g."""
+    import numpy_mirror as nm
+    cfg = wl.default_config(N, disc_mode=disc)
+    st, ds, di = wl.make_batch(cfg, 5, gaits=wl.GAITS)
+    for b in range(5):
+        qp = nm.build_qp(cfg, st[b], ds[b], di[b])
+        Ud = np.linalg.solve(qp["H"], -qp["g"])
+        Ur = nm.riccati_unconstrained(cfg, st[b], ds[b], di[b])
+        assert np.abs(Ud - Ur).max() <= 1e-12 * np.abs(Ud).max()
+        g0 = nm.stage_gradient(cfg, st[b], ds[b], di[b], np.zeros_like(Ur))
+        assert np.abs(g0 - qp["g"]).max() <= 1e-12 * (1 + np.abs(qp["g"]).max())
+        rng = np.random.default_rng(b)
+        U = rng.normal(size=Ur.shape) * ~qp["pinned"]
+        gu = nm.stage_gradient(cfg, st[b], ds[b], di[b], U)
+        assert np.abs(gu - (qp["H"] @ U + qp["g"]) * ~qp["pinned"]).max() <= 1e-11 * (1 + np.abs(gu).max())
