@@ -94,7 +94,9 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
   G.gid = threadIdx.x / GT;
   G.red = nullptr;
   const int lane = G.gtid;
-  double* base = smem + (size_t)G.gid * P.total;
+  // CTA-shared: pair e of a lower triangle stored row by row -> (row << 4 | column), 78 pairs for 12 x 12
+  uint8_t* c_tri = reinterpret_cast<uint8_t*>(smem);
+  double* base = smem + 10 + (size_t)G.gid * P.total;
   int* s_misc = reinterpret_cast<int*>(base + P.ints);  // [0]=nb, [1]=invalid, [2]=work slot, [3]=nb unclamped
   uint8_t* s_blk_j = reinterpret_cast<uint8_t*>(s_misc + 4);
   uint8_t* s_blk_i = s_blk_j + nbfull;
@@ -121,6 +123,12 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
   const double zeta = cfg.zoh ? 0.5 : 0.0;
   const double dpz = zeta * dt * dt * (-kGrav), dvz = dt * (-kGrav);  // affine term d = [dpz e_z; dvz e_z; 0]
   const int count = args.count ? *args.count : args.count_imm;
+  for (int e = threadIdx.x; e < 78; e += blockDim.x) {
+    int rr = 0;
+    while (((rr + 1) * (rr + 2)) >> 1 <= e) ++rr;
+    c_tri[e] = (uint8_t)((rr << 4) | (e - ((rr * (rr + 1)) >> 1)));
+  }
+  __syncthreads();
 
   while (true) {
     int slot = 0;
@@ -218,8 +226,14 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
           if (lane > c && lane < m) R.G[lane * kGld + c] *= inv;
           if (lane == c) R.G[c * kGld + c] = inv;
           __syncwarp();
-          for (int r = c + 1; r < m; ++r)
-            if (lane > c && lane <= r) R.G[r * kGld + lane] -= R.G[r * kGld + c] * R.G[lane * kGld + c];
+          {  // rank-1 update of the trailing lower triangle: one (row, column) pair per lane and pass
+            const int mt = m - c - 1, npair = (mt * (mt + 1)) >> 1;
+            for (int e = lane; e < npair; e += GT) {
+              const int rr = c_tri[e] >> 4, cc = c_tri[e] & 15;  // rr >= cc: pair e of a lower triangle
+              const int r = c + 1 + rr, c2 = c + 1 + cc;
+              R.G[r * kGld + c2] -= R.G[r * kGld + c] * R.G[c2 * kGld + c];
+            }
+          }
           __syncwarp();
         }
         ok = __all_sync(0xffffffffu, ok);
@@ -250,15 +264,19 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
           __syncwarp();
           for (int e = lane; e < 27; e += GT) { const int c = e / 3, r3 = e - 3 * c; R.P[(3 + r3) * nz + c] += dt * R.P[r3 * nz + c]; }  // A'(X A)
           __syncwarp();
-          for (int e = lane; e < nz * nz; e += GT) {
-            const int r = e / nz, c = e - r * nz;
-            if (c <= r) {
-              double acc = (r < 9) ? R.P[e] : 0.0;  // only the state block of Abar' P Abar is non-zero
+          {
+            const int npair = (nz * (nz + 1)) >> 1;
+            for (int e = lane; e < npair; e += GT) {
+              int r = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+              while (((r + 1) * (r + 2)) >> 1 <= e) ++r;
+              while ((r * (r + 1)) >> 1 > e) --r;
+              const int c = e - ((r * (r + 1)) >> 1);  // c <= r
+              double acc = (r < 9) ? R.P[r * nz + c] : 0.0;  // only the state block of Abar' P Abar is non-zero
               if (r == c) acc += r < 9 ? qdiag(cfg, k, r) : cfg.w[9 + 6 * L + r - 9];
 #pragma unroll
               for (int a = 0; a < kMu; ++a)
-                if (a < m) acc -= R.M[a * nz + r] * R.M[a * nz + c];
-              R.P[e] = acc;
+                if (a < m) acc = fma(-R.M[a * nz + r], R.M[a * nz + c], acc);
+              R.P[r * nz + c] = acc;
             }
           }
           double pn = 0.0;
