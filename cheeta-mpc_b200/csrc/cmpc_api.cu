@@ -26,10 +26,10 @@ struct cmpc_handle {
   bool own_stream = false;
   bool zero_copy = true;  // CMPC_NO_ZEROCOPY=1 forces the staged-copy path
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  // chunked, overlapped staging of cmpc_solve_batch: copy-in / compute / copy-out pipelines
+  // progressive host-buffer path of cmpc_solve_batch: chunked copy-in on its own stream
   static constexpr int kMaxChunks = 8;
-  cudaStream_t s_in = nullptr, s_out = nullptr;
-  cudaEvent_t ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {}, ev_span[4] = {};
+  cudaStream_t s_in = nullptr;
+  cudaEvent_t ev_span[4] = {};
   // device buffers
   double *d_state = nullptr, *d_ds = nullptr, *d_di = nullptr, *d_forces = nullptr, *d_kkt = nullptr,
          *d_lam = nullptr, *d_flog = nullptr, *d_hip = nullptr;
@@ -581,9 +581,6 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
   if (!h->stream) { CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
   for (auto& e : h->ev) CUDA_TRY(h, cudaEventCreate(&e));
   CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
-  CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
-  for (auto& e : h->ev_in) CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  for (auto& e : h->ev_k) CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : h->ev_span) CUDA_TRY(h, cudaEventCreate(&e));
 
   const int N = h->cfg.horizon, L = h->cfg.num_legs;
@@ -1074,11 +1071,8 @@ void cmpc_destroy(cmpc_handle* h) {
   cudaFree(h->d_status); cudaFree(h->d_iters);
   cudaFree(h->d_iters_sum); cudaFree(h->d_status_or); cudaFree(h->d_active); cudaFree(h->d_stats);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
-  for (auto& e : h->ev_in) if (e) cudaEventDestroy(e);
-  for (auto& e : h->ev_k) if (e) cudaEventDestroy(e);
   for (auto& e : h->ev_span) if (e) cudaEventDestroy(e);
   if (h->s_in) cudaStreamDestroy(h->s_in);
-  if (h->s_out) cudaStreamDestroy(h->s_out);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
