@@ -261,6 +261,26 @@ def main():
         ipm_only = {"value": B / (ms2 * 1e-3), "unit": UNIT, "p50_batch_latency_ms": ms2, "mean_ipm_iters": it2}
         m2.close()
 
+    # ---- optional exchange (north star: "no inter-GPU traffic beyond an optional NCCL gather of
+    # results over NVLink"): every rank ends up with all forces; timed on its own, NOT part of `value`
+    gather = None
+    if world > 1:
+        allf = torch.empty(world * B, mpc.n_forces, dtype=torch.float64, device=dev)
+        for _ in range(3):
+            dist.all_gather_into_tensor(allf, d_forces)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        g0.record(stream)
+        for _ in range(20):
+            dist.all_gather_into_tensor(allf, d_forces)
+        g1.record(stream)
+        torch.cuda.synchronize()
+        gms = torch.tensor([g0.elapsed_time(g1) / 20], dtype=torch.float64, device=dev)
+        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        assert torch.equal(allf[rank * B:(rank + 1) * B], d_forces)
+        gather = {"collective": "ncclAllGather of the forces", "bytes_total": world * B * mpc.n_forces * 8,
+                  "ms": float(gms[0]), "note": "outside the timed region; value is without it"}
+
     t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -318,6 +338,8 @@ def main():
             ipm_only["flops_per_solve"] = f2
             line["ipm_only"] = ipm_only
         line["config"]["presolve"] = args.presolve
+        if gather is not None:
+            line["nccl_gather"] = gather
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(pkg, cfg, st, ds, di)
         print(json.dumps(line))
