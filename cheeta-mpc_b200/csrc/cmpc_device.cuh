@@ -314,13 +314,18 @@ __device__ __forceinline__ void pivot4(const Group<W>& G, const double (&xr)[2],
   b0 = u.x; b1 = u.y; b2 = v.x; b3 = v.y;
 }
 
+// (For one- and two-warp groups chol / substitutions / symv / copies are called out of line: the interior-
+// point kernel uses each from several places, and inlining them all gave 41 k SASS instructions (660 KB);
+// when the resident warps are in different phases of different instances the instruction cache thrashes --
+// 8.4 stall cycles per issued instruction waiting for instructions on the tracking-heavy workload, 5.7 with
+// the calls.  The 4- and 8-warp variants keep them inline: out of line they spill.)
 // Tiled right-looking Cholesky in BC4 layout, in place; the whole group calls it.
 // tb[t] = bi | bj << 8 for storage tile t.  Diagonal tiles end up in solve form (potrf4).
 // If rhs != nullptr the forward substitution  y = L^-1 rhs  is fused into the sweep (rows
 // live in registers, the update of step kb rides along with the trailing update) and y
 // overwrites rhs.  Returns false (uniformly) on a non-positive pivot.
 template <int W>
-__device__ __forceinline__ bool chol_bc4(const Group<W>& G, double* M, int nblk, const uint16_t* tb, double* rhs, double* exch) {
+__device__ __forceinline__ bool chol_bc4_impl(const Group<W> G, double* M, int nblk, const uint16_t* tb, double* rhs, double* exch) {
   constexpr int GT = Group<W>::GT;
   const int gtid = G.gtid;
   const int ntiles = (nblk * (nblk + 1)) >> 1;
@@ -393,10 +398,16 @@ __device__ __forceinline__ bool chol_bc4(const Group<W>& G, double* M, int nblk,
   }
   return true;
 }
+template <int W>
+__device__ __noinline__ bool chol_bc4_call(const Group<W> G, double* M, int nblk, const uint16_t* tb, double* rhs, double* exch) { return chol_bc4_impl<W>(G, M, nblk, tb, rhs, exch); }
+template <int W>
+__device__ __forceinline__ bool chol_bc4(const Group<W> G, double* M, int nblk, const uint16_t* tb, double* rhs, double* exch) {
+  if constexpr (W <= 2) return chol_bc4_call<W>(G, M, nblk, tb, rhs, exch); else return chol_bc4_impl<W>(G, M, nblk, tb, rhs, exch);
+}
 
 // Forward substitution y = L^-1 x (in place in shared memory), rows in registers.
 template <int W>
-__device__ __forceinline__ void chol_fwd_bc4(const Group<W>& G, const double* M, int nblk, double* x, double* exch) {
+__device__ __forceinline__ void chol_fwd_bc4_impl(const Group<W> G, const double* M, int nblk, double* x, double* exch) {
   constexpr int GT = Group<W>::GT;
   const int gtid = G.gtid, n4 = nblk << 2;
   double xr[2] = {0.0, 0.0};
@@ -425,10 +436,16 @@ __device__ __forceinline__ void chol_fwd_bc4(const Group<W>& G, const double* M,
   }
   G.sync();
 }
+template <int W>
+__device__ __noinline__ void chol_fwd_bc4_call(const Group<W> G, const double* M, int nblk, double* x, double* exch) { chol_fwd_bc4_impl<W>(G, M, nblk, x, exch); }
+template <int W>
+__device__ __forceinline__ void chol_fwd_bc4(const Group<W> G, const double* M, int nblk, double* x, double* exch) {
+  if constexpr (W <= 2) chol_fwd_bc4_call<W>(G, M, nblk, x, exch); else chol_fwd_bc4_impl<W>(G, M, nblk, x, exch);
+}
 
 // Backward substitution x = L^-T y (in place in shared memory), rows in registers.
 template <int W>
-__device__ __forceinline__ void chol_bwd_bc4(const Group<W>& G, const double* M, int nblk, double* x, double* exch) {
+__device__ __forceinline__ void chol_bwd_bc4_impl(const Group<W> G, const double* M, int nblk, double* x, double* exch) {
   constexpr int GT = Group<W>::GT;
   const int gtid = G.gtid, n4 = nblk << 2;
   double xr[2] = {0.0, 0.0};
@@ -455,11 +472,17 @@ __device__ __forceinline__ void chol_bwd_bc4(const Group<W>& G, const double* M,
   }
   G.sync();
 }
+template <int W>
+__device__ __noinline__ void chol_bwd_bc4_call(const Group<W> G, const double* M, int nblk, double* x, double* exch) { chol_bwd_bc4_impl<W>(G, M, nblk, x, exch); }
+template <int W>
+__device__ __forceinline__ void chol_bwd_bc4(const Group<W> G, const double* M, int nblk, double* x, double* exch) {
+  if constexpr (W <= 2) chol_bwd_bc4_call<W>(G, M, nblk, x, exch); else chol_bwd_bc4_impl<W>(G, M, nblk, x, exch);
+}
 
 // y = H x for symmetric H in BC4 layout (diagonal tiles hold both triangles), one row per
 // thread (two passes when n4 > GT).  The whole group calls it; ends with a group barrier.
 template <int W>
-__device__ __forceinline__ void symv_bc4(const Group<W>& G, const double* H, int n4, int nblk, const double* x, double* y) {
+__device__ __forceinline__ void symv_bc4_impl(const Group<W> G, const double* H, int n4, int nblk, const double* x, double* y) {
   constexpr int GT = Group<W>::GT;
   for (int row = G.gtid; row < n4; row += GT) {
     const int bi = row >> 2, ri = row & 3;
@@ -484,19 +507,37 @@ __device__ __forceinline__ void symv_bc4(const Group<W>& G, const double* H, int
   }
   G.sync();
 }
+template <int W>
+__device__ __noinline__ void symv_bc4_call(const Group<W> G, const double* H, int n4, int nblk, const double* x, double* y) { symv_bc4_impl<W>(G, H, n4, nblk, x, y); }
+template <int W>
+__device__ __forceinline__ void symv_bc4(const Group<W> G, const double* H, int n4, int nblk, const double* x, double* y) {
+  if constexpr (W <= 2) symv_bc4_call<W>(G, H, n4, nblk, x, y); else symv_bc4_impl<W>(G, H, n4, nblk, x, y);
+}
 
 // Copy a BC4 matrix, 16 bytes per access (global scratch <-> shared).
 template <int W>
-__device__ __forceinline__ void copy_mat(const Group<W>& G, double* dst, const double* src, int ndoubles) {
+__device__ __forceinline__ void copy_mat_impl(const Group<W> G, double* dst, const double* src, int ndoubles) {
   const double2* s2 = reinterpret_cast<const double2*>(src);
   double2* d2 = reinterpret_cast<double2*>(dst);
   for (int t = G.gtid; t < (ndoubles >> 1); t += Group<W>::GT) d2[t] = __ldcg(s2 + t);
 }
 template <int W>
-__device__ __forceinline__ void store_mat(const Group<W>& G, double* dst, const double* src, int ndoubles) {
+__device__ __noinline__ void copy_mat_call(const Group<W> G, double* dst, const double* src, int ndoubles) { copy_mat_impl<W>(G, dst, src, ndoubles); }
+template <int W>
+__device__ __forceinline__ void copy_mat(const Group<W> G, double* dst, const double* src, int ndoubles) {
+  if constexpr (W <= 2) copy_mat_call<W>(G, dst, src, ndoubles); else copy_mat_impl<W>(G, dst, src, ndoubles);
+}
+template <int W>
+__device__ __forceinline__ void store_mat_impl(const Group<W> G, double* dst, const double* src, int ndoubles) {
   const double2* s2 = reinterpret_cast<const double2*>(src);
   double2* d2 = reinterpret_cast<double2*>(dst);
   for (int t = G.gtid; t < (ndoubles >> 1); t += Group<W>::GT) __stcg(d2 + t, s2[t]);
+}
+template <int W>
+__device__ __noinline__ void store_mat_call(const Group<W> G, double* dst, const double* src, int ndoubles) { store_mat_impl<W>(G, dst, src, ndoubles); }
+template <int W>
+__device__ __forceinline__ void store_mat(const Group<W> G, double* dst, const double* src, int ndoubles) {
+  if constexpr (W <= 2) store_mat_call<W>(G, dst, src, ndoubles); else store_mat_impl<W>(G, dst, src, ndoubles);
 }
 
 // ------------------------------------------------------------------ friction pyramid rows
