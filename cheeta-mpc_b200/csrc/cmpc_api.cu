@@ -29,7 +29,7 @@ struct cmpc_handle {
   // progressive host-buffer path of cmpc_solve_batch: chunked copy-in on its own stream
   static constexpr int kMaxChunks = 8;
   cudaStream_t s_in = nullptr;
-  cudaEvent_t ev_span[4] = {};
+  cudaEvent_t ev_span[4] = {}, ev_in[kMaxChunks] = {};
   // device buffers
   double *d_state = nullptr, *d_ds = nullptr, *d_di = nullptr, *d_forces = nullptr, *d_kkt = nullptr,
          *d_lam = nullptr, *d_flog = nullptr, *d_hip = nullptr;
@@ -58,7 +58,7 @@ struct cmpc_handle {
   int32_t* h_ready_vals = nullptr;   // pinned {1, 2, ...}: the values the copy stream writes into d_ready
   int32_t* h_error_dev = nullptr;    // device alias of h_error
   int32_t* h_error = nullptr;        // pinned + mapped: set by a kernel whose wait on d_ready timed out
-  int e2e_mode = 0;                  // CMPC_E2E_MODE: 0 (default) zero-copy reads of pinned inputs, 2 staged copies, 3 progressive copies
+  int e2e_mode = 0;                  // CMPC_E2E_MODE, see cmpc_solve_batch: 0 auto, 1 zero-copy, 2 staged, 3 progressive, 4 pipelined
   int32_t *d_counts = nullptr, *d_perm = nullptr;  // counts[4], work[4], then the presolve's deferred counts[4], work[4]; perm [2][4][B]
   std::string err;
 };
@@ -582,6 +582,7 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
   for (auto& e : h->ev) CUDA_TRY(h, cudaEventCreate(&e));
   CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
   for (auto& e : h->ev_span) CUDA_TRY(h, cudaEventCreate(&e));
+  for (auto& e : h->ev_in) CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
   const int N = h->cfg.horizon, L = h->cfg.num_legs;
   const size_t ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = (size_t)L * (4 * N + 3), nf = (size_t)3 * L * N;
@@ -741,14 +742,21 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
     dp[q] = mapped_device_pointer(hp[q]);
     if (!dp[q]) (q < 3 ? in_mapped : out_mapped) = false;
   }
-  // Inputs (pinned buffers).  Default: the kernels read them in place over the bus -- every byte
-  // crosses once, overlapped with the other resident instances' compute, no staging copy; measured
-  // 0.36-0.40 ms per 4096-instance step, stable.  CMPC_E2E_MODE=3 ("progressive"): DMA copies in chunks
-  // on a copy stream while the router kernel, launched at the same time, waits per instance for its
-  // chunk; the DMA engine moves the bytes twice as fast (54 GB/s), but the step measured 0.34-0.70 ms
-  // (the copies slow down erratically while 2000 warps poll), so it is not the default.
-  // CMPC_E2E_MODE=2, or pageable buffers: copy in, compute, copy out.
-  const bool zc_in = in_mapped && h->e2e_mode != 2 && h->e2e_mode != 3;
+  // Inputs (pinned buffers), CMPC_E2E_MODE:
+  //  0 (default) pipelined for batches of two waves or more, else zero-copy.
+  //    Pipelined: DMA copies in two chunks on the copy stream (54 GB/s), one launch sequence per chunk on
+  //    the compute stream behind an event -- chunk 0 computes while chunk 1 is copied; plain stream
+  //    dependencies, nothing polls.  0.34 ms per 4096-instance step, stable.
+  //  1 zero-copy: the kernels read the inputs in place over the bus -- every byte crosses once, overlapped
+  //    with the other resident instances' compute, no staging copy; SM-issued reads reach ~26 GB/s:
+  //    0.36-0.40 ms per step.
+  //  2 (and pageable buffers) staged: copy in, compute, copy out.
+  //  3 progressive: copies in 1024-instance chunks while the router kernel, launched at the same time,
+  //    waits per instance for its chunk; best case 0.335 ms but 0.34-0.70 ms over runs (the copies slow
+  //    down erratically while 2000 warps poll).
+  //  4 pipelined regardless of the batch size (>= 1024).
+  const bool pipelined = in_mapped && router && ((h->e2e_mode == 0 && B >= 4096) || (h->e2e_mode == 4 && B >= 1024));
+  const bool zc_in = in_mapped && h->e2e_mode != 2 && h->e2e_mode != 3 && !pipelined;
   // (progressive needs pinned inputs: a pageable cudaMemcpyAsync is staged by the driver and can
   // serialise behind the running kernel, which would then wait for its chunk until the time-out)
   const bool progressive = in_mapped && !zc_in && router && h->e2e_mode == 3 && B >= 256;
@@ -769,6 +777,12 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
     a.lam = lam ? h->d_lam : nullptr; a.active = active ? h->d_active : nullptr;
   }
   int nch = 1, per = B;
+  if (pipelined) {
+    const int want = getenv("CMPC_E2E_CHUNK") ? std::max(256, atoi(getenv("CMPC_E2E_CHUNK"))) : 2048;
+    nch = std::min((B + want - 1) / want, (int)cmpc_handle::kMaxChunks);
+    per = (((B + nch - 1) / nch) + 31) & ~31;
+    nch = (B + per - 1) / per;
+  }
   if (progressive) {
     per = getenv("CMPC_E2E_CHUNK") ? std::max(32, atoi(getenv("CMPC_E2E_CHUNK")) & ~31) : 1024;
     if ((B + per - 1) / per > cmpc_handle::kMaxChunks) per = (((B + cmpc_handle::kMaxChunks - 1) / cmpc_handle::kMaxChunks) + 31) & ~31;
@@ -780,8 +794,8 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
   if (!zc_in) {
     // pinned sources when progressive: these calls only enqueue (chunk c of the three arrays, then
     // the chunk counter); the router kernel launched below polls the counter
-    cudaStream_t sc[1] = {progressive ? h->s_in : s};
-    if (progressive) CUDA_TRY(h, cudaStreamWaitEvent(sc[0], h->ev_span[0], 0));
+    cudaStream_t sc[1] = {(progressive || pipelined) ? h->s_in : s};
+    if (progressive || pipelined) CUDA_TRY(h, cudaStreamWaitEvent(sc[0], h->ev_span[0], 0));
     for (int c = 0; c < nch; ++c) {
       const size_t o = (size_t)c * per;
       const size_t nbc = std::min<size_t>(per, (size_t)B - o);
@@ -790,6 +804,7 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
       CUDA_TRY(h, cudaMemcpyAsync(h->d_di + o * ndi, des_inputs + o * ndi, nbc * ndi * 8, cudaMemcpyHostToDevice, sc[0]));
       if (progressive)
         CUDA_TRY(h, cudaMemcpyAsync(h->d_ready, h->h_ready_vals + c, sizeof(int32_t), cudaMemcpyHostToDevice, sc[0]));
+      if (pipelined) CUDA_TRY(h, cudaEventRecord(h->ev_in[c], sc[0]));
     }
     CUDA_TRY(h, cudaEventRecord(h->ev_span[1], sc[0]));
   } else {
@@ -800,7 +815,23 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
     if (rc < 0) return rc;
     launches = rc;
   }
-  if (!progressive) {
+  if (pipelined) {
+    for (int c = 0; c < nch; ++c) {
+      const size_t o = (size_t)c * per;
+      const int nbc = (int)std::min<size_t>(per, (size_t)B - o);
+      SolveArgs ac = a;
+      ac.state = a.state + o * ns; ac.des_state = a.des_state + o * nds; ac.des_inputs = a.des_inputs + o * ndi;
+      ac.forces = a.forces + o * nf; ac.status = a.status + o;
+      if (a.iters) ac.iters = a.iters + o;
+      if (a.kkt) ac.kkt = a.kkt + o;
+      if (a.lam) ac.lam = a.lam + o * 10 * L * N;
+      if (a.active) ac.active = a.active + o * L * N;
+      CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_in[c], 0));
+      int rc = launch_solve(h, ac, nbc);
+      if (rc < 0) return rc;
+      launches += rc;
+    }
+  } else if (!progressive) {
     int rc = launch_solve(h, a, B);
     if (rc < 0) return rc;
     launches = rc;
@@ -815,7 +846,7 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
     if (active) CUDA_TRY(h, cudaMemcpyAsync(active, h->d_active, (size_t)B * L * N * 2, cudaMemcpyDeviceToHost, s));
   }
   CUDA_TRY(h, cudaEventRecord(h->ev_span[3], s));
-  if (progressive) CUDA_TRY(h, cudaStreamSynchronize(h->s_in));
+  if (progressive || pipelined) CUDA_TRY(h, cudaStreamSynchronize(h->s_in));
   CUDA_TRY(h, cudaStreamSynchronize(s));
   if (*h->h_error) { *h->h_error = 0; return fail(h, CMPC_ERR_CUDA, "cmpc_solve_batch: input chunk did not arrive (copy stream stalled)"); }
   if (stats) {
@@ -1072,6 +1103,7 @@ void cmpc_destroy(cmpc_handle* h) {
   cudaFree(h->d_iters_sum); cudaFree(h->d_status_or); cudaFree(h->d_active); cudaFree(h->d_stats);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->ev_span) if (e) cudaEventDestroy(e);
+  for (auto& e : h->ev_in) if (e) cudaEventDestroy(e);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;

@@ -163,11 +163,12 @@ def test_weights_update_and_zoh_mode(pkg, orc, wl):
     mz.close()
 
 
-@pytest.mark.parametrize("mode", [0, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 def test_host_buffer_paths_agree(pkg, wl, mode, monkeypatch):
-    """cmpc_solve_batch with host buffers: mode 0 = zero-copy reads of pinned inputs (default; outputs
-    written in place when pinned), mode 2 = copy in / compute / copy out, mode 3 = progressive (chunked
-    DMA copy-in overlapped with the router kernel that polls for its chunk).  Pageable and pinned
+    """cmpc_solve_batch with host buffers: mode 0 = automatic (pipelined chunks for big batches, else
+    zero-copy), 1 = zero-copy reads of pinned inputs (outputs written in place when pinned), 2 = copy in /
+    compute / copy out, 3 = progressive (chunked DMA copy-in overlapped with the router kernel that polls
+    for its chunk), 4 = pipelined (chunk c computes while chunk c + 1 is copied).  Pageable and pinned
     buffers, every mode: bit-identical results (mixed gaits, so the router also forwards the stand
     instances to their size class)."""
     import ctypes as C
