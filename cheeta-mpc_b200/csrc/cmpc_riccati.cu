@@ -36,30 +36,29 @@ __device__ __forceinline__ double contact_of(const RicView& R, int i, int k) { r
 
 // Free components of stage k (warp-uniform result m), B-bar = [Bf S; S] (nz x m), column a in Bb[.][a].
 __device__ __forceinline__ int stage_setup(const RicView& R, const DevConfig& cfg, int k, int lane) {
-  const int nf = R.nf, nz = R.nz;
+  const int nf = R.nf;
   const double zeta = cfg.zoh ? 0.5 : 0.0;
   const bool st = lane < nf && contact_of(R, lane / 3, k) > 0.0;
   const unsigned mask = __ballot_sync(0xffffffffu, st);
   const int m = __popc(mask);
   if (lane < nf) R.inv[lane] = st ? (int8_t)__popc(mask & ((1u << lane) - 1u)) : (int8_t)-1;
   if (st) R.cmp[__popc(mask & ((1u << lane) - 1u))] = (uint8_t)lane;
-  for (int e = lane; e < nz * kMu; e += 32) R.Bb[e] = 0.0;
   __syncwarp();
-  if (lane < m) {
+  if (lane < m) {  // only the nine state rows of B-bar are ever read: the selection rows are applied through cmp[]
     const int a = lane, c = R.cmp[a], i = c / 3, q = c - 3 * i;
     const double ce = contact_of(R, i, k), cm = ce / cfg.mass, dt = cfg.dt;
     const double* foot = R.in + R.ns + R.nds + i * (4 * R.N + 3) + R.N + 3 * k;
     const double* com = R.in + R.ns + 3 * k;
     const double r0 = foot[0] - com[0], r1 = foot[1] - com[1], r2 = foot[2] - com[2];  // frozen lever arm
-    R.Bb[q * kMu + a] = zeta * dt * dt * cm;
-    R.Bb[(3 + q) * kMu + a] = dt * cm;
+    const double bp = zeta * dt * dt * cm, bv = dt * cm;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) { R.Bb[x * kMu + a] = x == q ? bp : 0.0; R.Bb[(3 + x) * kMu + a] = x == q ? bv : 0.0; }
     // dt c [r]x e_q = dt c (r x e_q)
     const double s = dt * ce;
     const double v0 = q == 0 ? 0.0 : (q == 1 ? -r2 : r1);
     const double v1 = q == 0 ? r2 : (q == 1 ? 0.0 : -r0);
     const double v2 = q == 0 ? -r1 : (q == 1 ? r0 : 0.0);
     R.Bb[6 * kMu + a] = s * v0; R.Bb[7 * kMu + a] = s * v1; R.Bb[8 * kMu + a] = s * v2;
-    R.Bb[(9 + c) * kMu + a] = 1.0;
   }
   __syncwarp();
   return m;
@@ -277,6 +276,7 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
               for (int a = 0; a < kMu; ++a)
                 if (a < m) acc = fma(-R.M[a * nz + r], R.M[a * nz + c], acc);
               R.P[r * nz + c] = acc;
+              R.P[c * nz + r] = acc;  // (the upper entry is not read by any lane in this loop)
             }
           }
           double pn = 0.0;
@@ -287,7 +287,6 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
               if (a < m) pn -= R.M[a * nz + lane] * R.m0[a];
           }
           __syncwarp();
-          for (int e = lane; e < nz * nz; e += GT) { const int r = e / nz, c = e - r * nz; if (c > r) R.P[e] = R.P[c * nz + r]; }  // mirror
           if (lane < nz) R.p[lane] = pn;
         }
         // gains K = L^-T Y, kff = L^-T y0 -> L2 slab, transposed (K'[col][a]) for the forward sweep
