@@ -23,6 +23,7 @@ namespace {
 
 constexpr int kMu = 3 * kMaxLegs;  // most free inputs of one stage
 constexpr int kGld = 13;           // leading dimension of the stage Hessian G
+constexpr int kRicCta = 10 + 58;   // doubles of CTA-shared decode tables (78 bytes + 231 uint16)
 
 struct RicView {
   const double* in;  // staged inputs [state | des_state | des_inputs]
@@ -95,7 +96,8 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
   const int lane = G.gtid;
   // CTA-shared: pair e of a lower triangle stored row by row -> (row << 4 | column), 78 pairs for 12 x 12
   uint8_t* c_tri = reinterpret_cast<uint8_t*>(smem);
-  double* base = smem + 10 + (size_t)G.gid * P.total;
+  uint16_t* c_trz = reinterpret_cast<uint16_t*>(smem + 10);  // the same for the nz x nz cost-to-go: (row << 8 | column), 231 pairs at nz = 21
+  double* base = smem + kRicCta + (size_t)G.gid * P.total;
   int* s_misc = reinterpret_cast<int*>(base + P.ints);  // [0]=nb, [1]=invalid, [2]=work slot, [3]=nb unclamped
   uint8_t* s_blk_j = reinterpret_cast<uint8_t*>(s_misc + 4);
   uint8_t* s_blk_i = s_blk_j + nbfull;
@@ -126,6 +128,11 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
     int rr = 0;
     while (((rr + 1) * (rr + 2)) >> 1 <= e) ++rr;
     c_tri[e] = (uint8_t)((rr << 4) | (e - ((rr * (rr + 1)) >> 1)));
+  }
+  for (int e = threadIdx.x; e < ((nz * (nz + 1)) >> 1); e += blockDim.x) {
+    int rr = 0;
+    while (((rr + 1) * (rr + 2)) >> 1 <= e) ++rr;
+    c_trz[e] = (uint16_t)((rr << 8) | (e - ((rr * (rr + 1)) >> 1)));
   }
   __syncthreads();
 
@@ -174,13 +181,16 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
         // t = P dbar + p
         if (lane < nz) R.t[lane] = R.P[lane * nz + 2] * dpz + R.P[lane * nz + 5] * dvz + R.p[lane];
         // T1 = P Bbar : rows of Bbar below the state block are a selection
-        for (int e = lane; e < nz * kMu; e += GT) {
-          const int r = e / kMu, a = e - r * kMu;
-          if (a < m) {
+        if (lane < nz) {  // lane = row r: the state part of the P row stays in registers, Bbar entries are broadcast loads
+          const int r = lane;
+          double pr[9];
+#pragma unroll
+          for (int s = 0; s < 9; ++s) pr[s] = R.P[r * nz + s];
+          for (int a = 0; a < m; ++a) {
             double acc = R.P[r * nz + 9 + R.cmp[a]];
 #pragma unroll
-            for (int s = 0; s < 9; ++s) acc = fma(R.P[r * nz + s], R.Bb[s * kMu + a], acc);
-            R.T1[e] = acc;
+            for (int s = 0; s < 9; ++s) acc = fma(pr[s], R.Bb[s * kMu + a], acc);
+            R.T1[r * kMu + a] = acc;
           }
         }
         __syncwarp();
@@ -196,16 +206,16 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
             R.G[a * kGld + b] = acc;
           }
         }
-        for (int e = lane; e < kMu * nz; e += GT) {
-          const int a = e / nz, col = e - a * nz;
-          if (a < m) {
-            double v;
-            if (col < 3) v = R.T1[col * kMu + a];
-            else if (col < 6) v = dt * R.T1[(col - 3) * kMu + a] + R.T1[col * kMu + a];
-            else if (col < 9) v = R.T1[col * kMu + a];
-            else v = (R.cmp[a] == col - 9) ? -rate * cfg.w[9 + 6 * L + col - 9] : 0.0;
-            R.M[a * nz + col] = v;
+        if (lane < m) {  // row a of M = (T1 column a)' Abar, minus the rate coupling to the previous force
+          const int a = lane, c = R.cmp[a];
+          double* Ma = R.M + a * nz;
+#pragma unroll
+          for (int x = 0; x < 3; ++x) {
+            const double tp = R.T1[x * kMu + a];
+            Ma[x] = tp; Ma[3 + x] = dt * tp + R.T1[(3 + x) * kMu + a]; Ma[6 + x] = R.T1[(6 + x) * kMu + a];
           }
+          for (int col = 9; col < nz; ++col) Ma[col] = 0.0;
+          Ma[9 + c] = -rate * cfg.w[9 + 6 * L + c];
         }
         if (lane < m) {
           const int a = lane, c = R.cmp[a];
@@ -266,10 +276,7 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
           {
             const int npair = (nz * (nz + 1)) >> 1;
             for (int e = lane; e < npair; e += GT) {
-              int r = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-              while (((r + 1) * (r + 2)) >> 1 <= e) ++r;
-              while ((r * (r + 1)) >> 1 > e) --r;
-              const int c = e - ((r * (r + 1)) >> 1);  // c <= r
+              const int r = c_trz[e] >> 8, c = c_trz[e] & 0xff;  // c <= r
               double acc = (r < 9) ? R.P[r * nz + c] : 0.0;  // only the state block of Abar' P Abar is non-zero
               if (r == c) acc += r < 9 ? qdiag(cfg, k, r) : cfg.w[9 + 6 * L + r - 9];
 #pragma unroll
