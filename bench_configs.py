@@ -60,7 +60,7 @@ def main():
     ms, s, its, kk = timed_device(pkg, cfg, st, ds, di)
     out.append(dict(config="hard: tracking-heavy weights, mu=0.3, mixed gaits, N=10", batch=B, p50_ms=ms, solves_per_s=B / ms * 1e3,
                     mean_iters=float(its.mean()), status=np.bincount(s, minlength=5).tolist(), max_kkt=float(kk[s <= 1].max())))
-    # config 3: horizon 30.  qp_backend 0 = automatic (stage-wise Riccati presolve above 42 free leg-steps),
+    # config 3: horizon 30.  qp_backend 0 = automatic (stage-wise Riccati presolve above 20 free leg-steps),
     # 1 = condensed dense for every class (stand: n = 360, factor in L2, interior-point kernel only)
     for backend, tag in ((0, "Riccati presolve"), (1, "dense")):
         cfg = dict(wl.default_config(30), qp_backend=backend)

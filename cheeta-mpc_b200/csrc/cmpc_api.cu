@@ -415,7 +415,7 @@ int presolve_kind(const cmpc_handle* h, int c) {
   const bool dense_ok = h->cls[c].pre_used, ric_ok = h->ric_used;
   if (h->cfg.qp_backend == 1) return dense_ok ? 1 : 0;
   if (h->cfg.qp_backend == 2) return ric_ok ? 2 : (dense_ok ? 1 : 0);
-  if (c >= 2 && ric_ok) return 2;  // more than 42 free leg-steps
+  if (c >= 1 && ric_ok) return 2;  // more than 20 free leg-steps: the stage-wise sweep beats the multi-warp dense presolve
   return dense_ok ? 1 : (ric_ok ? 2 : 0);
 }
 

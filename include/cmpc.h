@@ -74,9 +74,9 @@ typedef struct cmpc_config {
                                        force-limit row it is the optimum (status OK, iters 0), else
                                        the instance goes through the interior-point iteration */
   int32_t qp_backend;               /* presolve back-end per size class:
-                                       0 (default) = condensed dense Cholesky for the small classes, stage-wise
-                                           Riccati sweep over [x; F_prev] for instances with more than 42 free
-                                           leg-steps (horizon-30 workloads: O(N 21^3) instead of O((3LN)^3));
+                                       0 (default) = condensed dense Cholesky for instances with up to 20 free
+                                           leg-steps (n <= 60: trot at horizon 10), stage-wise Riccati sweep over
+                                           [x; F_prev] above (stand, horizon 30: O(N 21^3) instead of O((3LN)^3));
                                        1 = dense for every class;  2 = Riccati for every class */
   int32_t reserved;
 } cmpc_config;
