@@ -650,9 +650,9 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
     if ((rc = set_smem_attr(h, 8, 1, false, h->exp_plan.smem_bytes))) return rc;
     {
       const RicPlan rp = make_ric_plan(N, L);
-      h->ric_groups = (int)std::min<size_t>(14, (kMaxSmem / 8 - 68) / (size_t)rp.total);  // 68 doubles: CTA-shared pair tables
+      h->ric_groups = (int)std::min<size_t>(14, (kMaxSmem / 8 - 102) / (size_t)rp.total);  // 102 doubles: CTA-shared tables (kRicCta)
       if (h->ric_groups >= 1) {
-        h->ric_smem_bytes = ((size_t)rp.total * h->ric_groups + 68) * 8;
+        h->ric_smem_bytes = ((size_t)rp.total * h->ric_groups + 102) * 8;
         CUDA_TRY(h, cudaMalloc(&h->d_ric_scratch, (size_t)rp.slab * 8 * (size_t)h->num_sms * h->ric_groups));
         CUDA_TRY(h, set_riccati_kernel_smem(h->ric_smem_bytes));
         h->ric_used = true;

@@ -23,7 +23,7 @@ namespace {
 
 constexpr int kMu = 3 * kMaxLegs;  // most free inputs of one stage
 constexpr int kGld = 13;           // leading dimension of the stage Hessian G
-constexpr int kRicCta = 10 + 58;   // doubles of CTA-shared decode tables (78 bytes + 231 uint16)
+constexpr int kRicCta = 10 + 58 + 34;  // doubles of CTA-shared tables (78 bytes + 231 uint16 decode entries + z weights of nodes 0..32)
 
 struct RicView {
   const double* in;  // staged inputs [state | des_state | des_inputs]
@@ -66,10 +66,8 @@ __device__ __forceinline__ int stage_setup(const RicView& R, const DevConfig& cf
 }
 
 // state weights of node `node` (1..N): diag(w0, w1, omega^2, w3..w8), omega inside the square (:205-210)
-__device__ __forceinline__ double qdiag(const DevConfig& cfg, int node, int r) {
-  if (r != 2) return cfg.w[r];
-  const double om = (cfg.w[2] * 0.5) * exp(-(double)node) + cfg.w[2] * 0.5;
-  return om * om;
+__device__ __forceinline__ double qdiag(const DevConfig& cfg, const double* qz, int node, int r) {
+  return r != 2 ? cfg.w[r] : qz[node];  // qz[node] = ((w2 / 2) e^-node + w2 / 2)^2, tabulated once per CTA
 }
 // reference of node `node`, entry r of [c; v; L]
 __device__ __forceinline__ double xref(const RicView& R, int node, int r) {
@@ -97,6 +95,7 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
   // CTA-shared: pair e of a lower triangle stored row by row -> (row << 4 | column), 78 pairs for 12 x 12
   uint8_t* c_tri = reinterpret_cast<uint8_t*>(smem);
   uint16_t* c_trz = reinterpret_cast<uint16_t*>(smem + 10);  // the same for the nz x nz cost-to-go: (row << 8 | column), 231 pairs at nz = 21
+  double* c_qz = smem + 68;
   double* base = smem + kRicCta + (size_t)G.gid * P.total;
   int* s_misc = reinterpret_cast<int*>(base + P.ints);  // [0]=nb, [1]=invalid, [2]=work slot, [3]=nb unclamped
   uint8_t* s_blk_j = reinterpret_cast<uint8_t*>(s_misc + 4);
@@ -124,6 +123,10 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
   const double zeta = cfg.zoh ? 0.5 : 0.0;
   const double dpz = zeta * dt * dt * (-kGrav), dvz = dt * (-kGrav);  // affine term d = [dpz e_z; dvz e_z; 0]
   const int count = args.count ? *args.count : args.count_imm;
+  for (int e = threadIdx.x; e <= N; e += blockDim.x) {
+    const double om = (cfg.w[2] * 0.5) * exp(-(double)e) + cfg.w[2] * 0.5;  // CentroidalMPC.cpp:205
+    c_qz[e] = om * om;
+  }
   for (int e = threadIdx.x; e < 78; e += blockDim.x) {
     int rr = 0;
     while (((rr + 1) * (rr + 2)) >> 1 <= e) ++rr;
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
       // ---- backward sweep.  V_N = (x - xr_N)' Q_N (x - xr_N)
       for (int e = lane; e < nz * nz; e += GT) R.P[e] = 0.0;
       __syncwarp();
-      if (lane < 9) { const double qd = qdiag(cfg, N, lane); R.P[lane * nz + lane] = qd; R.p[lane] = -qd * xref(R, N, lane); }
+      if (lane < 9) { const double qd = qdiag(cfg, c_qz, N, lane); R.P[lane * nz + lane] = qd; R.p[lane] = -qd * xref(R, N, lane); }
       else if (lane < nz) R.p[lane] = 0.0;
       __syncwarp();
       bool ok = true;
@@ -226,22 +229,21 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
           R.m0[a] = acc;
         }
         __syncwarp();
-        // Cholesky of G (m x m, lower, in place; the diagonal keeps 1 / l_cc)
+        // Cholesky of G (m x m).  The factor goes to Lf (the T1 buffer, dead by now): strict lower = l_rc,
+        // diagonal = 1 / l_cc; the trailing update works from the UNSCALED column (times 1 / d), so scaling and
+        // update of a column need no barrier between them -- one barrier per column.
+        double* Lf = R.T1;
         for (int c = 0; c < m; ++c) {
           const double d = R.G[c * kGld + c];
           ok = ok && d > 0.0;
-          const double inv = fast_rsqrt(d);
-          __syncwarp();
-          if (lane > c && lane < m) R.G[lane * kGld + c] *= inv;
-          if (lane == c) R.G[c * kGld + c] = inv;
-          __syncwarp();
-          {  // rank-1 update of the trailing lower triangle: one (row, column) pair per lane and pass
-            const int mt = m - c - 1, npair = (mt * (mt + 1)) >> 1;
-            for (int e = lane; e < npair; e += GT) {
-              const int rr = c_tri[e] >> 4, cc = c_tri[e] & 15;  // rr >= cc: pair e of a lower triangle
-              const int r = c + 1 + rr, c2 = c + 1 + cc;
-              R.G[r * kGld + c2] -= R.G[r * kGld + c] * R.G[c2 * kGld + c];
-            }
+          const double inv = fast_rsqrt(d), inv2 = inv * inv;
+          if (lane > c && lane < m) Lf[lane * kGld + c] = R.G[lane * kGld + c] * inv;
+          if (lane == c) Lf[c * kGld + c] = inv;
+          const int mt = m - c - 1, npair = (mt * (mt + 1)) >> 1;
+          for (int e = lane; e < npair; e += GT) {  // one (row, column) pair of the trailing lower triangle per lane and pass
+            const int rr = c_tri[e] >> 4, cc = c_tri[e] & 15;
+            const int r = c + 1 + rr, c2 = c + 1 + cc;
+            R.G[r * kGld + c2] -= R.G[r * kGld + c] * R.G[c2 * kGld + c] * inv2;
           }
           __syncwarp();
         }
@@ -256,8 +258,8 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
             if (a < m) {
               double acc = col < nz ? R.M[a * nz + col] : R.m0[a];
 #pragma unroll
-              for (int b = 0; b < a; ++b) acc -= R.G[a * kGld + b] * y[b];
-              y[a] = acc * R.G[a * kGld + a];
+              for (int b = 0; b < a; ++b) acc -= Lf[a * kGld + b] * y[b];
+              y[a] = acc * Lf[a * kGld + a];
             } else {
               y[a] = 0.0;
             }
@@ -274,24 +276,41 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
           for (int e = lane; e < 27; e += GT) { const int c = e / 3, r3 = e - 3 * c; R.P[(3 + r3) * nz + c] += dt * R.P[r3 * nz + c]; }  // A'(X A)
           __syncwarp();
           {
-            const int npair = (nz * (nz + 1)) >> 1;
-            for (int e = lane; e < npair; e += GT) {
-              const int r = c_trz[e] >> 8, c = c_trz[e] & 0xff;  // c <= r
-              double acc = (r < 9) ? R.P[r * nz + c] : 0.0;  // only the state block of Abar' P Abar is non-zero
-              if (r == c) acc += r < 9 ? qdiag(cfg, k, r) : cfg.w[9 + 6 * L + r - 9];
+            // P <- base - Y'Y in 2 x 2 blocks of the lower triangle (block pair e -> (br, bc) from c_tri): four
+            // accumulators per four loads; m is a multiple of 3 (whole legs), so the a-loop needs no predicate
+            const int nzb = (nz + 1) >> 1, nblkp = (nzb * (nzb + 1)) >> 1;
+            for (int e = lane; e < nblkp; e += GT) {
+              const int br = c_tri[e] >> 4, bc = c_tri[e] & 15;
+              const int r0 = 2 * br, c0 = 2 * bc;
+              const int r1 = r0 + 1 < nz ? r0 + 1 : r0, c1 = c0 + 1 < nz ? c0 + 1 : c0;  // (clamped: duplicates are not stored)
+              double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+              for (int a = 0; a < m; a += 3) {
 #pragma unroll
-              for (int a = 0; a < kMu; ++a)
-                if (a < m) acc = fma(-R.M[a * nz + r], R.M[a * nz + c], acc);
-              R.P[r * nz + c] = acc;
-              R.P[c * nz + r] = acc;  // (the upper entry is not read by any lane in this loop)
+                for (int x = 0; x < 3; ++x) {
+                  const double* Ya = R.M + (a + x) * nz;
+                  const double yr0 = Ya[r0], yr1 = Ya[r1], yc0 = Ya[c0], yc1 = Ya[c1];
+                  a00 = fma(yr0, yc0, a00); a01 = fma(yr0, yc1, a01); a10 = fma(yr1, yc0, a10); a11 = fma(yr1, yc1, a11);
+                }
+              }
+              auto put = [&](int r, int c, double yy) {  // entry (r, c), c <= r, and its mirror
+                double v = (r < 9) ? R.P[r * nz + c] : 0.0;  // only the state block of Abar' P Abar is non-zero
+                if (r == c) v += r < 9 ? qdiag(cfg, c_qz, k, r) : cfg.w[9 + 6 * L + r - 9];
+                v -= yy;
+                R.P[r * nz + c] = v; R.P[c * nz + r] = v;
+              };
+              put(r0, c0, a00);
+              if (r0 + 1 < nz) {
+                put(r0 + 1, c0, a10);
+                if (c0 + 1 < nz && c0 + 1 <= r0 + 1) put(r0 + 1, c0 + 1, a11);
+              }
+              if (c0 + 1 < nz && c0 + 1 <= r0) put(r0, c0 + 1, a01);  // (upper entry of a diagonal block: written by its mirror)
             }
           }
           double pn = 0.0;
           if (lane < nz) {
-            pn = lane < 9 ? At_mul(R.t, lane, dt) - qdiag(cfg, k, lane) * xref(R, k, lane) : 0.0;
-#pragma unroll
-            for (int a = 0; a < kMu; ++a)
-              if (a < m) pn -= R.M[a * nz + lane] * R.m0[a];
+            pn = lane < 9 ? At_mul(R.t, lane, dt) - qdiag(cfg, c_qz, k, lane) * xref(R, k, lane) : 0.0;
+            for (int a = 0; a < m; a += 3)
+              pn -= R.M[a * nz + lane] * R.m0[a] + R.M[(a + 1) * nz + lane] * R.m0[a + 1] + R.M[(a + 2) * nz + lane] * R.m0[a + 2];
           }
           __syncwarp();
           if (lane < nz) R.p[lane] = pn;
@@ -304,8 +323,8 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
               double acc = y[a];
 #pragma unroll
               for (int b = a + 1; b < kMu; ++b)
-                if (b < m) acc -= R.G[b * kGld + a] * y[b];
-              y[a] = acc * R.G[a * kGld + a];
+                if (b < m) acc -= Lf[b * kGld + a] * y[b];
+              y[a] = acc * Lf[a * kGld + a];
             }
           }
           double* dst = slab + (size_t)k * kstride + col * kMu;
@@ -353,7 +372,7 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
         const int m = stage_setup(R, cfg, k, lane);
         double l1 = 0.0, l2 = 0.0;
         if (lane < 9) {
-          l1 = 2.0 * qdiag(cfg, k + 1, lane) * (s_X[9 * k + lane] - xref(R, k + 1, lane)) + At_mul(s_lam, lane, dt);
+          l1 = 2.0 * qdiag(cfg, c_qz, k + 1, lane) * (s_X[9 * k + lane] - xref(R, k + 1, lane)) + At_mul(s_lam, lane, dt);
           l2 = 2.0 * V.eq[9 * k + lane] + At_mul(s_lam + 9, lane, dt);  // eq = Q (zero-input state - reference)
         }
         __syncwarp();
