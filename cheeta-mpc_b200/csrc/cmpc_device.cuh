@@ -961,8 +961,10 @@ __host__ __device__ inline RicPlan make_ric_plan(int N, int L) {
   int o = 0;
   auto take = [&](int cnt) { int r = o; o += (cnt + 1) & ~1; return r; };
   const int nin = (9 + 3 * L) + 9 * (N + 1) + L * (4 * N + 3);
-  p.in = take(((nin + 1) & ~1) + 10 * N + nbfull + 2);  // [inputs | eq 9N | qz N | fz nbfull]
-  p.ce = take(nbfull);
+  p.in = take((nin + 1) & ~1);  // the staged inputs stay resident through all three sweeps
+  // (the by-products of the shared prologue -- eq, qz, fz, ce -- are not needed here: they land in the
+  // work region P..M, which is initialised afterwards)
+  p.ce = 0;
   p.P = take(nz * nz);
   p.Bb = take(nz * 12); p.T1 = take(nz * 12); p.G = take(12 * 13); p.M = take(12 * nz + 12);
   // once the backward sweep is done P and T1..M are dead: the trajectory x_1..x_N and the forces go there

@@ -101,9 +101,9 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
   uint8_t* s_blk_j = reinterpret_cast<uint8_t*>(s_misc + 4);
   uint8_t* s_blk_i = s_blk_j + nbfull;
   int8_t* s_blk_of = reinterpret_cast<int8_t*>(s_blk_i + nbfull);
-  const int nin = (ns + nds + ndi + 1) & ~1;
   BuildView V;
-  V.Mm = base + P.in; V.eq = V.Mm + nin; V.qz = V.eq + 9 * N; V.fz = V.qz + N; V.ce = base + P.ce;
+  V.Mm = base + P.in;
+  V.eq = base + P.P; V.qz = V.eq + 9 * N; V.fz = V.qz + N + (N & 1); V.ce = V.fz + nbfull;  // scratch of the shared prologue, dead after it
   V.arm = nullptr; V.g = nullptr; V.tb = nullptr;
   V.misc = s_misc; V.blk_j = s_blk_j; V.blk_i = s_blk_i; V.blk_of = s_blk_of;
   RicView R;
@@ -373,7 +373,13 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
         double l1 = 0.0, l2 = 0.0;
         if (lane < 9) {
           l1 = 2.0 * qdiag(cfg, c_qz, k + 1, lane) * (s_X[9 * k + lane] - xref(R, k + 1, lane)) + At_mul(s_lam, lane, dt);
-          l2 = 2.0 * V.eq[9 * k + lane] + At_mul(s_lam + 9, lane, dt);  // eq = Q (zero-input state - reference)
+          // zero-input state of node k + 1 in closed form (x = A^node x0 + sum A^p d), for g = gradient at U = 0
+          const double kk = (double)(k + 1);
+          double xz = R.in[lane];
+          if (lane < 3) xz += kk * dt * R.in[3 + lane];
+          if (lane == 2) xz += (cfg.zoh ? 0.5 * kk * kk : 0.5 * kk * (kk - 1.0)) * dt * dt * (-kGrav);
+          if (lane == 5) xz += kk * dt * (-kGrav);
+          l2 = 2.0 * qdiag(cfg, c_qz, k + 1, lane) * (xz - xref(R, k + 1, lane)) + At_mul(s_lam + 9, lane, dt);
         }
         __syncwarp();
         if (lane < 9) { s_lam[lane] = l1; s_lam[9 + lane] = l2; }
