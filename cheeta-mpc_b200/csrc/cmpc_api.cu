@@ -59,6 +59,10 @@ struct cmpc_handle {
   int32_t* h_error_dev = nullptr;    // device alias of h_error
   int32_t* h_error = nullptr;        // pinned + mapped: set by a kernel whose wait on d_ready timed out
   int e2e_mode = 0;                  // CMPC_E2E_MODE, see cmpc_solve_batch: 0 auto, 1 zero-copy, 2 staged, 3 progressive, 4 pipelined
+  // auto mode, big pinned batches: the first calls time the zero-copy and the pipelined route (which one
+  // wins depends on the box: DMA 35-56 GB/s vs ~26 GB/s SM-issued reads), then the faster one is kept
+  int tune_calls = 0, tune_batch = 0;
+  float tune_best[2] = {1e30f, 1e30f};  // [0] zero-copy, [1] pipelined: best span in ms
   int32_t *d_counts = nullptr, *d_perm = nullptr;  // counts[4], work[4], then the presolve's deferred counts[4], work[4]; perm [2][4][B]
   std::string err;
 };
@@ -743,7 +747,9 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
     if (!dp[q]) (q < 3 ? in_mapped : out_mapped) = false;
   }
   // Inputs (pinned buffers), CMPC_E2E_MODE:
-  //  0 (default) pipelined for batches of two waves or more, else zero-copy.
+  //  0 (default) for batches of two waves or more: the first six calls time the pipelined and the zero-copy
+  //    route alternately and the faster one is kept (re-tuned when the batch size changes); smaller batches
+  //    use zero-copy.
   //    Pipelined: DMA copies in two chunks on the copy stream (54 GB/s), one launch sequence per chunk on
   //    the compute stream behind an event -- chunk 0 computes while chunk 1 is copied; plain stream
   //    dependencies, nothing polls.  0.34 ms per 4096-instance step, stable.
@@ -755,7 +761,11 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
   //    waits per instance for its chunk; best case 0.335 ms but 0.34-0.70 ms over runs (the copies slow
   //    down erratically while 2000 warps poll).
   //  4 pipelined regardless of the batch size (>= 1024).
-  const bool pipelined = in_mapped && router && ((h->e2e_mode == 0 && B >= 4096) || (h->e2e_mode == 4 && B >= 1024));
+  const bool tunable = in_mapped && router && h->e2e_mode == 0 && B >= 4096;
+  if (tunable && h->tune_batch != B) { h->tune_batch = B; h->tune_calls = 0; h->tune_best[0] = h->tune_best[1] = 1e30f; }
+  const bool tuning = tunable && h->tune_calls < 6;
+  const bool auto_pipelined = tunable && (tuning ? (h->tune_calls & 1) != 0 : h->tune_best[1] < h->tune_best[0]);
+  const bool pipelined = in_mapped && router && (auto_pipelined || (h->e2e_mode == 4 && B >= 1024));
   const bool zc_in = in_mapped && h->e2e_mode != 2 && h->e2e_mode != 3 && !pipelined;
   // (progressive needs pinned inputs: a pageable cudaMemcpyAsync is staged by the driver and can
   // serialise behind the running kernel, which would then wait for its chunk until the time-out)
@@ -849,6 +859,14 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
   if (progressive || pipelined) CUDA_TRY(h, cudaStreamSynchronize(h->s_in));
   CUDA_TRY(h, cudaStreamSynchronize(s));
   if (*h->h_error) { *h->h_error = 0; return fail(h, CMPC_ERR_CUDA, "cmpc_solve_batch: input chunk did not arrive (copy stream stalled)"); }
+  if (tuning) {
+    float span = 0;
+    CUDA_TRY(h, cudaEventElapsedTime(&span, h->ev_span[0], h->ev_span[3]));
+    float& best = h->tune_best[pipelined ? 1 : 0];
+    best = std::min(best, span);
+    ++h->tune_calls;
+    if (getenv("CMPC_DEBUG_TUNE")) fprintf(stderr, "[cmpc] tune call %d: %s %.3f ms (best zero-copy %.3f, pipelined %.3f)\n", h->tune_calls, pipelined ? "pipelined" : "zero-copy", span, h->tune_best[0], h->tune_best[1]);
+  }
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
     int rc = collect_stats(h, B, a.status, a.iters, a.kkt, stats, launches);

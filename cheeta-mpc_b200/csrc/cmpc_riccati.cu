@@ -78,6 +78,33 @@ __device__ __forceinline__ double At_mul(const double* v, int r, double dt) { re
 // (A v)[r]
 __device__ __forceinline__ double A_mul(const double* v, int r, double dt) { return r < 3 ? v[r] + dt * v[r + 3] : v[r]; }
 
+// Triangular solves of one column with the stage factor Lf (strict lower = l, diagonal = 1 / l_cc); the
+// number of free inputs MT is compiled in (3, 6, 9 or 12: whole legs), so no iteration is predicated.
+template <int MT>
+__device__ __forceinline__ void tri_fwd(const double* Lf, double* M, double* m0, int nz, int col, double (&y)[kMu]) {
+#pragma unroll
+  for (int a = 0; a < MT; ++a) {
+    double acc = col < nz ? M[a * nz + col] : m0[a];
+#pragma unroll
+    for (int b = 0; b < a; ++b) acc -= Lf[a * kGld + b] * y[b];
+    y[a] = acc * Lf[a * kGld + a];
+  }
+#pragma unroll
+  for (int a = MT; a < kMu; ++a) y[a] = 0.0;
+#pragma unroll
+  for (int a = 0; a < MT; ++a) { if (col < nz) M[a * nz + col] = y[a]; else m0[a] = y[a]; }
+}
+template <int MT>
+__device__ __forceinline__ void tri_bwd(const double* Lf, double (&y)[kMu]) {
+#pragma unroll
+  for (int a = MT - 1; a >= 0; --a) {
+    double acc = y[a];
+#pragma unroll
+    for (int b = a + 1; b < MT; ++b) acc -= Lf[b * kGld + a] * y[b];
+    y[a] = acc * Lf[a * kGld + a];
+  }
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, const SolveArgs args) {
@@ -253,20 +280,12 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
         double y[kMu];
         const int col = lane;
         if (col <= nz) {
-#pragma unroll
-          for (int a = 0; a < kMu; ++a) {
-            if (a < m) {
-              double acc = col < nz ? R.M[a * nz + col] : R.m0[a];
-#pragma unroll
-              for (int b = 0; b < a; ++b) acc -= Lf[a * kGld + b] * y[b];
-              y[a] = acc * Lf[a * kGld + a];
-            } else {
-              y[a] = 0.0;
-            }
+          switch (m) {
+            case 3: tri_fwd<3>(Lf, R.M, R.m0, nz, col, y); break;
+            case 6: tri_fwd<6>(Lf, R.M, R.m0, nz, col, y); break;
+            case 9: tri_fwd<9>(Lf, R.M, R.m0, nz, col, y); break;
+            default: tri_fwd<12>(Lf, R.M, R.m0, nz, col, y); break;
           }
-#pragma unroll
-          for (int a = 0; a < kMu; ++a)
-            if (a < m) { if (col < nz) R.M[a * nz + col] = y[a]; else R.m0[a] = y[a]; }
         }
         __syncwarp();
         if (k >= 1) {
@@ -317,15 +336,11 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
         }
         // gains K = L^-T Y, kff = L^-T y0 -> L2 slab, transposed (K'[col][a]) for the forward sweep
         if (col <= nz) {
-#pragma unroll
-          for (int a = kMu - 1; a >= 0; --a) {
-            if (a < m) {
-              double acc = y[a];
-#pragma unroll
-              for (int b = a + 1; b < kMu; ++b)
-                if (b < m) acc -= Lf[b * kGld + a] * y[b];
-              y[a] = acc * Lf[a * kGld + a];
-            }
+          switch (m) {
+            case 3: tri_bwd<3>(Lf, y); break;
+            case 6: tri_bwd<6>(Lf, y); break;
+            case 9: tri_bwd<9>(Lf, y); break;
+            default: tri_bwd<12>(Lf, y); break;
           }
           double* dst = slab + (size_t)k * kstride + col * kMu;
 #pragma unroll

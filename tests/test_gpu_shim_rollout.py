@@ -209,3 +209,29 @@ def test_host_buffer_paths_agree(pkg, wl, mode, monkeypatch):
     m.synchronize()
     assert np.array_equal(df.cpu().numpy(), pageable["forces"])
     m.close()
+
+
+def test_auto_route_tuning_keeps_results(pkg, wl):
+    """Default mode with a big pinned batch: the first six calls alternate between the zero-copy and the
+    pipelined route (the library keeps the faster one afterwards); every call must return the same bits."""
+    import ctypes as C
+    import torch
+    cfg = wl.default_config(10)
+    B = 4096
+    st, ds, di = wl.make_batch(cfg, B)
+    m = pkg.CentroidalMPC.from_dict(cfg)
+    m.SetupMPC(B)
+    pin = [torch.from_numpy(a).pin_memory() for a in (st, ds, di)]
+    f = torch.zeros(B, m.n_forces, dtype=torch.float64).pin_memory()
+    s = torch.full((B,), -1, dtype=torch.int32).pin_memory()
+    vp = C.c_void_p
+    ref = None
+    for call in range(9):
+        f.zero_(); s.fill_(-1)
+        rc = m.lib.cmpc_solve_batch(m.h, B, vp(pin[0].data_ptr()), vp(pin[1].data_ptr()), vp(pin[2].data_ptr()), vp(f.data_ptr()),
+                                    vp(s.data_ptr()), None, None, None, None, None)
+        assert rc == 0 and (s.numpy() == 0).all()
+        if ref is None:
+            ref = f.numpy().copy()
+        assert np.array_equal(f.numpy(), ref), call
+    m.close()

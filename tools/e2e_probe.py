@@ -12,7 +12,7 @@ def step(stats=None):
     rc = m.lib.cmpc_solve_batch(m.h, B, vp(pin[0].data_ptr()), vp(pin[1].data_ptr()), vp(pin[2].data_ptr()), vp(f.data_ptr()),
                                 vp(s.data_ptr()), None, None, None, None, C.byref(stats) if stats else None)
     assert rc == 0
-for _ in range(5): step()
+for _ in range(10): step()
 t0 = time.perf_counter()
 for _ in range(50): step()
 wall = (time.perf_counter() - t0) / 50
