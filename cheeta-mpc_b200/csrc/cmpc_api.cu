@@ -61,6 +61,8 @@ struct cmpc_handle {
   int e2e_mode = 0;                  // CMPC_E2E_MODE, see cmpc_solve_batch: 0 auto, 1 zero-copy, 2 staged, 3 progressive, 4 pipelined
   // auto mode, big pinned batches: the first calls time the zero-copy and the pipelined route (which one
   // wins depends on the box: DMA 35-56 GB/s vs ~26 GB/s SM-issued reads), then the faster one is kept
+  int e2e_chunk = 0;                 // CMPC_E2E_CHUNK: instances per copy chunk (0: default of the route)
+  bool debug_tune = false;           // CMPC_DEBUG_TUNE: print the route timings of the tuning calls
   int tune_calls = 0, tune_batch = 0;
   float tune_best[2] = {1e30f, 1e30f};  // [0] zero-copy, [1] pipelined: best span in ms
   int32_t *d_counts = nullptr, *d_perm = nullptr;  // counts[4], work[4], then the presolve's deferred counts[4], work[4]; perm [2][4][B]
@@ -612,6 +614,8 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
   *h->h_error = 0;
   CUDA_TRY(h, cudaHostGetDevicePointer((void**)&h->h_error_dev, h->h_error, 0));
   if (const char* m = getenv("CMPC_E2E_MODE")) h->e2e_mode = atoi(m);
+  if (const char* m = getenv("CMPC_E2E_CHUNK")) h->e2e_chunk = atoi(m);
+  h->debug_tune = getenv("CMPC_DEBUG_TUNE") != nullptr;
   CUDA_TRY(h, cudaMalloc(&h->d_counts, 4 * kNumClasses * sizeof(int32_t)));
   CUDA_TRY(h, cudaMalloc(&h->d_perm, (size_t)2 * kNumClasses * B * sizeof(int32_t)));
   // size classes by number of free 3-blocks: n4 <= 64 -> one warp per instance, n4 <= 128 ->
@@ -788,13 +792,13 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
   }
   int nch = 1, per = B;
   if (pipelined) {
-    const int want = getenv("CMPC_E2E_CHUNK") ? std::max(256, atoi(getenv("CMPC_E2E_CHUNK"))) : 2048;
+    const int want = h->e2e_chunk > 0 ? std::max(256, h->e2e_chunk) : 2048;
     nch = std::min((B + want - 1) / want, (int)cmpc_handle::kMaxChunks);
     per = (((B + nch - 1) / nch) + 31) & ~31;
     nch = (B + per - 1) / per;
   }
   if (progressive) {
-    per = getenv("CMPC_E2E_CHUNK") ? std::max(32, atoi(getenv("CMPC_E2E_CHUNK")) & ~31) : 1024;
+    per = h->e2e_chunk > 0 ? std::max(32, h->e2e_chunk & ~31) : 1024;
     if ((B + per - 1) / per > cmpc_handle::kMaxChunks) per = (((B + cmpc_handle::kMaxChunks - 1) / cmpc_handle::kMaxChunks) + 31) & ~31;
     nch = (B + per - 1) / per;
     CUDA_TRY(h, cudaMemsetAsync(h->d_ready, 0, 4 * sizeof(int32_t), s));
@@ -865,7 +869,7 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
     float& best = h->tune_best[pipelined ? 1 : 0];
     best = std::min(best, span);
     ++h->tune_calls;
-    if (getenv("CMPC_DEBUG_TUNE")) fprintf(stderr, "[cmpc] tune call %d: %s %.3f ms (best zero-copy %.3f, pipelined %.3f)\n", h->tune_calls, pipelined ? "pipelined" : "zero-copy", span, h->tune_best[0], h->tune_best[1]);
+    if (h->debug_tune) fprintf(stderr, "[cmpc] tune call %d: %s %.3f ms (best zero-copy %.3f, pipelined %.3f)\n", h->tune_calls, pipelined ? "pipelined" : "zero-copy", span, h->tune_best[0], h->tune_best[1]);
   }
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
