@@ -47,24 +47,38 @@ class CentroidalMPC {
     cmpc_stats stats;
   };
 
+  /* solver knobs the reference does not have (cmpc_config); none of them changes the optimum returned */
+  struct Options {
+    int disc_mode = 0;     // 0 explicit Euler (the reference), 1 zero-order hold
+    int presolve = 1;      // unconstrained minimiser verified first (one Cholesky of H)
+    int qp_backend = 0;    // 0 automatic, 1 condensed dense, 2 stage-wise Riccati presolve
+    int polish = 1;        // active-set polish after the interior-point iteration
+    int max_iter = 50;
+    double ipm_tol = 1e-9;
+  };
+
   CentroidalMPC() = delete;
   CentroidalMPC(const CentroidalMPC&) = delete;             // reference NonlinearMPC.h:49-51
   CentroidalMPC& operator=(const CentroidalMPC&) = delete;
 
   CentroidalMPC(double mass, int num_legs, int predict_horizon, double time_step, const double* weights,
-                size_t n_weights, const double* mu, size_t n_mu, IPOPT_SOLVER = IPOPT_SOLVER::MA97, int device = 0)
+                size_t n_weights, const double* mu, size_t n_mu, IPOPT_SOLVER = IPOPT_SOLVER::MA97, int device = 0,
+                const Options& opt = Options())
       : num_legs_(num_legs), horizon_(predict_horizon), device_(device) {
     if (!(mass > 0) || num_legs <= 0 || predict_horizon <= 0)
       throw std::runtime_error("CentroidalMPC: mass > 0 && num_legs > 0 && predict_horizon > 0 required");
     if (n_mu != (size_t)num_legs) throw std::runtime_error("CentroidalMPC: mu.size() == num_legs required");
     if (n_weights < (size_t)(9 + 9 * num_legs)) throw std::runtime_error("CentroidalMPC: weights needs 9 + 9*num_legs entries");
-    if (cmpc_config_init(&cfg_, mass, num_legs, predict_horizon, time_step, weights, mu) != CMPC_OK ||
-        cmpc_create(&cfg_, &h_) != CMPC_OK)
+    if (cmpc_config_init(&cfg_, mass, num_legs, predict_horizon, time_step, weights, mu) != CMPC_OK)
       throw std::runtime_error("CentroidalMPC: invalid constructor arguments");
+    cfg_.disc_mode = opt.disc_mode; cfg_.presolve = opt.presolve; cfg_.qp_backend = opt.qp_backend;
+    cfg_.polish = opt.polish; cfg_.max_iter = opt.max_iter; cfg_.ipm_tol = opt.ipm_tol;
+    if (cmpc_create(&cfg_, &h_) != CMPC_OK) throw std::runtime_error("CentroidalMPC: invalid constructor arguments");
   }
   CentroidalMPC(double mass, int num_legs, int predict_horizon, double time_step, const std::vector<double>& weights,
-                const std::vector<double>& mu, IPOPT_SOLVER s = IPOPT_SOLVER::MA97, int device = 0)
-      : CentroidalMPC(mass, num_legs, predict_horizon, time_step, weights.data(), weights.size(), mu.data(), mu.size(), s, device) {}
+                const std::vector<double>& mu, IPOPT_SOLVER s = IPOPT_SOLVER::MA97, int device = 0,
+                const Options& opt = Options())
+      : CentroidalMPC(mass, num_legs, predict_horizon, time_step, weights.data(), weights.size(), mu.data(), mu.size(), s, device, opt) {}
 #ifdef CMPC_HAVE_EIGEN
   CentroidalMPC(double mass, int num_legs, int predict_horizon, double time_step, const Eigen::VectorXd& weights,
                 const Eigen::VectorXd& mu, IPOPT_SOLVER s = IPOPT_SOLVER::MA97)
