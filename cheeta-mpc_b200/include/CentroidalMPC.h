@@ -37,6 +37,16 @@
  * solved by the library's own batched interior point, not by IPOPT + HSL */
 enum class IPOPT_SOLVER : unsigned int { MUMPS = 0, WSMP = 1, PARDISO = 2, MA27 = 3, MA57 = 4, MA77 = 5, MA86 = 6, MA97 = 7 };
 
+/* solver knobs the reference does not have (cmpc_config); none of them changes the optimum returned */
+struct CentroidalMPCOptions {
+  int disc_mode = 0;     // 0 explicit Euler (the reference), 1 zero-order hold
+  int presolve = 1;      // unconstrained minimiser verified first (one Cholesky of H)
+  int qp_backend = 0;    // 0 automatic, 1 condensed dense, 2 stage-wise Riccati presolve
+  int polish = 1;        // active-set polish after the interior-point iteration
+  int max_iter = 50;
+  double ipm_tol = 1e-9;
+};
+
 class CentroidalMPC {
  public:
   struct BatchResult {
@@ -47,15 +57,7 @@ class CentroidalMPC {
     cmpc_stats stats;
   };
 
-  /* solver knobs the reference does not have (cmpc_config); none of them changes the optimum returned */
-  struct Options {
-    int disc_mode = 0;     // 0 explicit Euler (the reference), 1 zero-order hold
-    int presolve = 1;      // unconstrained minimiser verified first (one Cholesky of H)
-    int qp_backend = 0;    // 0 automatic, 1 condensed dense, 2 stage-wise Riccati presolve
-    int polish = 1;        // active-set polish after the interior-point iteration
-    int max_iter = 50;
-    double ipm_tol = 1e-9;
-  };
+  using Options = CentroidalMPCOptions;
 
   CentroidalMPC() = delete;
   CentroidalMPC(const CentroidalMPC&) = delete;             // reference NonlinearMPC.h:49-51
