@@ -490,12 +490,12 @@ int plan_class(cmpc_handle* h, cmpc_handle::ClassPlan& p, int W, int nbmax, int 
   p.W = W; p.nbmax = nbmax; p.n4max = ((3 * nbmax + 3) / 4) * 4;
   p.m_in_smem = 1;
   SmemPlan sp = make_plan(N, L, W, p.nbmax, p.n4max, 1);
-  if (mode == 1 || (size_t)sp.total * 8 > kMaxSmem) { p.m_in_smem = 0; sp = make_plan(N, L, W, p.nbmax, p.n4max, 0); }
-  if ((size_t)sp.total * 8 > kMaxSmem) return fail(h, CMPC_ERR_ARG, "horizon too large for the shared-memory vectors");
+  if (mode == 1 || ((size_t)sp.total + sp.cta) * 8 > kMaxSmem) { p.m_in_smem = 0; sp = make_plan(N, L, W, p.nbmax, p.n4max, 0); }
+  if (((size_t)sp.total + sp.cta) * 8 > kMaxSmem) return fail(h, CMPC_ERR_ARG, "horizon too large for the shared-memory vectors");
   const int gmax = (W == 2 ? 512 : (W == 1 ? 320 : 256)) / (32 * W);
-  p.groups = (int)std::min<size_t>((size_t)gmax, kMaxSmem / ((size_t)sp.total * 8));
+  p.groups = (int)std::min<size_t>((size_t)gmax, (kMaxSmem / 8 - sp.cta) / (size_t)sp.total);
   if (p.groups < 1) p.groups = 1;
-  p.smem_bytes = (size_t)sp.total * 8 * p.groups;
+  p.smem_bytes = ((size_t)sp.total * p.groups + sp.cta) * 8;
   p.grid = h->num_sms;
   // H (and the factor when it does not fit on chip) + the polish's null-space bases (9 doubles per leg-step)
   p.scratch_per_group = (size_t)mat_region_doubles(N, L, p.n4max) * (p.m_in_smem ? 1 : 2) + (size_t)((9 * p.nbmax + 1) & ~1);

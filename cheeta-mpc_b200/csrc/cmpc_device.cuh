@@ -24,6 +24,8 @@
 #include <stdint.h>
 #include <math.h>
 
+#include <type_traits>
+
 #include "../../include/cmpc.h"
 
 namespace cmpc {
@@ -60,6 +62,7 @@ struct SmemPlan {
   int ce, g, u, rd, tv, rhs, du, dua;
   int zl, zu, red, exch, ints, Mm;
   int total;  // doubles, multiple of 2
+  int cta;    // doubles of CTA-shared tables in front of the groups: z1[N], z2[N] (build_qp)
 };
 
 // One launch = one size class.
@@ -703,6 +706,7 @@ __host__ __device__ inline SmemPlan make_plan(int N, int L, int W, int nbmax, in
   p.Mm = o;
   if (m_in_smem) o += mat_region_doubles(N, L, n4max);
   p.total = (o + 1) & ~1;
+  p.cta = (2 * N + 1) & ~1;
   return p;
 }
 
@@ -803,10 +807,35 @@ __device__ __forceinline__ bool stage_inputs(const Group<W>& G, const DevConfig&
   return finite;
 }
 
+// z-weighted power-stacking sums of the position rows, one table per CTA (they depend on the weights only):
+//   z1[j] = sum_{k >= j} (k - j + zeta) qz_k,  z2[j] = sum_{k >= j} (k - j + zeta)^2 qz_k,  qz_k = omega_{k+1}^2
+// (CentroidalMPC.cpp:203-210).  Called by the first N threads of the CTA, followed by __syncthreads().
+__device__ __forceinline__ void fill_z_tables(const DevConfig& cfg, double* z1, double* z2, int j) {
+  const double zeta = cfg.zoh ? 0.5 : 0.0;
+  double a1 = 0.0, a2 = 0.0;
+  for (int k = j; k < cfg.N; ++k) {
+    const double om = (cfg.w[2] * 0.5) * exp(-(double)(k + 1)) + cfg.w[2] * 0.5;
+    const double al = (double)(k - j) + zeta;
+    a1 += al * om * om; a2 += al * al * om * om;
+  }
+  z1[j] = a1; z2[j] = a2;
+}
+
 // H = 2 (Bqp' L Bqp + K) in BC4 layout into Hb, g into V.g; reads the inputs staged in V.Mm (Hb may
 // be V.Mm itself: the staged inputs are consumed before the first tile is written).
+// One thread per block pair (b >= b2, hence j >= j2), every lane the same instruction stream.  With
+// d = j - j2, cnt = N - j (row blocks k >= j contribute; column (j,i) of Bqp at row block k is
+// A_d^{k-j} B_j = [dt^2 (k-j+zeta)(c/m) I; dt (c/m) I; dt c [r]x], Euler zeta = 0, ZOH 1/2):
+//   angular   cnt dt^2 c c2 [r]x' diag(w6..8) [r2]x
+//   diagonal  (c/m)(c2/m) (dt^4 P_a + cnt dt^2 w[3+a]),  P_a = w[a] (S2 + d S1) for x, y and z2[j] + d z1[j]
+//             for z;  S1, S2 = sums of (t + zeta), (t + zeta)^2 over t < cnt
+//   same leg  K = W_f + D' W_r D (CentroidalMPC.cpp:223-231)
+// Element (gi, gj) of a lower tile lives at R(gi) + C(gj): R = (gi >> 2) kTS + 4 (gi & 3),
+// C = colbase(gj >> 2) kTS + (gj & 3).  Far pairs (b2 <= b - 2) lie strictly below the diagonal tiles;
+// near pairs (b2 = b, b - 1) may touch one and mirror into it; the two kinds run in separate loops.
 template <int W>
-__device__ __forceinline__ void build_qp(const Group<W>& G, const DevConfig& cfg, const BuildView& V, double* Hb, int nb) {
+__device__ __forceinline__ void build_qp(const Group<W>& G, const DevConfig& cfg, const BuildView& V, double* Hb, int nb,
+                                         const double* z1, const double* z2) {
   constexpr int GT = Group<W>::GT;
   const int gtid = G.gtid;
   const int N = cfg.N, L = cfg.L;
@@ -814,7 +843,6 @@ __device__ __forceinline__ void build_qp(const Group<W>& G, const DevConfig& cfg
   const double dt = cfg.dt, mass = cfg.mass;
   const double zeta = cfg.zoh ? 0.5 : 0.0;
   const int n = 3 * nb, nblk = (n + 3) >> 2, n4 = nblk << 2;
-  const int matd = ((nblk * (nblk + 1)) >> 1) * kTS;
   // lever arms r = des_foot_pos[:, j] - des_com_pos[:, j] (frozen), tile table
   for (int b = gtid; b < nb; b += GT) {
     const int j = V.blk_j[b], i = V.blk_i[b];
@@ -824,75 +852,82 @@ __device__ __forceinline__ void build_qp(const Group<W>& G, const DevConfig& cfg
     const int o = blkoff(bj, bj, nblk);
     for (int bi = bj; bi < nblk; ++bi) V.tb[o + bi - bj] = (uint16_t)(bi | (bj << 8));
   }
-  // ---- H = 2 (Bqp' L Bqp + K) on the free variables, one thread per block pair (b >= b2),
-  // assembled on chip (in the factor's buffer) and then streamed to the L2-resident copy.
-  // Column (j,i) of Bqp at row block k >= j is A_d^{k-j} B_j =
-  //   [ dt^2 (k-j+zeta) (c/m) I ; dt (c/m) I ; dt c [r]x ]   (a2/a3; Euler zeta=0, ZOH 1/2)
     G.sync();  // all reads of the staged inputs (they live in the factor's buffer) are done
-    for (int t = gtid; t < matd; t += GT) Hb[t] = 0.0;
-    G.sync();
-    const int npairs = (nb * (nb + 1)) >> 1;
-    const double dt2 = dt * dt, dt4 = dt2 * dt2;
-    for (int idx = gtid; idx < npairs; idx += GT) {
-      int a = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
-      while (((a + 1) * (a + 2)) >> 1 <= idx) ++a;
-      while ((a * (a + 1)) >> 1 > idx) --a;
-      const int b2 = idx - ((a * (a + 1)) >> 1), b = a;  // b >= b2  => j >= j2
-      const int j = V.blk_j[b], i = V.blk_i[b], j2 = V.blk_j[b2], i2 = V.blk_i[b2];
-      const double ce = V.ce[b], ce2 = V.ce[b2];
-      const double r0 = V.arm[3 * b], r1 = V.arm[3 * b + 1], r2 = V.arm[3 * b + 2];
-      const double p0 = V.arm[3 * b2], p1 = V.arm[3 * b2 + 1], p2 = V.arm[3 * b2 + 2];
-      const double cm = ce / mass, cm2 = ce2 / mass;
-      // position rows: sum_k alpha_{k-j} alpha_{k-j2} Qp_k ; only the z weight depends on k
-      double s0 = 0.0, sz = 0.0;
-      for (int k = j; k < N; ++k) {
-        const double aa = ((double)(k - j) + zeta) * ((double)(k - j2) + zeta);
-        s0 += aa; sz += aa * V.qz[k];
-      }
-      const double cnt = (double)(N - j);
-      // angular rows: dt^2 c c2 [r]x' diag(ql) [r2]x summed over the N-j row blocks below;
-      // [r]x = [[0,-rz,ry],[rz,0,-rx],[-ry,rx,0]]
+    {
+      const double dt2 = dt * dt, dt4 = dt2 * dt2;
       const double q0 = cfg.w[6], q1 = cfg.w[7], q2 = cfg.w[8];
-      const double sc = cnt * dt2 * ce * ce2;
-      double blk[3][3];
-      blk[0][0] = sc * (r2 * q1 * p2 + r1 * q2 * p1);
-      blk[0][1] = sc * (-r1 * q2 * p0);
-      blk[0][2] = sc * (-r2 * q1 * p0);
-      blk[1][0] = sc * (-r0 * q2 * p1);
-      blk[1][1] = sc * (r2 * q0 * p2 + r0 * q2 * p0);
-      blk[1][2] = sc * (-r2 * q0 * p1);
-      blk[2][0] = sc * (-r0 * q1 * p2);
-      blk[2][1] = sc * (-r1 * q0 * p2);
-      blk[2][2] = sc * (r1 * q0 * p1 + r0 * q1 * p0);
-      const double pos[3] = {cfg.w[0] * s0, cfg.w[1] * s0, sz};
-      for (int aa = 0; aa < 3; ++aa) blk[aa][aa] += cm * cm2 * (dt4 * pos[aa] + cnt * dt2 * cfg.w[3 + aa]);
-      // K = W_f + D' W_r D (CentroidalMPC.cpp:223-231): same leg, same component
-      if (i == i2) {
-        for (int aa = 0; aa < 3; ++aa) {
-          const double wr = cfg.w[9 + 6 * L + 3 * i + aa];
-          if (j == j2) {
-            const double nn = (j > 0 ? 1.0 : 0.0) + (j + 1 < N ? 1.0 : 0.0);
-            blk[aa][aa] += cfg.w[9 + 3 * L + 3 * i + aa] + nn * wr;
-          } else if (j == j2 + 1) {
-            blk[aa][aa] -= wr;
+      const double im2 = 1.0 / (mass * mass);
+      auto Rof = [&](int g) { return (g >> 2) * kTS + ((g & 3) << 2); };
+      auto Cof = [&](int g) { const int tj = g >> 2; return (tj * nblk - ((tj * (tj + 1)) >> 1)) * kTS + (g & 3); };
+      auto do_pair = [&](int b, int b2, auto far_tag) {
+        constexpr bool FAR = decltype(far_tag)::value;
+        const int j = V.blk_j[b], i = V.blk_i[b], j2 = V.blk_j[b2], i2 = V.blk_i[b2];
+        const double ce = V.ce[b], ce2 = V.ce[b2];
+        const double r0 = V.arm[3 * b], r1 = V.arm[3 * b + 1], r2 = V.arm[3 * b + 2];
+        const double p0 = V.arm[3 * b2], p1 = V.arm[3 * b2 + 1], p2 = V.arm[3 * b2 + 2];
+        const double cnt = (double)(N - j), dd = (double)(j - j2);
+        const double s1 = 0.5 * cnt * (cnt - 1.0) + zeta * cnt;
+        const double s2 = (cnt - 1.0) * cnt * (2.0 * cnt - 1.0) * (1.0 / 6.0) + zeta * cnt * (cnt - 1.0) + zeta * zeta * cnt;
+        const double s0 = s2 + dd * s1, sz = z2[j] + dd * z1[j];
+        const double cc = ce * ce2;
+        const double sc = cnt * dt2 * cc, cmm = cc * im2;
+        double blk[3][3];
+        blk[0][0] = sc * (r2 * q1 * p2 + r1 * q2 * p1) + cmm * (dt4 * cfg.w[0] * s0 + cnt * dt2 * cfg.w[3]);
+        blk[0][1] = sc * (-r1 * q2 * p0);
+        blk[0][2] = sc * (-r2 * q1 * p0);
+        blk[1][0] = sc * (-r0 * q2 * p1);
+        blk[1][1] = sc * (r2 * q0 * p2 + r0 * q2 * p0) + cmm * (dt4 * cfg.w[1] * s0 + cnt * dt2 * cfg.w[4]);
+        blk[1][2] = sc * (-r2 * q0 * p1);
+        blk[2][0] = sc * (-r0 * q1 * p2);
+        blk[2][1] = sc * (-r1 * q0 * p2);
+        blk[2][2] = sc * (r1 * q0 * p1 + r0 * q1 * p0) + cmm * (dt4 * sz + cnt * dt2 * cfg.w[5]);
+        if (i == i2 && j - j2 <= 1) {
+          const double nn = (j > 0 ? 1.0 : 0.0) + (j + 1 < N ? 1.0 : 0.0);
+#pragma unroll
+          for (int aa = 0; aa < 3; ++aa) {
+            const double wr = cfg.w[9 + 6 * L + 3 * i + aa];
+            blk[aa][aa] += (j == j2) ? cfg.w[9 + 3 * L + 3 * i + aa] + nn * wr : -wr;
           }
         }
+        const int g0 = 3 * b, h0 = 3 * b2;
+        if constexpr (FAR) {
+          int R[3], C[3];
+#pragma unroll
+          for (int aa = 0; aa < 3; ++aa) { R[aa] = Rof(g0 + aa); C[aa] = Cof(h0 + aa); }
+#pragma unroll
+          for (int aa = 0; aa < 3; ++aa)
+#pragma unroll
+            for (int bb = 0; bb < 3; ++bb) Hb[R[aa] + C[bb]] = 2.0 * blk[aa][bb];
+        } else {
+#pragma unroll
+          for (int aa = 0; aa < 3; ++aa)
+#pragma unroll
+            for (int bb = 0; bb < 3; ++bb) {
+              const int gi = g0 + aa, gj = h0 + bb;
+              const double v = 2.0 * blk[aa][bb];
+              if ((gi >> 2) >= (gj >> 2)) Hb[Rof(gi) + Cof(gj)] = v;
+              if (b != b2 && (gi >> 2) == (gj >> 2)) Hb[Rof(gj) + Cof(gi)] = v;
+            }
+        }
+      };
+      const int nfar = nb >= 3 ? ((nb - 1) * (nb - 2)) >> 1 : 0;
+      for (int idx = gtid; idx < nfar; idx += GT) {
+        int a = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
+        while (((a + 1) * (a + 2)) >> 1 <= idx) ++a;
+        while ((a * (a + 1)) >> 1 > idx) --a;
+        do_pair(a + 2, idx - ((a * (a + 1)) >> 1), std::true_type{});
       }
-      for (int aa = 0; aa < 3; ++aa)
-        for (int bb = 0; bb < 3; ++bb) {
-          const int gi = 3 * b + aa, gj = 3 * b2 + bb;
-          const double v = 2.0 * blk[aa][bb];
-          if (b != b2) {
-            Hb[midx(gi, gj, nblk)] = v;                              // gi > gj always here
-            if ((gi >> 2) == (gj >> 2)) Hb[midx(gj, gi, nblk)] = v;  // same diagonal tile: mirror
-          } else if ((gi >> 2) >= (gj >> 2)) {
-            // diagonal 3x3 block: all 9 (aa,bb) are visited, so both triangles of a
-            // diagonal tile get written; a straddling entry lands in the lower tile only
-            Hb[midx(gi, gj, nblk)] = v;
-          }
-        }
+      for (int idx = gtid; idx < 2 * nb - 1; idx += GT) {
+        const int b = (idx + 1) >> 1;
+        do_pair(b, b - (idx & 1), std::false_type{});
+      }
+      // padding rows (n .. n4-1): identity
+      for (int e = gtid; e < (n4 - n) * n4; e += GT) {
+        const int gi = n + e / n4, gj = e % n4;
+        if ((gi >> 2) >= (gj >> 2)) Hb[Rof(gi) + Cof(gj)] = gi == gj ? 1.0 : 0.0;
+        if ((gi >> 2) == (gj >> 2) && gj < n) Hb[Rof(gj) + Cof(gi)] = 0.0;
+      }
     }
-    if (gtid < n4 - n) Hb[midx(n + gtid, n + gtid, nblk)] = 1.0;  // padding rows: identity
     // ---- g = 2 Bqp' L (Aqp x0 + dqp - Xref) - 2 W_f Uref, one thread per block (adjoint sum)
     for (int b = gtid; b < nb; b += GT) {
       const int j = V.blk_j[b], i = V.blk_i[b];

@@ -18,7 +18,9 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solv
   G.gtid = threadIdx.x % GT;
   G.gid = threadIdx.x / GT;
   const int gtid = G.gtid;
-  double* base = smem + (size_t)G.gid * P.total;
+  double* c_z1 = smem;      // CTA-shared z-weighted sums for the build (fill_z_tables)
+  double* c_z2 = smem + N;
+  double* base = smem + P.cta + (size_t)G.gid * P.total;
   G.red = base + P.red;
   double* s_exch = base + P.exch;
   double* s_ce = base + P.ce;
@@ -55,6 +57,8 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solv
 
   const double mass = cfg.mass;
   const int count = args.count ? *args.count : args.count_imm;
+  if ((int)threadIdx.x < N) fill_z_tables(cfg, c_z1, c_z2, threadIdx.x);
+  __syncthreads();
 
   while (true) {
     int slot = 0;
@@ -87,7 +91,7 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solv
 
     double* Hb;
     if constexpr (MS) Hb = Mm; else Hb = Hm;
-    build_qp<W>(G, cfg, V, Hb, nb);
+    build_qp<W>(G, cfg, V, Hb, nb, c_z1, c_z2);
     if constexpr (MS) store_mat<W>(G, Hm, Mm, matd);
 
     if (MODE == 1) {
