@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
   const double mass = cfg.mass, dt = cfg.dt;
   const double zeta = cfg.zoh ? 0.5 : 0.0;
   const int count = args.count ? *args.count : args.count_imm;
+  if (count <= 0) return;  // empty list (uniform over the grid): nothing to set up
 
   // forces leave in the reference's per-leg order [L][N][3] (CentroidalMPC.cpp:270): output t reads
   // component q of free block blk_of[j L + i]; the map is the same for every instance

@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
   const double zeta = cfg.zoh ? 0.5 : 0.0;
   const double dpz = zeta * dt * dt * (-kGrav), dvz = dt * (-kGrav);  // affine term d = [dpz e_z; dvz e_z; 0]
   const int count = args.count ? *args.count : args.count_imm;
+  if (count <= 0) return;  // empty list (uniform over the grid): nothing to set up
   for (int e = threadIdx.x; e <= N; e += blockDim.x) {
     const double om = (cfg.w[2] * 0.5) * exp(-(double)e) + cfg.w[2] * 0.5;  // CentroidalMPC.cpp:205
     c_qz[e] = om * om;

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solv
 
   const double mass = cfg.mass;
   const int count = args.count ? *args.count : args.count_imm;
+  if (count <= 0) return;  // empty list (uniform over the grid): nothing to set up
   if ((int)threadIdx.x < N) fill_z_tables(cfg, c_z1, c_z2, threadIdx.x);
   __syncthreads();
 
