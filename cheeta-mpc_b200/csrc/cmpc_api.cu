@@ -546,7 +546,7 @@ int collect_stats(cmpc_handle* h, int B, const int32_t* d_status, const int32_t*
 
 extern "C" {
 
-const char* cmpc_version(void) { return "cmpc_b200 0.1 (sm_100a)"; }
+const char* cmpc_version(void) { return "cmpc_b200 0.2 (sm_100a)"; }
 
 int cmpc_config_init(cmpc_config* cfg, double mass, int num_legs, int horizon, double dt, const double* weights,
                      const double* mu) {
