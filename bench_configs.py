@@ -75,6 +75,13 @@ def main():
     ms, s, its, kk = timed_device(pkg, cfg, st, ds, di, steps=5, warmup=2)
     out.append(dict(config="3: N=30 mixed gaits, batch 8192, Riccati presolve", batch=B, p50_ms=ms, solves_per_s=B / ms * 1e3,
                     mean_iters=float(its.mean()), status=np.bincount(s, minlength=5).tolist(), max_kkt=float(kk.max())))
+    # horizon 30 with active rows: Riccati presolve defers, dense interior-point kernel (n = 180..360) solves
+    cfg = hard_config(wl, 30, 0.3)
+    B = 512
+    st, ds, di = wl.make_batch(cfg, B, gaits=wl.GAITS)
+    ms, s, its, kk = timed_device(pkg, cfg, st, ds, di, steps=3, warmup=1)
+    out.append(dict(config="hard N=30: tracking-heavy weights, mu=0.3, mixed gaits", batch=B, p50_ms=ms, solves_per_s=B / ms * 1e3,
+                    mean_iters=float(its.mean()), status=np.bincount(s, minlength=5).tolist(), max_kkt=float(kk[s <= 1].max())))
     # config 5: closed loop
     cfg = wl.default_config(10)
     B, ticks = 4096, 1000
