@@ -100,6 +100,7 @@ def load_library():
     lib.cmpc_solve_batch_device.argtypes = [vp, C.c_int] + [vp] * 9 + [C.POINTER(CmpcStats)]
     lib.cmpc_build_batch.argtypes = [vp, C.c_int] + [vp] * 6
     lib.cmpc_rollout.argtypes = [vp, C.c_int, C.c_int, C.c_int] + [vp] * 6 + [C.POINTER(CmpcStats)]
+    lib.cmpc_stage_step_batch.argtypes = [vp, C.c_int, C.c_int] + [vp] * 8
     lib.cmpc_foot_plan_batch.argtypes = [vp, C.c_int, vp, vp, vp]
     lib.cmpc_solve_batch_sqp.argtypes = [vp, C.c_int, C.c_int] + [vp] * 6
     lib.cmpc_fill_contact_tables.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp]
@@ -225,6 +226,18 @@ class CentroidalMPC:
                                           _ptr(flog), _ptr(iters), _ptr(stor), C.byref(stats)))
         return dict(state=st, des_state=ds, des_inputs=di, force_log=flog, iters_sum=iters, status_or=stor,
                     stats=stats.as_dict())
+
+    def StageStep(self, state, des_state, des_inputs, hess, rhs, mode=1):
+        """Stage-wise linear algebra alone (cmpc_stage_step_batch). Returns d_fused, d_resolve, grad [B, N*L*3]."""
+        st = _f64(state); B = st.shape[0]
+        st = _f64(st, (B, self.n_state)); ds = _f64(des_state, (B, self.n_des_state)); di = _f64(des_inputs, (B, self.n_des_inputs))
+        hs = _f64(hess, (B, 6 * self.L * self.N)); r = _f64(rhs, (B, self.n_forces))
+        if self.max_batch == 0:
+            self.SetupMPC(B)
+        o = [np.zeros((B, self.n_forces)) for _ in range(3)]
+        self._check(self.lib.cmpc_stage_step_batch(self.h, B, int(mode), _ptr(st), _ptr(ds), _ptr(di), _ptr(hs), _ptr(r),
+                                                   _ptr(o[0]), _ptr(o[1]), _ptr(o[2])))
+        return o
 
     def FootPlan(self, state, des_inputs):
         """Optimal foot positions [B, L, N+1, 3] (the foot_pos outputs of the reference controller)."""

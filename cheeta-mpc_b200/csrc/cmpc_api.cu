@@ -54,6 +54,11 @@ struct cmpc_handle {
   int ric_groups = 0;
   size_t ric_smem_bytes = 0;
   double* d_ric_scratch = nullptr;
+  // stage-wise interior-point kernel (cmpc_ripm.cu): takes the deferred instances of the classes ipm_kind() gives it
+  bool rip_used = false;
+  int rip_groups = 0, rip_mode = 0;  // rip_mode (CMPC_IPM_BACKEND): 0 follow qp_backend, 1 dense everywhere, 2 stage-wise everywhere
+  size_t rip_smem_bytes = 0, rip_slab = 0;
+  double* d_rip_scratch = nullptr;
   int32_t* d_ready = nullptr;        // chunks of inputs landed (written by the copy stream, polled by the router kernel)
   int32_t* h_ready_vals = nullptr;   // pinned {1, 2, ...}: the values the copy stream writes into d_ready
   int32_t* h_error_dev = nullptr;    // device alias of h_error
@@ -415,6 +420,28 @@ int launch_riccati(cmpc_handle* h, SolveArgs a) {
   return CMPC_OK;
 }
 
+int launch_ripm(cmpc_handle* h, SolveArgs a) {
+  a.scratch = h->d_rip_scratch;
+  a.scratch_per_group = h->rip_slab;
+  a.nbmax = h->cfg.horizon * h->cfg.num_legs; a.n4max = 0; a.m_in_smem = 1; a.groups = h->rip_groups;
+  const cudaError_t e = launch_ripm_kernel(h->num_sms, 32 * h->rip_groups, h->rip_smem_bytes, h->stream, h->dev, a);
+  if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, std::string("stage-wise interior-point launch: ") + cudaGetErrorString(e));
+  return CMPC_OK;
+}
+
+// which interior-point kernel takes the (deferred) instances of size class c: 0 condensed dense (cmpc_solve.cu),
+// 1 stage-wise Riccati (cmpc_ripm.cu).  Automatic: dense for up to 20 free leg-steps (n <= 60, one warp, the
+// condensed factor is as cheap as the sweep), stage-wise above (stand at horizon 10, everything at horizon 30).
+// A warm-started call (closed loop) keeps the dense kernel, whose polish takes the previous active set.
+int ipm_kind(const cmpc_handle* h, int c, bool warm) {
+  if (!h->rip_used || warm || !h->cfg.polish) return 0;
+  if (h->rip_mode == 1) return 0;
+  if (h->rip_mode == 2) return 1;
+  if (h->cfg.qp_backend == 1) return 0;
+  if (h->cfg.qp_backend == 2) return 1;
+  return c >= 1 ? 1 : 0;
+}
+
 // which presolve kernel settles size class c: 0 none, 1 dense (cmpc_presolve.cu), 2 Riccati (cmpc_riccati.cu)
 int presolve_kind(const cmpc_handle* h, int c) {
   if (!(h->cfg.presolve && h->cfg.polish)) return 0;
@@ -470,7 +497,7 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
       a.fail_perm = nullptr; a.fail_count = nullptr;
       a.route = 0; a.ready = nullptr;
     }
-    int rc = launch_class<0>(h, h->cls[c], a);
+    int rc = ipm_kind(h, c, a.warm_active != nullptr) ? launch_ripm(h, a) : launch_class<0>(h, h->cls[c], a);
     if (rc) return rc;
     ++launches;
   }
@@ -664,6 +691,20 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
         CUDA_TRY(h, cudaMalloc(&h->d_ric_scratch, (size_t)rp.slab * 8 * (size_t)h->num_sms * h->ric_groups));
         CUDA_TRY(h, set_riccati_kernel_smem(h->ric_smem_bytes));
         h->ric_used = true;
+      }
+    }
+    {
+      int gd = 0, cd = 0, sd = 0;
+      ripm_sizes(N, L, &gd, &cd, &sd);
+      h->rip_groups = (int)std::min<size_t>(12, (kMaxSmem / 8 - cd) / (size_t)gd);
+      if (const char* m = getenv("CMPC_RIPM_GROUPS")) h->rip_groups = std::max(1, std::min(h->rip_groups, atoi(m)));
+      if (const char* m = getenv("CMPC_IPM_BACKEND")) h->rip_mode = std::max(0, std::min(2, atoi(m)));
+      if (h->rip_groups >= 1) {
+        h->rip_smem_bytes = ((size_t)gd * h->rip_groups + cd) * 8;
+        h->rip_slab = ((size_t)sd + 1) & ~(size_t)1;
+        CUDA_TRY(h, cudaMalloc(&h->d_rip_scratch, h->rip_slab * 8 * (size_t)h->num_sms * h->rip_groups));
+        CUDA_TRY(h, set_ripm_kernel_smem(h->rip_smem_bytes));
+        h->rip_used = true;
       }
     }
     if (p1 && (rc = set_pre_smem_attr(h, 1, p1))) return rc;
@@ -918,6 +959,42 @@ int cmpc_build_batch(cmpc_handle* h, int B, const double* state, const double* d
   return CMPC_OK;
 }
 
+int cmpc_stage_step_batch(cmpc_handle* h, int B, int mode, const double* state, const double* des_state, const double* des_inputs,
+                          const double* hess, const double* rhs, double* d_fused, double* d_resolve, double* grad) {
+  if (!h || !h->ready) return fail(h, CMPC_ERR_STATE, "cmpc_stage_step_batch: call cmpc_setup first");
+  if (B < 0 || B > h->max_batch) return fail(h, CMPC_ERR_STATE, "batch exceeds max_batch given to cmpc_setup");
+  if (!h->rip_used) return fail(h, CMPC_ERR_STATE, "stage-wise kernel not planned");
+  if ((mode != 1 && mode != 2) || !state || !des_state || !des_inputs || !hess || !rhs || !d_fused || !d_resolve || !grad)
+    return fail(h, CMPC_ERR_ARG, "cmpc_stage_step_batch: bad arguments");
+  if (B == 0) return CMPC_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const int N = h->cfg.horizon, L = h->cfg.num_legs;
+  const size_t ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = (size_t)L * (4 * N + 3), nf = (size_t)3 * L * N, nh = (size_t)6 * L * N;
+  cudaStream_t s = h->stream;
+  double* tmp = nullptr;  // diagnostic path: a temporary buffer is fine here
+  CUDA_TRY(h, cudaMalloc(&tmp, (size_t)B * (nh + 4 * nf) * 8));
+  double *dh = tmp, *dr = dh + (size_t)B * nh, *o1 = dr + (size_t)B * nf, *o2 = o1 + (size_t)B * nf, *o3 = o2 + (size_t)B * nf;
+  cudaMemcpyAsync(h->d_state, state, B * ns * 8, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(h->d_ds, des_state, B * nds * 8, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(h->d_di, des_inputs, B * ndi * 8, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(dh, hess, (size_t)B * nh * 8, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(dr, rhs, (size_t)B * nf * 8, cudaMemcpyHostToDevice, s);
+  SolveArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.state = h->d_state; a.des_state = h->d_ds; a.des_inputs = h->d_di;
+  a.scratch = h->d_rip_scratch; a.scratch_per_group = h->rip_slab; a.groups = h->rip_groups;
+  cudaError_t e = launch_ripm_probe(h->num_sms, 32 * h->rip_groups, h->rip_smem_bytes, s, h->dev, a, dh, dr, mode, o1, o2, o3, B);
+  if (e == cudaSuccess) {
+    cudaMemcpyAsync(d_fused, o1, (size_t)B * nf * 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(d_resolve, o2, (size_t)B * nf * 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(grad, o3, (size_t)B * nf * 8, cudaMemcpyDeviceToHost, s);
+    e = cudaStreamSynchronize(s);
+  }
+  cudaFree(tmp);
+  if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, std::string("cmpc_stage_step_batch: ") + cudaGetErrorString(e));
+  return CMPC_OK;
+}
+
 int cmpc_rollout(cmpc_handle* h, int B, int ticks, int warm_start, double* state, double* des_state,
                  double* des_inputs, double* force_log, int32_t* iters_sum, int32_t* status_or, cmpc_stats* stats) {
   if (!h || !h->ready) return fail(h, CMPC_ERR_STATE, "cmpc_rollout: call cmpc_setup first");
@@ -1119,7 +1196,7 @@ void cmpc_destroy(cmpc_handle* h) {
   cudaFree(h->d_state); cudaFree(h->d_ds); cudaFree(h->d_di); cudaFree(h->d_forces); cudaFree(h->d_kkt);
   cudaFree(h->d_lam); cudaFree(h->d_hip); cudaFree(h->d_counts); cudaFree(h->d_perm); cudaFree(h->exp_plan.d_scratch);
   for (auto& c : h->cls) { cudaFree(c.d_scratch); cudaFree(c.d_pre_scratch); }
-  cudaFree(h->d_ric_scratch);
+  cudaFree(h->d_ric_scratch); cudaFree(h->d_rip_scratch);
   cudaFree(h->d_ready); cudaFreeHost(h->h_ready_vals); cudaFreeHost(h->h_error);
   cudaFree(h->d_status); cudaFree(h->d_iters);
   cudaFree(h->d_iters_sum); cudaFree(h->d_status_or); cudaFree(h->d_active); cudaFree(h->d_stats);

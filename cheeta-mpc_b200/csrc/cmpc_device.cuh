@@ -1026,5 +1026,12 @@ cudaError_t set_presolve_kernel_smem(int W, size_t bytes);
 cudaError_t launch_riccati_kernel(int grid, int block, size_t smem, cudaStream_t stream, const DevConfig& cfg,
                                   const SolveArgs& args);
 cudaError_t set_riccati_kernel_smem(size_t bytes);
+// cmpc_ripm.cu: stage-wise (Riccati) interior-point + polish kernel for the instances the presolve defers, one warp per instance
+cudaError_t launch_ripm_kernel(int grid, int block, size_t smem, cudaStream_t stream, const DevConfig& cfg,
+                               const SolveArgs& args);
+cudaError_t set_ripm_kernel_smem(size_t bytes);
+void ripm_sizes(int N, int L, int* group_doubles, int* cta_doubles, int* slab_doubles);
+cudaError_t launch_ripm_probe(int grid, int block, size_t smem, cudaStream_t stream, const DevConfig& cfg, const SolveArgs& args,
+                              const double* hess, const double* rhs, int mode, double* d_fused, double* d_resolve, double* grad, int B);
 
 }  // namespace cmpc

@@ -171,6 +171,18 @@ int cmpc_solve_batch_sqp(cmpc_handle* h, int B, int sqp_iters, const double* sta
                          const double* des_state, const double* des_inputs, double* forces,
                          int32_t* status, double* defect);
 
+/* Parity entry for the stage-wise (Riccati) linear algebra of the interior-point / polish kernel (SURVEY §8 f3;
+ * stage interface as in ocs2_sqp/hpipm_catkin/src/HpipmInterface.cpp:166-301).  For every instance it solves
+ *     minimise 1/2 d'(H + C' diag(sigma) C) d - rhs' d
+ * mode 1: hess [B][N][L][6] = the entries (xx, yy, zz, zx, zy, unused) of 1/2 F_i' diag(sigma) F_i per leg-step;
+ * mode 2: sigma = 0 and d restricted per leg-step to the range of the symmetric projector given as
+ *         (00, 11, 22, 10, 20, 21) -- the polish's equality-constrained system.
+ * d_fused: right-hand side carried by the factor sweep; d_resolve: the same right-hand side through the
+ * stored factors; grad = H rhs + g (rhs taken as a force vector).  All force vectors [B][N][L][3]. Host buffers. */
+int cmpc_stage_step_batch(cmpc_handle* h, int B, int mode, const double* state, const double* des_state,
+                          const double* des_inputs, const double* hess, const double* rhs, double* d_fused,
+                          double* d_resolve, double* grad);
+
 /* Gait template = ModeSequenceTemplate of the vendored OCS2 stack (ocs2_legged_robot/
  * config/command/gait.info; src/gait/ModeSequenceTemplate.cpp:74-87 converts it to a Gait).
  * modes[] are ModeNumber values 0..15 with bits {LF = 8, RF = 4, LH = 2, RH = 1}

@@ -480,3 +480,67 @@ def stage_gradient(cfg, state, des_state, des_inputs, U):
         mask = np.zeros(nf); mask[S["free"][k]] = 1.0
         grad[k] = gk * mask
     return grad.reshape(-1)
+
+
+# ------------------------------------------------------------------ stage-wise interior-point step
+def stage_newton_step(cfg, state, des_state, des_inputs, sigma, rhs, Zmaps=None):
+    """The linear system of one interior-point iteration (or of one active-set polish pass) in the
+    stage-wise form the kernel cmpc_ripm.cu uses, restated densely per stage:
+
+        minimise  1/2 d'(H + C' diag(sigma) C) d - rhs' d     over  d_k = Z_k t_k,
+
+    H the condensed Hessian, sigma [N, L, 5] the barrier weights z_l/s_l + z_u/s_u of the friction
+    rows (CentroidalMPC.cpp:186-190), Z_k an nf x m_k basis per stage (default: the unit vectors of the
+    stance-leg components; the polish passes the per-leg null-space bases of its working set).
+    Homogeneous LQR over z_k = [xi_k; d_{k-1}] (deviation state, xi_0 = 0):  backward sweep
+    G = Bbar' P Bbar + Z'(Wf + rate Wr + 1/2 C' S C) Z,  M = Bbar' P Abar - rate Z' Wr [0 I],
+    Y = L^-1 M, y0 = L^-1 (Bbar' p - Z' rhs_k / 2),  P <- blkdiag(Q_k, Wr) + Abar' P Abar - Y'Y,
+    p <- Abar' p - Y' y0;  forward  t_k = -L^-T (Y z_k + y0).  Returns d [N * nf]."""
+    S = stage_data(cfg, state, des_state, des_inputs)
+    N, L = S["N"], S["L"]
+    nx, nf = 9, 3 * L
+    nz = nx + nf
+    A, Wf, Wr = S["A"], S["Wf"], S["Wr"]
+    mu = np.asarray(cfg["mu"], float)
+    sigma = np.asarray(sigma, float).reshape(N, L, 5)
+    rhs = np.asarray(rhs, float).reshape(N, nf)
+    Abar = np.zeros((nz, nz)); Abar[:nx, :nx] = A
+    P = np.zeros((nz, nz)); p = np.zeros(nz)
+    P[:nx, :nx] = S["Q"][N - 1]
+    fac = [None] * N
+    for k in range(N - 1, -1, -1):
+        if Zmaps is None:
+            fr = S["free"][k]
+            Z = np.zeros((nf, len(fr))); Z[fr, np.arange(len(fr))] = 1.0
+        else:
+            Z = np.asarray(Zmaps[k], float).reshape(nf, -1)
+        rate = 1.0 if k >= 1 else 0.0
+        Rk = Wf + rate * Wr
+        for i in range(L):
+            Fi = np.array([[-1, 0, mu[i]], [1, 0, mu[i]], [0, -1, mu[i]], [0, 1, mu[i]], [0, 0, 1.0]])
+            Rk[3 * i:3 * i + 3, 3 * i:3 * i + 3] += 0.5 * Fi.T @ (sigma[k, i][:, None] * Fi)
+        Bbar = np.vstack([S["Bf"][k] @ Z, Z])
+        G = Bbar.T @ P @ Bbar + Z.T @ Rk @ Z
+        M = Bbar.T @ P @ Abar
+        M[:, nx:] -= rate * (Z.T @ Wr)
+        m0 = Bbar.T @ p - 0.5 * Z.T @ rhs[k]
+        if Z.shape[1]:
+            Lc = np.linalg.cholesky(G)
+            Y = np.linalg.solve(Lc, M); y0 = np.linalg.solve(Lc, m0)
+        else:
+            Lc = np.zeros((0, 0)); Y = np.zeros((0, nz)); y0 = np.zeros(0)
+        fac[k] = (Lc, Y, y0, Z)
+        if k >= 1:
+            Pn = Abar.T @ P @ Abar - Y.T @ Y
+            Pn[:nx, :nx] += S["Q"][k - 1]
+            Pn[nx:, nx:] += Wr
+            p = Abar.T @ p - Y.T @ y0
+            P = 0.5 * (Pn + Pn.T)
+    z = np.zeros(nz)
+    d = np.zeros((N, nf))
+    for k in range(N):
+        Lc, Y, y0, Z = fac[k]
+        t = -np.linalg.solve(Lc.T, Y @ z + y0) if Z.shape[1] else np.zeros(0)
+        d[k] = Z @ t
+        z = np.concatenate([A @ z[:nx] + S["Bf"][k] @ d[k], d[k]])
+    return d.reshape(-1)

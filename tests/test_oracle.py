@@ -240,3 +240,42 @@ def test_stage_wise_riccati_equals_condensed_solve(pkg, wl, N, disc):
         U = rng.normal(size=Ur.shape) * ~qp["pinned"]
         gu = nm.stage_gradient(cfg, st[b], ds[b], di[b], U)
         assert np.abs(gu - (qp["H"] @ U + qp["g"]) * ~qp["pinned"]).max() <= 1e-11 * (1 + np.abs(gu).max())
+
+
+@pytest.mark.parametrize("N,disc", [(6, 0), (10, 1)])
+def test_stage_newton_step_equals_dense_system(wl, N, disc):
+    """The stage-wise (Riccati) form of one interior-point step / one polish pass (numpy_mirror.stage_newton_step,
+    the mirror of cmpc_ripm.cu) against the dense solves (H + C'SC)^-1 rhs and Z (Z'HZ)^-1 Z' rhs."""
+    import numpy_mirror as nm
+    from conftest import hard_config
+    cfg = hard_config(wl, N, 0.3, disc_mode=disc)
+    st, ds, di = wl.make_batch(cfg, 3, gaits=("gallop", "stand", "trot"))
+    rng = np.random.default_rng(7)
+    L, nf = 4, 12
+    for b in range(3):
+        qp = nm.build_qp(cfg, st[b], ds[b], di[b])
+        C, lb, ub, tags = nm.constraints(cfg, qp["contact"])
+        sv = rng.uniform(0.01, 100, len(tags))
+        sig = np.zeros((N, L, 5))
+        for t, (j, i, r) in enumerate(tags):
+            sig[j, i, r] = sv[t]
+        free = ~qp["pinned"]
+        rhs = rng.normal(size=N * nf) * free
+        dref = np.zeros(N * nf)
+        dref[free] = np.linalg.solve((qp["H"] + C.T @ (sv[:, None] * C))[np.ix_(free, free)], rhs[free])
+        d = nm.stage_newton_step(cfg, st[b], ds[b], di[b], sig, rhs)
+        assert np.abs(d - dref).max() <= 1e-12 * np.abs(dref).max()
+        Zm, cols = [], []
+        for k in range(N):
+            Zk = []
+            for i in range(L):
+                if qp["contact"][i, k] > 0:
+                    Q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+                    for c in range(rng.integers(0, 4)):
+                        v = np.zeros(nf); v[3 * i:3 * i + 3] = Q[:, c]; Zk.append(v)
+                        full = np.zeros(N * nf); full[nf * k:nf * k + nf] = v; cols.append(full)
+            Zm.append(np.array(Zk).T.reshape(nf, -1) if Zk else np.zeros((nf, 0)))
+        Zf = np.array(cols).T
+        dref2 = Zf @ np.linalg.solve(Zf.T @ qp["H"] @ Zf, Zf.T @ rhs)
+        d2 = nm.stage_newton_step(cfg, st[b], ds[b], di[b], np.zeros((N, L, 5)), rhs, Zm)
+        assert np.abs(d2 - dref2).max() <= 1e-11 * np.abs(dref2).max()
