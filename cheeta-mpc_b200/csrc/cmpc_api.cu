@@ -430,8 +430,8 @@ int launch_ripm(cmpc_handle* h, SolveArgs a) {
 }
 
 // which interior-point kernel takes the (deferred) instances of size class c: 0 condensed dense (cmpc_solve.cu),
-// 1 stage-wise Riccati (cmpc_ripm.cu).  Automatic: dense for up to 20 free leg-steps (n <= 60, one warp, the
-// condensed factor is as cheap as the sweep), stage-wise above (stand at horizon 10, everything at horizon 30).
+// 1 stage-wise Riccati (cmpc_ripm.cu).  Automatic: dense for up to 42 free leg-steps (n <= 126: the one- and four-warp
+// kernels, whose per-instance latency is lower), stage-wise above (the eight-warp classes: everything at horizon 30).
 // A warm-started call (closed loop) keeps the dense kernel, whose polish takes the previous active set.
 int ipm_kind(const cmpc_handle* h, int c, bool warm) {
   if (!h->rip_used || warm || !h->cfg.polish) return 0;
@@ -439,7 +439,7 @@ int ipm_kind(const cmpc_handle* h, int c, bool warm) {
   if (h->rip_mode == 2) return 1;
   if (h->cfg.qp_backend == 1) return 0;
   if (h->cfg.qp_backend == 2) return 1;
-  return c >= 1 ? 1 : 0;
+  return c >= 2 ? 1 : 0;
 }
 
 // which presolve kernel settles size class c: 0 none, 1 dense (cmpc_presolve.cu), 2 Riccati (cmpc_riccati.cu)

@@ -3,7 +3,8 @@
    python tools/ncu_summary.py report.ncu-rep [B] > profiles/xxx.txt"""
 import collections, csv, io, subprocess, sys
 rep = sys.argv[1]; B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+skip = ["--launch-skip", sys.argv[3], "--launch-count", "1"] if len(sys.argv) > 3 else []  # which launch of the report
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + skip, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 h, v = rows[0], rows[2]
 print("kernel:", v[h.index("Kernel Name")] if "Kernel Name" in h else "?")
@@ -19,7 +20,7 @@ want += [k for k in h if k.startswith("smsp__average_warps_issue_stalled") and k
 for w in want:
     if w in h:
         print(f"{w} = {v[h.index(w)]} {rows[1][h.index(w)]}")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + skip, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hdr = rows[2]; samp = hdr.index('Warp Stall Sampling (All Samples)'); inst = hdr.index('Instructions Executed')
 cur = None; lines = collections.defaultdict(lambda: [0, 0, ''])
