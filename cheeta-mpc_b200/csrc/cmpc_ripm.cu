@@ -50,21 +50,22 @@ struct Lay {
   int st;    // state (9 + 3L) | des_state (9 (N + 1))
   int tab;   // [N][4][4]: lever arm (3), contact (1) per leg slot
   int fz;    // [N] desired fz of the stance legs (:331-333)
-  int u, du, dua, rd;  // force-space vectors, full layout [N][L][3]
-  int Rs;    // 6 per leg-step: 1/2 C'SC entries (interior point) or the projector (polish)
+  int u, du, rd;  // force-space vectors, full layout [N][L][3] (the copy of the affine direction lives in the slab)
+  int rsb;   // [2][24]: input-Hessian data of the current / next stage (cp.async from the slab)
   int W, G, Y, Lm;     // stage work area (contiguous); X (9N) aliases it between sweeps
   int m0, ps, zs, us, act, total;
 };
 __host__ __device__ __forceinline__ Lay make_lay(int N, int L, int gb) {
   const int nfN = (3 * L * N + 1) & ~1, nbfull = L * N;
+  (void)nbfull;
   Lay y;
   int o = gb;
   auto take = [&](int cnt) { int r = o; o += (cnt + 1) & ~1; return r; };
   y.st = take(9 + 3 * L + 9 * (N + 1));
   y.tab = take(16 * N);
   y.fz = take(N);
-  y.u = take(nfN); y.du = take(nfN); y.dua = take(nfN); y.rd = take(nfN);
-  y.Rs = take(6 * nbfull);
+  y.u = take(nfN); y.du = take(nfN); y.rd = take(nfN);
+  y.rsb = take(48);
   int work = 2 * kFac;  // W, G, Y, Lm of the factor sweep (804) <= the vector sweeps' double buffer of stage factors
   if (work < 9 * N) work = 9 * N;
   y.W = take(work); y.G = y.W + kNZ * kNF; y.Y = y.G + kNF * kNF; y.Lm = y.Y + kNF * kYS;
@@ -128,11 +129,36 @@ __device__ __forceinline__ unsigned stance_mask(const double* tk, int lane) {
 // Backward sweep: factor the stage systems of  1/2 d'(H + C'SC) d - rhs'd  (mode 1) or of the projected polish
 // system (mode 2); the right-hand side in du rides along (y0 = column 21 of Y).  Factors -> slab.
 // Returns false (uniformly) on a non-positive pivot.
-__device__ __noinline__ bool lqr_factor(int N, int L, int gb, int lane, int mode, double* fac) {
+// Stage factors travel from the slab into a shared-memory double buffer (the stage work area, idle during the vector
+// sweeps) with 16-byte asynchronous copies issued one stage ahead: L2 latency stays off the dependent chain and no
+// registers are spent on staging.
+__device__ __forceinline__ void fac_prefetch(double* buf, const double* fk, int lane) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(buf);
+#pragma unroll
+  for (int c = 0; c < (kFac / 2 + 31) / 32; ++c) {
+    const int e = lane + 32 * c;
+    if (e < kFac / 2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + 16u * e), "l"(fk + 2 * e) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void fac_wait() {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+}
+
+// Rsg (slab): 6 doubles per leg-step -- 1/2 C'SC entries (xx, yy, zz, zx, zy, -) in mode 1, the projector (00, 11, 22, 10, 20, 21) in mode 2.
+__device__ __forceinline__ void rs_prefetch(double* buf, const double* src, int L, int lane) {
+  if (lane < 3 * L) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(buf);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + 16u * lane), "l"(src + 2 * lane) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __noinline__ bool lqr_factor(int N, int L, int gb, int lane, int mode, double* fac, const double* Rsg) {
   const Lay y_ = make_lay(N, L, gb);
   double* const W = smem + y_.W; double* const G = smem + y_.G; double* const Y = smem + y_.Y; double* const Lm = smem + y_.Lm;
   double* const m0 = smem + y_.m0; double* const ps = smem + y_.ps;
-  const double* const du = smem + y_.du; const double* const Rs = smem + y_.Rs;
+  const double* const du = smem + y_.du;
   const double* const hw = smem + kHdrW;
   const double dt = smem[kHdrSc], kp = smem[kHdrSc + 1], kv = smem[kHdrSc + 2];
   const int nf = 3 * L;
@@ -146,11 +172,16 @@ __device__ __noinline__ bool lqr_factor(int N, int L, int gb, int lane, int mode
   }
   double pv = 0.0;
   bool ok = true;
+  __syncwarp();
+  rs_prefetch(smem + y_.rsb + ((N - 1) & 1) * 24, Rsg + (size_t)6 * (N - 1) * L, L, lane);
+  fac_wait();
 #pragma unroll 1
   for (int k = N - 1; k >= 0; --k) {
     const double* tk = smem + y_.tab + 16 * k;
+    const double* Rs = smem + y_.rsb + (k & 1) * 24;  // this stage's block: 6 per leg
     const unsigned mask = stance_mask(tk, lane);
     const double rate = k >= 1 ? 1.0 : 0.0;
+    if (k >= 1) rs_prefetch(smem + y_.rsb + ((k - 1) & 1) * 24, Rsg + (size_t)6 * (k - 1) * L, L, lane);
     // ---- T1 = P Bbar, row `lane`
     if (lane < kNZ) {
 #pragma unroll
@@ -194,7 +225,7 @@ __device__ __noinline__ bool lqr_factor(int N, int L, int gb, int lane, int mode
         if (i2 == i) {
           // input Hessian block of the leg: Wf + rate Wr (+ 1/2 C'SC in mode 1)
           const int cq = c2 - 3 * i;
-          const double* rs = Rs + 6 * (k * L + i);
+          const double* rs = Rs + 6 * i;
           const double dq = hw[9 + c2] + rate * hw[21 + c2] + (mode == 1 ? rs[cq] : 0.0);
           const double zx = mode == 1 ? rs[3] : 0.0, zy = mode == 1 ? rs[4] : 0.0;
           g0 += cq == 0 ? dq : (cq == 2 ? zx : 0.0);
@@ -212,7 +243,7 @@ __device__ __noinline__ bool lqr_factor(int N, int L, int gb, int lane, int mode
         for (int i = 0; i < 4; ++i) {
           if (!((mask >> i) & 1u)) continue;
           double x = G[(3 * i) * kNF + lane], yy = G[(3 * i + 1) * kNF + lane], z = G[(3 * i + 2) * kNF + lane];
-          proj3(Rs + 6 * (k * L + i), x, yy, z);
+          proj3(Rs + 6 * i, x, yy, z);
           G[(3 * i) * kNF + lane] = x; G[(3 * i + 1) * kNF + lane] = yy; G[(3 * i + 2) * kNF + lane] = z;
         }
       }
@@ -223,7 +254,7 @@ __device__ __noinline__ bool lqr_factor(int N, int L, int gb, int lane, int mode
         for (int i = 0; i < 4; ++i) {
           if (!((mask >> i) & 1u)) continue;
           double x = G[lane * kNF + 3 * i], yy = G[lane * kNF + 3 * i + 1], z = G[lane * kNF + 3 * i + 2];
-          const double* pi = Rs + 6 * (k * L + i);
+          const double* pi = Rs + 6 * i;
           proj3(pi, x, yy, z);
           if (i == il) {  // + (I - Pi), row ql
             x += (ql == 0 ? 1.0 : 0.0) - (ql == 0 ? pi[0] : (ql == 1 ? pi[3] : pi[4]));
@@ -261,7 +292,7 @@ __device__ __noinline__ bool lqr_factor(int N, int L, int gb, int lane, int mode
         }
       }
     }
-    if (!ok) break;  // uniform: d is a broadcast value
+    if (!ok) { fac_wait(); break; }  // uniform: d is a broadcast value
     // ---- Y = L^-1 [M | m0], lane = column (column 21 = m0); M = T1(0:9)' Abar - rate [0, Wr]
     double y[kNF];
     {
@@ -280,7 +311,7 @@ __device__ __noinline__ bool lqr_factor(int N, int L, int gb, int lane, int mode
           if (col == kNZ) v = m0[c];
           mf[qa] = v;
         }
-        if (mode == 2) proj3(Rs + 6 * (k * L + ia), mf[0], mf[1], mf[2]);
+        if (mode == 2) proj3(Rs + 6 * ia, mf[0], mf[1], mf[2]);
 #pragma unroll
         for (int qa = 0; qa < 3; ++qa) {
           const int a = 3 * ia + qa;
@@ -344,25 +375,9 @@ __device__ __noinline__ bool lqr_factor(int N, int L, int gb, int lane, int mode
       }
       pv = pn;
     }
+    fac_wait();
   }
   return ok;
-}
-
-// Stage factors travel from the slab into a shared-memory double buffer (the stage work area, idle during the vector
-// sweeps) with 16-byte asynchronous copies issued one stage ahead: L2 latency stays off the dependent chain and no
-// registers are spent on staging.
-__device__ __forceinline__ void fac_prefetch(double* buf, const double* fk, int lane) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(buf);
-#pragma unroll
-  for (int c = 0; c < (kFac / 2 + 31) / 32; ++c) {
-    const int e = lane + 32 * c;
-    if (e < kFac / 2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + 16u * e), "l"(fk + 2 * e) : "memory");
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void fac_wait() {
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncwarp();
 }
 
 // Backward vector sweep for a new right-hand side (du) with the stored factors: y0 of every stage -> slab.
@@ -485,11 +500,11 @@ __device__ __noinline__ void lqr_forward(int N, int L, int gb, int lane, const d
 
 // dst = H src + g on the stance entries (0 elsewhere) by one roll-out and one adjoint sweep over the problem
 // data (CentroidalMPC.cpp:85-92 dynamics with frozen arms, :203-232 cost) -- independent of the factors.
-// X (9N doubles) aliases the stage work area.  src, dst: shared-memory offsets.
-__device__ __noinline__ void stage_gradient(int N, int L, int gb, int lane, int src_off, int dst_off) {
+// X (9N doubles) aliases the stage work area.  src: shared-memory offset; dst: shared or global.
+__device__ __noinline__ void stage_gradient(int N, int L, int gb, int lane, int src_off, double* dst) {
   const Lay y_ = make_lay(N, L, gb);
   double* const X = smem + y_.W; double* const zs = smem + y_.zs; double* const us = smem + y_.us; double* const ps = smem + y_.ps;
-  const double* const src = smem + src_off; double* const dst = smem + dst_off;
+  const double* const src = smem + src_off;
   const double* const st = smem + y_.st; const double* const hw = smem + kHdrW;
   const double dt = smem[kHdrSc], kp = smem[kHdrSc + 1], kv = smem[kHdrSc + 2];
   const int nf = 3 * L, ns = 9 + 3 * L;
@@ -619,8 +634,9 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
   double* const fac = slab;
   double* const g_zl = slab + (size_t)N * kFac;
   double* const g_zu = g_zl + mfull;
-  double* const s_u = smem + y_.u; double* const s_du = smem + y_.du; double* const s_dua = smem + y_.dua; double* const s_rd = smem + y_.rd;
-  double* const s_Rs = smem + y_.Rs;
+  double* const g_dua = g_zu + mfull;                       // copy of the affine direction; the polish's gradients
+  double* const g_Rs = g_dua + ((nfN + 1) & ~1);            // input-Hessian data per leg-step (lqr_factor stages it)
+  double* const s_u = smem + y_.u; double* const s_du = smem + y_.du; double* const s_rd = smem + y_.rd;
   const double* const s_tab = smem + y_.tab;
   uint16_t* const s_act = reinterpret_cast<uint16_t*>(smem + y_.act);
   const double mass = cfg.mass;
@@ -652,9 +668,9 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
     const int m = 5 * nb;
 
     // ---- g (gradient at 0) for the scale gs, strictly feasible start f = (0, 0, fz0), centred duals
-    for (int t = lane; t < nfN; t += 32) { s_dua[t] = 0.0; s_du[t] = 0.0; }
+    for (int t = lane; t < nfN; t += 32) { g_dua[t] = 0.0; s_du[t] = 0.0; }
     __syncwarp();
-    stage_gradient(N, L, gb, lane, y_.dua, y_.rd);
+    stage_gradient(N, L, gb, lane, y_.du, s_rd);
     double gmax = 0.0;
     for (int t = lane; t < nfN; t += 32) gmax = fmax(gmax, fabs(s_rd[t]));
 #pragma unroll 1
@@ -673,7 +689,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
     for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(kFull, gmax, o));
     __syncwarp();
     const double gs = 1.0 + gmax;
-    stage_gradient(N, L, gb, lane, y_.u, y_.rd);  // H u0 + g
+    stage_gradient(N, L, gb, lane, y_.u, s_rd);  // H u0 + g
     double r0max = 0.0;
     for (int t = lane; t < nfN; t += 32) r0max = fmax(r0max, fabs(s_rd[t]));
 #pragma unroll
@@ -699,7 +715,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
     double us = 1.0;
 #pragma unroll 1
     for (it = 0; it <= cfg.max_iter; ++it) {
-      if (!grad_fresh) stage_gradient(N, L, gb, lane, y_.u, y_.rd);
+      if (!grad_fresh) stage_gradient(N, L, gb, lane, y_.u, s_rd);
       grad_fresh = false;
       double rmax = 0.0, umax = 0.0, gap = 0.0;
 #pragma unroll 1
@@ -784,7 +800,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
                 p00 += Z[cc][0] * Z[cc][0]; p11 += Z[cc][1] * Z[cc][1]; p22 += Z[cc][2] * Z[cc][2];
                 p10 += Z[cc][1] * Z[cc][0]; p20 += Z[cc][2] * Z[cc][0]; p21 += Z[cc][2] * Z[cc][1];
               }
-              double* rs = s_Rs + 6 * tb;
+              double* rs = g_Rs + 6 * tb;
               rs[0] = p00; rs[1] = p11; rs[2] = p22; rs[3] = p10; rs[4] = p20; rs[5] = p21;
             }
             s_rd[3 * tb] = f0[0]; s_rd[3 * tb + 1] = f0[1]; s_rd[3 * tb + 2] = f0[2];
@@ -792,14 +808,14 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
           __syncwarp();
           ok_all = __all_sync(kFull, ok_all);
           if (!ok_all) break;
-          stage_gradient(N, L, gb, lane, y_.rd, y_.dua);  // H f0 + g
-          for (int t = lane; t < nfN; t += 32) s_du[t] = -s_dua[t];
+          stage_gradient(N, L, gb, lane, y_.rd, g_dua);  // H f0 + g
+          for (int t = lane; t < nfN; t += 32) s_du[t] = -g_dua[t];
           __syncwarp();
-          if (!lqr_factor(N, L, gb, lane, 2, fac)) break;
+          if (!lqr_factor(N, L, gb, lane, 2, fac, g_Rs)) break;
           lqr_forward(N, L, gb, lane, fac, y_.du);
           for (int t = lane; t < nfN; t += 32) s_du[t] += s_rd[t];  // candidate point up = f0 + Z t
           __syncwarp();
-          stage_gradient(N, L, gb, lane, y_.du, y_.dua);  // H up + g
+          stage_gradient(N, L, gb, lane, y_.du, g_dua);  // H up + g
           // multipliers, verification, correction; when the pass verifies the loop runs once more to commit
           bool good = false;
 #pragma unroll 1
@@ -814,7 +830,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
               const double ubxy = kFricUb * ce, ubz = mass * kGrav * (double)L * ce;
               const unsigned a = s_act[tb];
               double rb[3], y[5], ll[5] = {0, 0, 0, 0, 0}, lu[5] = {0, 0, 0, 0, 0};
-              for (int q = 0; q < 3; ++q) rb[q] = s_dua[3 * tb + q];
+              for (int q = 0; q < 3; ++q) rb[q] = g_dua[3 * tb + q];
               if ((a & 0x3ffu) == 0u) {
                 okm = okm && fmax(fabs(rb[0]), fmax(fabs(rb[1]), fabs(rb[2]))) <= 1e-9 * gs;
               } else {
@@ -854,14 +870,14 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
           if (good) accepted = true;
         }
         if (accepted) {
-          for (int t = lane; t < nfN; t += 32) { s_u[t] = s_du[t]; s_rd[t] = s_dua[t]; }  // rd = H u + g at the KKT point
+          for (int t = lane; t < nfN; t += 32) { s_u[t] = s_du[t]; s_rd[t] = g_dua[t]; }  // rd = H u + g at the KKT point
           __syncwarp();
           status = CMPC_STATUS_OK;
           break;
         }
         __syncwarp();
         // polish not accepted: rd was the f0 scratch -> recompute the dual residual
-        stage_gradient(N, L, gb, lane, y_.u, y_.rd);
+        stage_gradient(N, L, gb, lane, y_.u, s_rd);
 #pragma unroll 1
         for (int tb = lane; tb < nbfull; tb += 32) {
           const int k = tb / L, i = tb - k * L;
@@ -894,21 +910,21 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
           tq[q] = zu - zl;
         }
         const double sx = sg[0] + sg[1], sy = sg[2] + sg[3];
-        double* rs = s_Rs + 6 * tb;
+        double* rs = g_Rs + 6 * tb;
         rs[0] = 0.5 * sx; rs[1] = 0.5 * sy; rs[2] = 0.5 * (mb * mb * (sx + sy) + sg[4]);
         rs[3] = 0.5 * mb * (sg[1] - sg[0]); rs[4] = 0.5 * mb * (sg[3] - sg[2]);
         ctmul5(mb, tq, o);
         for (int q = 0; q < 3; ++q) s_du[3 * tb + q] = -s_rd[3 * tb + q] + o[q];
       }
       __syncwarp();
-      if (!lqr_factor(N, L, gb, lane, 1, fac)) { numerical = true; break; }
+      if (!lqr_factor(N, L, gb, lane, 1, fac, g_Rs)) { numerical = true; break; }
 
       double tmax = 0.0, sigma = 0.0;
 #pragma unroll 1
       for (int phase = 0; phase < 2; ++phase) {
         // phase 0: affine predictor (its right-hand side rode along the factor sweep); phase 1: centred corrector (Mehrotra)
         if (phase) {
-          for (int t = lane; t < nfN; t += 32) s_dua[t] = s_du[t];
+          for (int t = lane; t < nfN; t += 32) g_dua[t] = s_du[t];
           __syncwarp();
 #pragma unroll 1
           for (int tb = lane; tb < nbfull; tb += 32) {
@@ -919,7 +935,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
             const double ubxy = kFricUb * ce, ubz = mass * kGrav * (double)L * ce;
             double tq[5], o[3], ys[5], ya[5];
             cmul5(mub, s_u + 3 * tb, ys);
-            cmul5(mub, s_dua + 3 * tb, ya);
+            cmul5(mub, g_dua + 3 * tb, ya);
             for (int q = 0; q < 5; ++q) {
               const int t = 5 * tb + q;
               const double sl = ys[q], su = (q < 4 ? ubxy : ubz) - sl, zl = g_zl[t], zu = g_zu[t];
@@ -948,7 +964,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
           double ys[5], yd[5], ya[5] = {0, 0, 0, 0, 0};
           cmul5(mub, s_u + 3 * tb, ys);
           cmul5(mub, s_du + 3 * tb, yd);
-          if (phase) cmul5(mub, s_dua + 3 * tb, ya);
+          if (phase) cmul5(mub, g_dua + 3 * tb, ya);
           for (int q = 0; q < 5; ++q) {
             const int t = 5 * tb + q;
             const double sl = ys[q], su = (q < 4 ? ubxy : ubz) - sl, zl = g_zl[t], zu = g_zu[t];
@@ -1009,7 +1025,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
         double ys[5], yd[5], ya[5];
         cmul5(mub, s_u + 3 * tb, ys);  // slacks at the current point (before the update)
         cmul5(mub, s_du + 3 * tb, yd);
-        cmul5(mub, s_dua + 3 * tb, ya);
+        cmul5(mub, g_dua + 3 * tb, ya);
         for (int q = 0; q < 5; ++q) {
           const int t = 5 * tb + q;
           const double sl = ys[q], su = (q < 4 ? ubxy : ubz) - sl, zl = g_zl[t], zu = g_zu[t];
@@ -1034,7 +1050,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
 
     // ---- outputs
     if (!numerical) {
-      if (status != CMPC_STATUS_OK) stage_gradient(N, L, gb, lane, y_.u, y_.rd);  // an accepted polish left H u + g in rd
+      if (status != CMPC_STATUS_OK) stage_gradient(N, L, gb, lane, y_.u, s_rd);  // an accepted polish left H u + g in rd
       double stat = 0.0, umax = 0.0, prim = 0.0, dual = 0.0, comp = 0.0;
 #pragma unroll 1
       for (int tb = lane; tb < nbfull; tb += 32) {
@@ -1136,25 +1152,26 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_probe_kernel(const __grid_co
   const int gb = kHdr + gid * y0_.total;
   const Lay y_ = make_lay(N, L, gb);
   double* const fac = args.scratch + (size_t)(blockIdx.x * args.groups + gid) * args.scratch_per_group;
-  double* const s_u = smem + y_.u; double* const s_du = smem + y_.du; double* const s_rd = smem + y_.rd; double* const s_dua = smem + y_.dua;
+  double* const s_u = smem + y_.u; double* const s_du = smem + y_.du; double* const s_rd = smem + y_.rd;
+  double* const g_Rs = fac + (size_t)N * kFac;  // (the solve kernel keeps its multipliers here)
   fill_header(cfg);
   for (int inst = blockIdx.x * args.groups + gid; inst < B; inst += gridDim.x * args.groups) {
     bool invalid; int nb;
     stage_instance(cfg, args, y_, inst, lane, invalid, nb);
-    for (int t = lane; t < 6 * nbfull; t += 32) smem[y_.Rs + t] = hess[(size_t)inst * 6 * nbfull + t];
-    for (int t = lane; t < nfN; t += 32) { s_du[t] = rhs[(size_t)inst * nfN + t]; s_dua[t] = s_du[t]; }
+    for (int t = lane; t < 6 * nbfull; t += 32) g_Rs[t] = hess[(size_t)inst * 6 * nbfull + t];
+    for (int t = lane; t < nfN; t += 32) { s_du[t] = rhs[(size_t)inst * nfN + t]; s_u[t] = s_du[t]; }
     __syncwarp();
-    const bool ok = lqr_factor(N, L, gb, lane, mode, fac);
+    const bool ok = lqr_factor(N, L, gb, lane, mode, fac, g_Rs);
     lqr_forward(N, L, gb, lane, fac, y_.du);
-    for (int t = lane; t < nfN; t += 32) { d_fused[(size_t)inst * nfN + t] = ok ? s_du[t] : nan(""); s_du[t] = s_dua[t]; }
+    for (int t = lane; t < nfN; t += 32) { d_fused[(size_t)inst * nfN + t] = ok ? s_du[t] : nan(""); s_du[t] = s_u[t]; }
     __syncwarp();
     if (ok) {
       lqr_backsolve(N, L, gb, lane, fac);
       lqr_forward(N, L, gb, lane, fac, y_.du);
     }
-    for (int t = lane; t < nfN; t += 32) { d_resolve[(size_t)inst * nfN + t] = ok ? s_du[t] : nan(""); s_u[t] = s_dua[t]; }
+    for (int t = lane; t < nfN; t += 32) { d_resolve[(size_t)inst * nfN + t] = ok ? s_du[t] : nan(""); }
     __syncwarp();
-    stage_gradient(N, L, gb, lane, y_.u, y_.rd);
+    stage_gradient(N, L, gb, lane, y_.u, s_rd);
     for (int t = lane; t < nfN; t += 32) grad[(size_t)inst * nfN + t] = s_rd[t];
     __syncwarp();
   }
@@ -1172,7 +1189,7 @@ void ripm_sizes(int N, int L, int* group_doubles, int* cta_doubles, int* slab_do
   const Lay y = make_lay(N, L, 0);
   *group_doubles = y.total;
   *cta_doubles = kHdr;
-  *slab_doubles = N * kFac + 2 * 5 * L * N;
+  *slab_doubles = N * kFac + 2 * 5 * L * N + ((3 * L * N + 1) & ~1) + 6 * L * N;
 }
 
 cudaError_t launch_ripm_kernel(int grid, int block, size_t smem_bytes, cudaStream_t stream, const DevConfig& cfg, const SolveArgs& args) {
