@@ -177,7 +177,7 @@ int cmpc_solve_batch_sqp(cmpc_handle* h, int B, int sqp_iters, const double* sta
  * mode 1: hess [B][N][L][6] = the entries (xx, yy, zz, zx, zy, unused) of 1/2 F_i' diag(sigma) F_i per leg-step;
  * mode 2: sigma = 0 and d restricted per leg-step to the range of the symmetric projector given as
  *         (00, 11, 22, 10, 20, 21) -- the polish's equality-constrained system.
- * d_fused: right-hand side carried by the factor sweep; d_resolve: the same right-hand side through the
+ * d_fused: right-hand side carried by the factor sweep; d_resolve (mode 1 only): the same right-hand side through the
  * stored factors; grad = H rhs + g (rhs taken as a force vector).  All force vectors [B][N][L][3]. Host buffers. */
 int cmpc_stage_step_batch(cmpc_handle* h, int B, int mode, const double* state, const double* des_state,
                           const double* des_inputs, const double* hess, const double* rhs, double* d_fused,
