@@ -20,6 +20,12 @@ int cmpc_oracle_solve(const cmpc_config* c, const double* state, const double* d
 int cmpc_oracle_solve_batch(const cmpc_config* c, int B, const double* state, const double* des_state,
                             const double* des_inputs, double* forces, int32_t* status, int32_t* iters,
                             double* kkt, double* lam, uint16_t* active, int nthreads);
+/* The CPU BASELINE port (cmpc_cpu_fast.c): same algorithm, compact closed-form build, no allocation per solve,
+ * persistent thread pool (created on the first call, re-created when nthreads changes).  Checked against
+ * cmpc_oracle_solve_batch in tests/test_oracle.py; timed by bench.py's cpu_baseline / --impl reference legs. */
+int cmpc_fast_solve_batch(const cmpc_config* c, int B, const double* state, const double* des_state,
+                          const double* des_inputs, double* forces, int32_t* status, int32_t* iters,
+                          double* kkt, uint16_t* active, int nthreads);
 /* Reference plant step (CentroidalMPC.cpp:85-92). forces [L][3], contact [L]. */
 void cmpc_oracle_plant_step(const cmpc_config* c, const double* x, const double* feet,
                             const double* contact, const double* forces, double* xn);

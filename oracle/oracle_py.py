@@ -13,8 +13,29 @@ _SO = os.path.join(_HERE, "_build", "libcmpc_oracle.so")
 _LIB = None
 
 
+def _cpu_sig():
+    import hashlib
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                return hashlib.md5((line.rstrip("\n") + "\n").encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def build(force=False):
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(os.path.join(_HERE, "cmpc_oracle.c")):
+    """(Re)build when a source is newer than the library, or when the library was built on a different CPU
+    (the baseline port is compiled with -march=native; built artefacts travel to the GPU box)."""
+    srcs = [os.path.join(_HERE, f) for f in ("cmpc_oracle.c", "cmpc_cpu_fast.c", "cmpc_oracle.h", "Makefile")]
+    sig = os.path.join(_HERE, "_build", "cpu_sig")
+    stale = force or not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(f) for f in srcs)
+    if not stale:
+        try:
+            stale = open(sig).read().strip() != _cpu_sig()
+        except OSError:
+            stale = True
+    if stale:
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
     return _SO
 
@@ -28,6 +49,7 @@ def lib():
         l.cmpc_oracle_build.argtypes = [vp] * 7
         l.cmpc_oracle_solve.argtypes = [vp] * 10
         l.cmpc_oracle_solve_batch.argtypes = [vp, C.c_int] + [vp] * 9 + [C.c_int]
+        l.cmpc_fast_solve_batch.argtypes = [vp, C.c_int] + [vp] * 8 + [C.c_int]
         l.cmpc_oracle_plant_step.argtypes = [vp] * 6
         l.cmpc_oracle_plant_step.restype = None
         _LIB = l
@@ -62,6 +84,19 @@ def solve_batch(ccfg, state, des_state, des_inputs, nthreads=1, want_lam=True):
     lib().cmpc_oracle_solve_batch(C.addressof(ccfg), B, _p(s), _p(d), _p(i), _p(forces), _p(status), _p(iters),
                                   _p(kkt), _p(lam), _p(active), int(nthreads))
     return dict(forces=forces, status=status, iters=iters, kkt=kkt, lam=lam, active=active)
+
+
+def fast_solve_batch(ccfg, state, des_state, des_inputs, nthreads=1):
+    """The CPU baseline port (cmpc_cpu_fast.c): same outputs as solve_batch, no multipliers."""
+    N, L = ccfg.horizon, ccfg.num_legs
+    s = _f(state); B = s.shape[0] if s.ndim == 2 else 1
+    s = s.reshape(B, -1); d = _f(des_state).reshape(B, -1); i = _f(des_inputs).reshape(B, -1)
+    forces = np.zeros((B, 3 * L * N)); status = np.zeros(B, np.int32); iters = np.zeros(B, np.int32)
+    kkt = np.zeros(B); active = np.zeros((B, N, L), np.uint16)
+    rc = lib().cmpc_fast_solve_batch(C.addressof(ccfg), B, _p(s), _p(d), _p(i), _p(forces), _p(status), _p(iters),
+                                     _p(kkt), _p(active), int(nthreads))
+    assert rc == 0
+    return dict(forces=forces, status=status, iters=iters, kkt=kkt, active=active)
 
 
 def plant_step(ccfg, x, feet, contact, forces):

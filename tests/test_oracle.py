@@ -279,3 +279,26 @@ def test_stage_newton_step_equals_dense_system(wl, N, disc):
         dref2 = Zf @ np.linalg.solve(Zf.T @ qp["H"] @ Zf, Zf.T @ rhs)
         d2 = nm.stage_newton_step(cfg, st[b], ds[b], di[b], np.zeros((N, L, 5)), rhs, Zm)
         assert np.abs(d2 - dref2).max() <= 1e-11 * np.abs(dref2).max()
+
+
+@pytest.mark.parametrize("N,hard,disc", [(10, False, 0), (10, True, 0), (6, True, 1), (30, True, 0), (30, False, 0)])
+def test_fast_cpu_port_matches_oracle(pkg, orc, wl, N, hard, disc):
+    """The CPU baseline port that bench.py times (oracle/cmpc_cpu_fast.c: compact closed-form build, workspace,
+    thread pool) against the explicit oracle: same status, iterations and active set, forces to 1e-9."""
+    from conftest import hard_config
+    cfg = hard_config(wl, N, 0.3, disc_mode=disc) if hard else wl.default_config(N, disc_mode=disc)
+    B = 24 if N == 30 else 96
+    st, ds, di = wl.make_batch(cfg, B, gaits=wl.GAITS)
+    di[1].reshape(4, 4 * N + 3)[:, 2] = 0.0    # invalid table
+    st[2, 4] = np.inf                           # non-finite input
+    ccfg = pkg.make_config(cfg)
+    ref = orc.solve_batch(ccfg, st, ds, di, nthreads=4)
+    for threads in (1, 3):
+        out = orc.fast_solve_batch(ccfg, st, ds, di, nthreads=threads)
+        assert np.array_equal(out["status"], ref["status"])
+        assert out["status"][1] == 3 and out["status"][2] == 4
+        assert np.array_equal(out["iters"], ref["iters"])
+        assert np.array_equal(out["active"], ref["active"])
+        sc = np.abs(ref["forces"]).max(axis=1, keepdims=True) + 1e-300
+        assert (np.abs(out["forces"] - ref["forces"]) / sc).max() <= 1e-9
+        assert out["kkt"].max() <= 1e-8
