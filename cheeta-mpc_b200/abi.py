@@ -113,6 +113,8 @@ def load_library():
     lib.cmpc_last_error.argtypes = [vp]
     lib.cmpc_last_error.restype = C.c_char_p
     lib.cmpc_version.restype = C.c_char_p
+    lib.cmpc_last_route.argtypes = [vp]
+    lib.cmpc_last_route.restype = C.c_char_p
     _LIB = lib
     return lib
 
@@ -268,6 +270,9 @@ class CentroidalMPC:
             self.SetupMPC(B)
         self._check(self.lib.cmpc_fill_contact_tables(self.h, B, C.cast(arr, C.c_void_p), len(gaits), _ptr(gid), _ptr(tt), _ptr(di)))
         return di
+
+    def last_route(self):
+        return self.lib.cmpc_last_route(self.h).decode()
 
     def set_stream(self, stream_ptr):
         self._check(self.lib.cmpc_set_stream(self.h, C.c_void_p(stream_ptr)))

@@ -28,8 +28,8 @@ struct cmpc_handle {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // progressive host-buffer path of cmpc_solve_batch: chunked copy-in on its own stream
   static constexpr int kMaxChunks = 8;
-  cudaStream_t s_in = nullptr;
-  cudaEvent_t ev_span[4] = {}, ev_in[kMaxChunks] = {};
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_span[4] = {}, ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {};
   // device buffers
   double *d_state = nullptr, *d_ds = nullptr, *d_di = nullptr, *d_forces = nullptr, *d_kkt = nullptr,
          *d_lam = nullptr, *d_flog = nullptr, *d_hip = nullptr;
@@ -63,13 +63,14 @@ struct cmpc_handle {
   int32_t* h_ready_vals = nullptr;   // pinned {1, 2, ...}: the values the copy stream writes into d_ready
   int32_t* h_error_dev = nullptr;    // device alias of h_error
   int32_t* h_error = nullptr;        // pinned + mapped: set by a kernel whose wait on d_ready timed out
-  int e2e_mode = 0;                  // CMPC_E2E_MODE, see cmpc_solve_batch: 0 auto, 1 zero-copy, 2 staged, 3 progressive, 4 pipelined
+  int e2e_mode = 0;                  // CMPC_E2E_MODE, see cmpc_solve_batch: 0 auto, 1 zero-copy, 2 staged, 3 progressive, 4 pipelined, 5 full duplex
   // auto mode, big pinned batches: the first calls time the zero-copy and the pipelined route (which one
   // wins depends on the box: DMA 35-56 GB/s vs ~26 GB/s SM-issued reads), then the faster one is kept
   int e2e_chunk = 0;                 // CMPC_E2E_CHUNK: instances per copy chunk (0: default of the route)
   bool debug_tune = false;           // CMPC_DEBUG_TUNE: print the route timings of the tuning calls
   int tune_calls = 0, tune_batch = 0;
-  float tune_best[2] = {1e30f, 1e30f};  // [0] zero-copy, [1] pipelined: best span in ms
+  float tune_best[3] = {1e30f, 1e30f, 1e30f};  // [0] zero-copy, [1] pipelined, [2] full duplex: best span in ms
+  char route[96] = "none";           // what the last cmpc_solve_batch call did (cmpc_last_route)
   int32_t *d_counts = nullptr, *d_perm = nullptr;  // counts[4], work[4], then the presolve's deferred counts[4], work[4]; perm [2][4][B]
   std::string err;
 };
@@ -573,7 +574,7 @@ int collect_stats(cmpc_handle* h, int B, const int32_t* d_status, const int32_t*
 
 extern "C" {
 
-const char* cmpc_version(void) { return "cmpc_b200 0.2 (sm_100a)"; }
+const char* cmpc_version(void) { return "cmpc_b200 0.3 (sm_100a)"; }
 
 int cmpc_config_init(cmpc_config* cfg, double mass, int num_legs, int horizon, double dt, const double* weights,
                      const double* mu) {
@@ -614,6 +615,8 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
   if (!h->stream) { CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
   for (auto& e : h->ev) CUDA_TRY(h, cudaEventCreate(&e));
   CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+  CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+  for (auto& e : h->ev_k) CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : h->ev_span) CUDA_TRY(h, cudaEventCreate(&e));
   for (auto& e : h->ev_in) CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
@@ -806,23 +809,35 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
   //    waits per instance for its chunk; best case 0.335 ms but 0.34-0.70 ms over runs (the copies slow
   //    down erratically while 2000 warps poll).
   //  4 pipelined regardless of the batch size (>= 1024).
+  //  5 full duplex: pipelined copy-in, and the outputs of every chunk leave by the copy engine on a third stream
+  //    while the next chunk is still coming in (the SMs never wait on posted writes over the bus).
+  // Automatic tuning (mode 0, pinned buffers, batches of two waves or more): the first two calls of a batch size are
+  // warm-up (pipelined; page tables, clocks and the copy engines are cold), the next six time the three routes
+  // twice each (library-side events), then the fastest is kept; cmpc_last_route() says which.
   const bool tunable = in_mapped && router && h->e2e_mode == 0 && B >= 4096;
-  if (tunable && h->tune_batch != B) { h->tune_batch = B; h->tune_calls = 0; h->tune_best[0] = h->tune_best[1] = 1e30f; }
-  const bool tuning = tunable && h->tune_calls < 6;
-  const bool auto_pipelined = tunable && (tuning ? (h->tune_calls & 1) != 0 : h->tune_best[1] < h->tune_best[0]);
-  const bool pipelined = in_mapped && router && (auto_pipelined || (h->e2e_mode == 4 && B >= 1024));
+  if (tunable && h->tune_batch != B) { h->tune_batch = B; h->tune_calls = 0; h->tune_best[0] = h->tune_best[1] = h->tune_best[2] = 1e30f; }
+  const bool tuning = tunable && h->tune_calls >= 2 && h->tune_calls < 8;
+  int kind = 0;  // 0 zero-copy, 1 pipelined, 2 full duplex
+  if (tunable) {
+    if (h->tune_calls < 2) kind = 1;
+    else if (tuning) kind = (h->tune_calls - 2) % 3;
+    else kind = h->tune_best[1] <= h->tune_best[0] ? (h->tune_best[2] < h->tune_best[1] ? 2 : 1) : (h->tune_best[2] < h->tune_best[0] ? 2 : 0);
+  }
+  if (in_mapped && router && B >= 1024 && (h->e2e_mode == 4 || h->e2e_mode == 5)) kind = h->e2e_mode == 4 ? 1 : 2;
+  const bool pipelined = in_mapped && router && kind >= 1;
+  const bool duplex = pipelined && kind == 2 && out_mapped;
   const bool zc_in = in_mapped && h->e2e_mode != 2 && h->e2e_mode != 3 && !pipelined;
   // (progressive needs pinned inputs: a pageable cudaMemcpyAsync is staged by the driver and can
   // serialise behind the running kernel, which would then wait for its chunk until the time-out)
   const bool progressive = in_mapped && !zc_in && router && h->e2e_mode == 3 && B >= 256;
   // Outputs: written in place over the bus when every output buffer is pinned (posted writes,
   // overlapped with the remaining compute); otherwise device buffers and one copy back.
-  const bool zc_out = out_mapped && h->e2e_mode != 2;
+  const bool zc_out = out_mapped && h->e2e_mode != 2 && !duplex;
   SolveArgs a = base_args(h, B);
   a.state = zc_in ? (const double*)dp[0] : h->d_state;
   a.des_state = zc_in ? (const double*)dp[1] : h->d_ds;
   a.des_inputs = zc_in ? (const double*)dp[2] : h->d_di;
-  if (zc_out) {
+  if (zc_out) {  // (full duplex: device buffers, copied out per chunk)
     a.forces = (double*)dp[3]; a.status = (int32_t*)dp[4];
     a.iters = iters ? (int32_t*)dp[5] : (stats ? h->d_iters : nullptr);
     a.kkt = kkt ? (double*)dp[6] : (stats ? h->d_kkt : nullptr);
@@ -885,6 +900,20 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
       int rc = launch_solve(h, ac, nbc);
       if (rc < 0) return rc;
       launches += rc;
+      if (duplex) {  // this chunk's results leave on the copy-out stream while the next chunk computes / copies in
+        CUDA_TRY(h, cudaEventRecord(h->ev_k[c], s));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->s_out, h->ev_k[c], 0));
+        CUDA_TRY(h, cudaMemcpyAsync(forces + o * nf, h->d_forces + o * nf, (size_t)nbc * nf * 8, cudaMemcpyDeviceToHost, h->s_out));
+        CUDA_TRY(h, cudaMemcpyAsync(status + o, h->d_status + o, (size_t)nbc * 4, cudaMemcpyDeviceToHost, h->s_out));
+        if (iters) CUDA_TRY(h, cudaMemcpyAsync(iters + o, h->d_iters + o, (size_t)nbc * 4, cudaMemcpyDeviceToHost, h->s_out));
+        if (kkt) CUDA_TRY(h, cudaMemcpyAsync(kkt + o, h->d_kkt + o, (size_t)nbc * 8, cudaMemcpyDeviceToHost, h->s_out));
+        if (lam) CUDA_TRY(h, cudaMemcpyAsync(lam + o * 10 * L * N, h->d_lam + o * 10 * L * N, (size_t)nbc * 10 * L * N * 8, cudaMemcpyDeviceToHost, h->s_out));
+        if (active) CUDA_TRY(h, cudaMemcpyAsync(active + o * L * N, h->d_active + o * L * N, (size_t)nbc * L * N * 2, cudaMemcpyDeviceToHost, h->s_out));
+      }
+    }
+    if (duplex) {  // the span ends when the last copy-out has landed
+      CUDA_TRY(h, cudaEventRecord(h->ev_k[0], h->s_out));
+      CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_k[0], 0));
     }
   } else if (!progressive) {
     int rc = launch_solve(h, a, B);
@@ -892,7 +921,7 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
     launches = rc;
   }
   CUDA_TRY(h, cudaEventRecord(h->ev_span[2], s));
-  if (!zc_out) {
+  if (!zc_out && !duplex) {
     CUDA_TRY(h, cudaMemcpyAsync(forces, h->d_forces, (size_t)B * nf * 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaMemcpyAsync(status, h->d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
     if (iters) CUDA_TRY(h, cudaMemcpyAsync(iters, h->d_iters, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
@@ -902,16 +931,18 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
   }
   CUDA_TRY(h, cudaEventRecord(h->ev_span[3], s));
   if (progressive || pipelined) CUDA_TRY(h, cudaStreamSynchronize(h->s_in));
+  if (duplex) CUDA_TRY(h, cudaStreamSynchronize(h->s_out));
   CUDA_TRY(h, cudaStreamSynchronize(s));
   if (*h->h_error) { *h->h_error = 0; return fail(h, CMPC_ERR_CUDA, "cmpc_solve_batch: input chunk did not arrive (copy stream stalled)"); }
-  if (tuning) {
+  if (tunable && h->tune_calls < 8) {
     float span = 0;
     CUDA_TRY(h, cudaEventElapsedTime(&span, h->ev_span[0], h->ev_span[3]));
-    float& best = h->tune_best[pipelined ? 1 : 0];
-    best = std::min(best, span);
+    if (tuning) { float& best = h->tune_best[kind]; best = std::min(best, span); }
     ++h->tune_calls;
-    if (h->debug_tune) fprintf(stderr, "[cmpc] tune call %d: %s %.3f ms (best zero-copy %.3f, pipelined %.3f)\n", h->tune_calls, pipelined ? "pipelined" : "zero-copy", span, h->tune_best[0], h->tune_best[1]);
+    if (h->debug_tune) fprintf(stderr, "[cmpc] tune call %d: route %d %.3f ms (best zero-copy %.3f, pipelined %.3f, duplex %.3f)\n", h->tune_calls, kind, span, h->tune_best[0], h->tune_best[1], h->tune_best[2]);
   }
+  snprintf(h->route, sizeof(h->route), "%s%s%s", progressive ? "progressive" : pipelined ? (duplex ? "full-duplex" : "pipelined") : zc_in ? "zero-copy" : "staged",
+           pipelined ? (nch == 2 ? " x2 chunks" : " chunks") : "", tunable ? (h->tune_calls < 8 ? " (tuning)" : " (tuned)") : "");
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
     int rc = collect_stats(h, B, a.status, a.iters, a.kkt, stats, launches);
@@ -1203,11 +1234,14 @@ void cmpc_destroy(cmpc_handle* h) {
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->ev_span) if (e) cudaEventDestroy(e);
   for (auto& e : h->ev_in) if (e) cudaEventDestroy(e);
+  for (auto& e : h->ev_k) if (e) cudaEventDestroy(e);
   if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
 
 const char* cmpc_last_error(const cmpc_handle* h) { return h ? h->err.c_str() : "null handle"; }
+const char* cmpc_last_route(const cmpc_handle* h) { return h ? h->route : "null handle"; }
 
 }  // extern "C"

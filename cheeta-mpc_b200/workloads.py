@@ -151,6 +151,15 @@ def gait_table(gait, N, phase, L=4):
     return t
 
 
+def hard_config(N=10, mu=0.3, dt=0.03, wf=1e-2, disc_mode=0):
+    """The CONSTRAINED workload: tracking-heavy weights (state tracking dominates force tracking) + low friction, so
+    that friction-pyramid rows go active in (almost) every instance and the presolve cannot settle them.  Not a
+    BASELINE.json config -- the reference driver's weights never activate a row -- but the workload every
+    "identical active set" claim and every constrained-path throughput number of this repo is made on."""
+    w = np.array([5e4, 5e4, 300, 500, 500, 500, 200, 200, 200] + [0.2] * 12 + [wf] * 12 + [wf / 10] * 12)
+    return default_config(N, dt=dt, mu=[mu] * 4, weights=w, disc_mode=disc_mode)
+
+
 def make_batch(cfg, B, first=0, gaits=("trot",), hard_fraction=0.25, seed=SEED):
     """Instances [first, first+B) of the synthetic workload.
 

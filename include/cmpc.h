@@ -217,6 +217,9 @@ int cmpc_measure_fp64_peak(cmpc_handle* h, double* tflops);
 
 void cmpc_destroy(cmpc_handle* h);
 const char* cmpc_last_error(const cmpc_handle* h);
+/* How the last cmpc_solve_batch call moved its data: "zero-copy", "pipelined x2 chunks", "full-duplex x2 chunks",
+ * "staged", "progressive", with "(tuning)" / "(tuned)" while / after the library times its routes. */
+const char* cmpc_last_route(const cmpc_handle* h);
 const char* cmpc_version(void);
 
 #ifdef __cplusplus

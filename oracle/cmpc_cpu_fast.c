@@ -426,7 +426,7 @@ static void solve_one(const cmpc_config* c, const double* state, const double* d
   const int n = w->n, nb = w->nb, m = 5 * nb;
   double *u = w->u, *rd = w->rd, *rhs = w->rhs, *du = w->du, *sl = w->sl, *su = w->su, *zl = w->zl, *zu = w->zu;
   int status = CMPC_STATUS_MAX_ITER, it = 0;
-  memset(u, 0, n * 8);
+  memset(u, 0, (size_t)n * 8);
   for (int b = 0; b < nb; ++b) {
     double fz = w->fz[b];
     if (fz > 0.5 * w->ub[5 * b + 4]) fz = 0.5 * w->ub[5 * b + 4];
@@ -440,7 +440,7 @@ static void solve_one(const cmpc_config* c, const double* state, const double* d
   for (int a = 0; a < n; ++a) rd[a] += w->g[a];
   double mu0 = maxabs(rd, n); if (mu0 < 1e-2) mu0 = 1e-2;
   for (int t = 0; t < m; ++t) { zl[t] = mu0 / sl[t]; zu[t] = mu0 / su[t]; }
-  memset(w->actl, 0, m); memset(w->actu, 0, m);
+  memset(w->actl, 0, (size_t)m); memset(w->actu, 0, (size_t)m);
   int npolish = 0, numerical = 0, ipm_ok = 0;
   if (c->polish && c->presolve && polish(w, gs, 0.0, u, zl, zu, 1)) status = CMPC_STATUS_OK;
   for (it = 0; status != CMPC_STATUS_OK && it <= c->max_iter; ++it) {

@@ -31,9 +31,8 @@ def wl(pkg):
 
 
 def hard_config(wl, N=10, mu=0.3, dt=0.03, wf=1e-2, disc_mode=0):
-    """Tracking-heavy weights + low friction: friction-pyramid rows go active."""
-    w = np.array([5e4, 5e4, 300, 500, 500, 500, 200, 200, 200] + [0.2] * 12 + [wf] * 12 + [wf / 10] * 12)
-    return wl.default_config(N, dt=dt, mu=[mu] * 4, weights=w, disc_mode=disc_mode)
+    """Tracking-heavy weights + low friction: friction-pyramid rows go active (workloads.hard_config)."""
+    return wl.hard_config(N, mu, dt, wf, disc_mode)
 
 
 def to_step_major(forces, N, L):
