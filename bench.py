@@ -60,6 +60,27 @@ def alg_flops(n_free, iters, polish_dim=None):
     return iters * (p ** 3 / 3 + 4 * p ** 2) + (q ** 3 / 3 + 2 * q ** 2)
 
 
+def stage_flops(m):
+    """Useful flops of ONE stage of the stage-wise (Riccati) sweep with m free inputs over the augmented state
+    (nz = 21): P Bbar exploiting the input structure (12 MACs per entry), the lower triangle of G, an m x m Cholesky,
+    22 triangular solves, the symmetric half of P -= Y'Y, and the three vector sweeps of an iteration."""
+    m = np.asarray(m, float)
+    return 504 * m + 12 * m * (m + 1) + m ** 3 / 3 + 22 * m ** 2 + 462 * m + 3 * (42 * m + 2 * m ** 2)
+
+
+def useful_flops(a16, its, N, L):
+    """Per-instance useful flops by the route the library takes (cmpc_api.cu presolve_kind / ipm_kind, automatic
+    back-end): presolve = condensed Cholesky up to 20 free leg-steps, stage-wise sweep above; interior point =
+    condensed factorisations up to 42 free leg-steps, stage-wise sweeps above.  a16 [B, N*L]: bit 15 = swing leg."""
+    stance = ((a16.reshape(len(a16), N, L) & 0x8000) == 0)
+    nb = stance.sum(axis=(1, 2))
+    n = 3.0 * nb
+    sweep = stage_flops(3 * stance.sum(axis=2)).sum(axis=1)          # one backward + forward sweep over the horizon
+    pre = np.where(nb <= 20, n ** 3 / 3 + 2 * n ** 2, sweep)         # presolve or final polish system
+    it = np.where(nb <= 42, its * (n ** 3 / 3 + 4 * n ** 2), its * sweep)
+    return it + pre
+
+
 class ClockSampler(threading.Thread):
     """SM clock and throttle reasons sampled DURING the timed region: NVML every 2 ms (nvidia_ml_py),
     falling back to the nvidia-smi query line of the profiling recipe (slower: a few samples per run)."""
@@ -250,6 +271,7 @@ def main():
         ms = np.array([a.elapsed_time(b) for a, b in evs])
         st_ = s.cpu().numpy(); its = it.cpu().numpy(); kkt_ = kk.cpu().numpy()
         a16 = act.cpu().numpy().view(np.uint16)
+        NL = (m.N, m.L)
         nact = np.array([[bin(int(x) & 0x3FF).count("1") for x in row] for row in a16[:256]]).sum(axis=1)
         nfree = 3 * ((a16 & 0x8000) == 0).sum(axis=1)
         ok = st_ <= 1
@@ -258,7 +280,7 @@ def main():
         return {"p50_ms": p50, "p99_ms": reduce_max(float(np.percentile(ms, 99))), "steps": steps, "batch_per_gpu": nb,
                 "status_counts": np.bincount(st_, minlength=5).tolist(), "mean_ipm_iters": float(its.mean()),
                 "max_kkt": float(kkt_[ok].max()) if ok.any() else None, "mean_active_rows": float(nact.mean()),
-                "flops_per_solve": float(np.mean(alg_flops(nfree, its))), "_nfree": float(nfree.mean())}
+                "flops_per_solve": float(np.mean(useful_flops(a16, its, NL[0], NL[1]))), "_nfree": float(nfree.mean())}
 
     # rank r owns instance ids [r*B, (r+1)*B): contiguous block split, no inter-GPU traffic
     st, ds, di = wl.make_batch(cfg, B, first=rank * B, gaits=gaits)

@@ -74,9 +74,7 @@ def main():
         blob[pre + "state"], blob[pre + "des_state"], blob[pre + "des_inputs"] = st, ds, di
         blob[pre + "forces"], blob[pre + "active"] = res["forces"], res["active"]
         blob[pre + "lam"], blob[pre + "iters"] = res["lam"], res["iters"]
-        # H is large at N=30: keep g and a few H invariants there, full H for N<=10
-        if N <= 10:
-            blob[pre + "H"] = np.array(Hs)
+        blob[pre + "H"] = np.array(Hs)   # full H at every horizon (the N = 30 matrices compress to a few hundred KB)
         blob[pre + "g"] = np.array(gs)
         blob[pre + "H_diag"] = np.array([np.diag(h) for h in Hs])
         blob[pre + "H_rowsum"] = np.array([h.sum(axis=1) for h in Hs])

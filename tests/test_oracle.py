@@ -302,3 +302,72 @@ def test_fast_cpu_port_matches_oracle(pkg, orc, wl, N, hard, disc):
         sc = np.abs(ref["forces"]).max(axis=1, keepdims=True) + 1e-300
         assert (np.abs(out["forces"] - ref["forces"]) / sc).max() <= 1e-9
         assert out["kkt"].max() <= 1e-8
+
+
+def _golden_cfg(v):
+    L = int(v[1])
+    return dict(mass=float(v[0]), num_legs=L, horizon=int(v[2]), dt=float(v[3]), disc_mode=int(v[4]),
+                mu=list(v[5:5 + L]), weights=list(v[5 + L:5 + L + 9 + 9 * L]))
+
+
+def test_scipy_pin(pkg, orc):
+    """The oracle against arithmetic this repo did not write (tests/golden/make_scipy_pin.py): SciPy's SLSQP on the
+    swing-eliminated QP of every golden case -- raw SLSQP forces <= 5e-6 relative (SLSQP's own accuracy), its
+    active set refined by one LAPACK KKT solve <= 1e-9, identical active set incl. the cases with 28-69 active rows."""
+    import os
+    from conftest import to_step_major
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    z, p = np.load(os.path.join(here, "golden_v1.npz")), np.load(os.path.join(here, "scipy_pin_v1.npz"))
+    nact = 0
+    for name in sorted({k.split("/")[0] for k in z.files}):
+        cfg = _golden_cfg(z[name + "/cfg"])
+        ref = orc.solve_batch(pkg.make_config(cfg), z[name + "/state"], z[name + "/des_state"], z[name + "/des_inputs"])
+        U = to_step_major(ref["forces"], cfg["horizon"], cfg["num_legs"])
+        sc = np.abs(U).max(axis=1, keepdims=True)
+        assert (np.abs(U - p[name + "/U_slsqp"]) / sc).max() <= 5e-6, name
+        assert (np.abs(U - p[name + "/U_refined"]) / sc).max() <= 1e-9, name
+        assert np.array_equal(ref["active"] & 0x3FF, p[name + "/active_slsqp"]), name
+        nact += sum(bin(int(a)).count("1") for a in p[name + "/active_slsqp"].ravel())
+    assert nact > 500   # the pin covers active rows, not only interior optima
+
+
+def test_scipy_pin_live_small(pkg, orc, wl):
+    """Live SciPy run (SLSQP + trust-constr) on the reference driver's fixture: agrees with the oracle."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_scipy_pin as M
+    from conftest import to_step_major
+    cfg, st, ds, di = wl.fixture_f1()
+    H, g, C, ub, tags, free, qp = M.reduced_qp(cfg, st, ds, di)
+    u0 = M.feasible_start(cfg, qp, free, C, ub, tags)
+    u, _ = M.solve_slsqp(H, g, C, ub, u0)
+    u2, _ = M.solve_trust_constr(H, g, C, ub, u0)
+    ref = orc.solve_batch(pkg.make_config(cfg), st[None], ds[None], di[None])
+    U = to_step_major(ref["forces"], cfg["horizon"], cfg["num_legs"])[0][free]
+    assert np.abs(u - U).max() <= 5e-6 * np.abs(U).max()
+    assert np.abs(u2 - U).max() <= 5e-6 * np.abs(U).max()
+
+
+def test_reference_nlp_pin(pkg, orc):
+    """Model fidelity: the reference's own non-convex NLP (CentroidalMPC.cpp:102-276) solved by SciPy
+    (tests/golden/make_nlp_pin.py) against the convex model.  On the reference driver's fixture the frozen-arm QP's
+    forces are within 1 % of the NLP's, the re-linearised fixed point within 0.05 %; with tracking-heavy weights the
+    NLP moves the swing footholds to the edge of the step box and the convex model (footholds fixed) is 13-45 % off --
+    the stored gaps are re-derived here from the oracle, so they cannot drift silently."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_nlp_pin as M
+    p = np.load(os.path.join(os.path.dirname(__file__), "golden", "nlp_pin_v1.npz"))
+    for name in sorted({k.split("/")[0] for k in p.files}):
+        cfg = _golden_cfg(p[name + "/cfg"])
+        st, ds, di = p[name + "/state"], p[name + "/des_state"], p[name + "/des_inputs"]
+        seq = M.relinearised_fixed_point(pkg, orc, cfg, st, ds, di)
+        fn = p[name + "/forces_nlp"]
+        sc = np.abs(fn).max()
+        gaps = np.array([np.abs(seq[0] - fn).max() / sc, np.abs(seq[-1] - fn).max() / sc])
+        assert np.allclose(gaps, p[name + "/gaps"], rtol=1e-4, atol=1e-9), (name, gaps, p[name + "/gaps"])
+        assert np.abs(seq[0] - p[name + "/forces_qp"]).max() <= 1e-9 * sc
+        if name.startswith("fixture_f1"):
+            assert gaps[0] <= 1e-2 and gaps[1] <= 5e-4, (name, gaps)
+        # the NLP solution is feasible for the reference's constraints and not worse than the convex model's point
+        assert p[name + "/cost_nlp"][0] <= p[name + "/cost_nlp"][1]

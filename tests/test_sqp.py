@@ -72,3 +72,26 @@ def test_sqp_loop_matches_oracle_loop_and_contracts(pkg, orc, wl, name):
     assert dk.max() <= 1e-3 * d0.max()
     print(name, "defect per iteration (max over batch):", out["defect"].max(axis=0))
     m.close()
+
+
+def test_sqp_against_reference_nlp_pin(pkg):
+    """cmpc_solve_batch_sqp against the stored solutions of the reference's own NLP (tests/golden/nlp_pin_v1.npz,
+    SciPy SLSQP on CentroidalMPC.cpp:102-276): the GPU's re-linearised forces equal the oracle-emulated fixed point
+    and sit at the stored distance from the NLP optimum (0.012 % on the reference driver's fixture)."""
+    import os
+    p = np.load(os.path.join(os.path.dirname(__file__), "golden", "nlp_pin_v1.npz"))
+    for name in sorted({k.split("/")[0] for k in p.files}):
+        v = p[name + "/cfg"]
+        L = int(v[1]); N = int(v[2])
+        cfg = dict(mass=float(v[0]), num_legs=L, horizon=N, dt=float(v[3]), disc_mode=int(v[4]),
+                   mu=list(v[5:5 + L]), weights=list(v[5 + L:5 + L + 9 + 9 * L]))
+        m = pkg.CentroidalMPC.from_dict(cfg)
+        m.SetupMPC(1)
+        out = m.SolveSQP(p[name + "/state"][None], p[name + "/des_state"][None], p[name + "/des_inputs"][None], sqp_iters=8)
+        F = out["forces"][0].reshape(L, N, 3).transpose(1, 0, 2)
+        fn = p[name + "/forces_nlp"]
+        sc = np.abs(fn).max()
+        assert np.abs(F - p[name + "/forces_fixed_point"]).max() <= 1e-6 * sc, name
+        gap = np.abs(F - fn).max() / sc
+        assert abs(gap - p[name + "/gaps"][1]) <= 1e-5 + 1e-3 * p[name + "/gaps"][1], (name, gap)
+        m.close()
