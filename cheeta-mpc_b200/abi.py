@@ -105,6 +105,8 @@ def load_library():
     lib.cmpc_solve_batch_sqp.argtypes = [vp, C.c_int, C.c_int] + [vp] * 6
     lib.cmpc_fill_contact_tables.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp]
     lib.cmpc_fill_contact_tables_device.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp]
+    lib.cmpc_fill_contact_tables_switch.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, C.c_double, vp, vp]
+    lib.cmpc_fill_contact_tables_switch_device.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, C.c_double, vp, vp]
     lib.cmpc_set_stream.argtypes = [vp, vp]
     lib.cmpc_synchronize.argtypes = [vp]
     lib.cmpc_measure_fp64_peak.argtypes = [vp, dp]
@@ -269,6 +271,18 @@ class CentroidalMPC:
         if self.max_batch == 0:
             self.SetupMPC(B)
         self._check(self.lib.cmpc_fill_contact_tables(self.h, B, C.cast(arr, C.c_void_p), len(gaits), _ptr(gid), _ptr(tt), _ptr(di)))
+        return di
+
+    def FillContactTablesSwitch(self, gaits, gait_from, gait_to, t_tile, t_switch, stance_time, t0, des_inputs):
+        """Gait switch with intermediate stance (GaitSchedule.cpp:47-72,107-137); returns a des_inputs copy."""
+        di = _f64(des_inputs).copy(); B = di.shape[0]
+        ga = np.ascontiguousarray(gait_from, dtype=np.int32); gb = np.ascontiguousarray(gait_to, dtype=np.int32)
+        tt, ts, tz = _f64(t_tile), _f64(t_switch), _f64(t0)
+        arr = (CmpcGait * len(gaits))(*gaits)
+        if self.max_batch == 0:
+            self.SetupMPC(B)
+        self._check(self.lib.cmpc_fill_contact_tables_switch(self.h, B, C.cast(arr, C.c_void_p), len(gaits), _ptr(ga), _ptr(gb),
+                                                             _ptr(tt), _ptr(ts), float(stance_time), _ptr(tz), _ptr(di)))
         return di
 
     def last_route(self):

@@ -329,6 +329,57 @@ __global__ void gait_kernel(const DevConfig cfg, int B, const GaitTable tab, con
   for (int i = 0; i < L; ++i) des_inputs[(size_t)b * L * (4 * N + 3) + i * (4 * N + 3) + j] = (mode & bit[i]) ? 1.0 : 0.0;
 }
 
+// Gait SWITCH (the stance-insertion rule): the contact flags of a mode schedule in which template `from`,
+// tiled from t_tile (GaitSchedule::tileModeSequenceTemplate, GaitSchedule.cpp:107-137: event times by repeated addition
+// of the template's intervals, whole cycles), is replaced at t_switch by template `to` the way
+// GaitSchedule::insertModeSequenceTemplate does it (GaitSchedule.cpp:47-72): events at or after t_switch are erased, the
+// mode active there runs on until t_switch, an intermediate STANCE phase of stance_time follows unless that mode already
+// is STANCE, then `to` is tiled from t_switch (+ stance_time).  Mode at time t = modeSequence[lower_bound(eventTimes, t)]
+// (ModeSchedule::modeAtTime of the un-vendored ocs2_core: a step that lands exactly on an event keeps the earlier mode).
+// One thread per instance walks the event stream once; every time is formed by the same additions as the host code
+// (no fused multiply-add), so the flags are bit-exact against the mirror.
+__global__ void gait_switch_kernel(const DevConfig cfg, int B, const GaitTable tab, const int32_t* gait_from, const int32_t* gait_to,
+                                   const double* t_tile, const double* t_switch, double stance_time, const double* t0, double* des_inputs) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int N = cfg.N, L = cfg.L;
+  constexpr int kStance = 15;
+  int ga = gait_from[b], gb = gait_to[b];
+  if (ga < 0 || ga >= tab.num_gaits) ga = 0;
+  if (gb < 0 || gb >= tab.num_gaits) gb = 0;
+  const double ts = t_switch[b];
+  const double t_end = __dadd_rn(t0[b], __dmul_rn((double)N, cfg.dt));
+  const bool sw = isfinite(ts);
+  // Event stream: `mode` is active up to and including the next event `te`.  stage 0: the old tiling (its events at or
+  // after t_switch are never taken), 1: the inserted stance event at t_switch is pending, 2: the new tiling.
+  int stage = 0, gi = ga, idx = 0, mode = kStance;
+  double te = t_tile[b], fin = sw ? ts : t_end;
+  const int bit[4] = {8, 4, 1, 2};  // {lf, rf, rh, lh} <- {LF, RF, RH, LH}
+  for (int j = 0; j < N; ++j) {
+    const double t = __dadd_rn(t0[b], __dmul_rn((double)j, cfg.dt));
+    for (;;) {
+      if (stage == 0 && sw && !(te < ts)) {  // insertion (GaitSchedule.cpp:52-71): the current mode runs on until t_switch
+        if (mode != kStance && stance_time > 0.0) { stage = 1; te = ts; }
+        else { stage = 2; gi = gb; idx = 0; te = ts; fin = t_end; }
+        continue;
+      }
+      if (!(te < t)) break;                  // lower_bound: an event equal to t has not happened yet
+      if (stage == 1) {                      // intermediate stance, the new template is tiled from t_switch + stance_time
+        mode = kStance; stage = 2; gi = gb; idx = 0; te = __dadd_rn(ts, stance_time); fin = t_end;
+      } else {                               // tiling (GaitSchedule.cpp:121-136): whole cycles while the last event is before the final time
+        const cmpc_gait& g = tab.g[gi];
+        if (idx == 0 && !(te < fin)) { mode = kStance; te = INFINITY; }   // default final phase
+        else {
+          mode = g.modes[idx];
+          te = __dadd_rn(te, __dsub_rn(g.switching_times[idx + 1], g.switching_times[idx]));
+          if (++idx == g.num_modes) idx = 0;
+        }
+      }
+    }
+    for (int i = 0; i < L; ++i) des_inputs[(size_t)b * L * (4 * N + 3) + i * (4 * N + 3) + j] = (mode & bit[i]) ? 1.0 : 0.0;
+  }
+}
+
 // FP64 throughput probe: 8 independent DFMA chains per thread.
 __global__ void fp64_peak_kernel(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1e-9, a2 = a0 + 2e-9, a3 = a0 + 3e-9;
@@ -1192,6 +1243,48 @@ int cmpc_fill_contact_tables(cmpc_handle* h, int B, const cmpc_gait* gaits, int 
   CUDA_TRY(h, cudaMemcpyAsync(h->d_kkt, t0, (size_t)B * 8, cudaMemcpyHostToDevice, s));
   CUDA_TRY(h, cudaMemcpyAsync(h->d_di, des_inputs, B * ndi * 8, cudaMemcpyHostToDevice, s));
   int rc = cmpc_fill_contact_tables_device(h, B, gaits, num_gaits, h->d_status, h->d_kkt, h->d_di);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(des_inputs, h->d_di, B * ndi * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  return CMPC_OK;
+}
+
+int cmpc_fill_contact_tables_switch_device(cmpc_handle* h, int B, const cmpc_gait* gaits, int num_gaits, const int32_t* d_gait_from,
+                                           const int32_t* d_gait_to, const double* d_t_tile, const double* d_t_switch, double stance_time,
+                                           const double* d_t0, double* d_des_inputs) {
+  if (!h || !h->ready) return fail(h, CMPC_ERR_STATE, "cmpc_fill_contact_tables_switch: call cmpc_setup first");
+  if (B < 0 || !d_gait_from || !d_gait_to || !d_t_tile || !d_t_switch || !d_t0 || !d_des_inputs) return fail(h, CMPC_ERR_ARG, "null buffer");
+  if (!(stance_time >= 0.0)) return fail(h, CMPC_ERR_ARG, "stance_time must be >= 0");
+  GaitTable tab;
+  int rc = check_gaits(h, gaits, num_gaits, &tab);
+  if (rc) return rc;
+  if (B == 0) return CMPC_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  gait_switch_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(h->dev, B, tab, d_gait_from, d_gait_to, d_t_tile, d_t_switch, stance_time, d_t0, d_des_inputs);
+  CUDA_TRY(h, cudaGetLastError());
+  return CMPC_OK;
+}
+
+int cmpc_fill_contact_tables_switch(cmpc_handle* h, int B, const cmpc_gait* gaits, int num_gaits, const int32_t* gait_from,
+                                    const int32_t* gait_to, const double* t_tile, const double* t_switch, double stance_time,
+                                    const double* t0, double* des_inputs) {
+  if (!h || !h->ready) return fail(h, CMPC_ERR_STATE, "cmpc_fill_contact_tables_switch: call cmpc_setup first");
+  if (B < 0 || B > h->max_batch) return fail(h, CMPC_ERR_STATE, "batch exceeds max_batch given to cmpc_setup");
+  if (!gait_from || !gait_to || !t_tile || !t_switch || !t0 || !des_inputs) return fail(h, CMPC_ERR_ARG, "null buffer");
+  if (B == 0) return CMPC_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t ndi = (size_t)h->cfg.num_legs * (4 * h->cfg.horizon + 3);
+  cudaStream_t s = h->stream;
+  // the handle's per-instance arrays double as staging: status / iters (int32), kkt and two rows of the force buffer (double)
+  double* d_tt = h->d_forces; double* d_ts = h->d_forces + h->max_batch;
+  if ((size_t)3 * h->cfg.num_legs * h->cfg.horizon < 2) return fail(h, CMPC_ERR_STATE, "staging too small");
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_status, gait_from, (size_t)B * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_iters, gait_to, (size_t)B * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_kkt, t0, (size_t)B * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaMemcpyAsync(d_tt, t_tile, (size_t)B * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaMemcpyAsync(d_ts, t_switch, (size_t)B * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_di, des_inputs, B * ndi * 8, cudaMemcpyHostToDevice, s));
+  int rc = cmpc_fill_contact_tables_switch_device(h, B, gaits, num_gaits, h->d_status, h->d_iters, d_tt, d_ts, stance_time, h->d_kkt, h->d_di);
   if (rc) return rc;
   CUDA_TRY(h, cudaMemcpyAsync(des_inputs, h->d_di, B * ndi * 8, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(h, cudaStreamSynchronize(s));

@@ -207,6 +207,24 @@ int cmpc_fill_contact_tables(cmpc_handle* h, int B, const cmpc_gait* gaits, int 
 int cmpc_fill_contact_tables_device(cmpc_handle* h, int B, const cmpc_gait* gaits, int num_gaits,
                                     const int32_t* d_gait_id, const double* d_t0, double* d_des_inputs);
 
+/* Gait SWITCH with the reference stack's stance-insertion rule: for instance b the contact flags at times
+ * t0[b] + j*dt come from the mode schedule that GaitSchedule produces when template gait_from[b], tiled from t_tile[b]
+ * (tileModeSequenceTemplate, ocs2_legged_robot/src/gait/GaitSchedule.cpp:107-137: initial STANCE, then whole template
+ * cycles with event times accumulated by repeated addition), is replaced at t_switch[b] by template gait_to[b] through
+ * insertModeSequenceTemplate (GaitSchedule.cpp:47-72): events at or after t_switch are erased, the mode active there runs
+ * on until t_switch, an intermediate STANCE phase of `stance_time` (phaseTransitionStanceTime) follows unless that mode
+ * already is STANCE, then gait_to is tiled from t_switch (+ stance_time).  The mode at time t is
+ * modeSequence[lower_bound(eventTimes, t)] (ModeSchedule::modeAtTime of ocs2_core, an un-vendored dependency: a step that
+ * lands exactly on an event keeps the earlier mode).  t_switch[b] = NaN or +-inf: no switch.  Leg order and FLY modes as
+ * in cmpc_fill_contact_tables.  Host buffers; `_device` takes device pointers for the per-instance arrays. */
+int cmpc_fill_contact_tables_switch(cmpc_handle* h, int B, const cmpc_gait* gaits, int num_gaits,
+                                    const int32_t* gait_from, const int32_t* gait_to, const double* t_tile,
+                                    const double* t_switch, double stance_time, const double* t0, double* des_inputs);
+int cmpc_fill_contact_tables_switch_device(cmpc_handle* h, int B, const cmpc_gait* gaits, int num_gaits,
+                                           const int32_t* d_gait_from, const int32_t* d_gait_to, const double* d_t_tile,
+                                           const double* d_t_switch, double stance_time, const double* d_t0,
+                                           double* d_des_inputs);
+
 /* Use an externally owned CUDA stream (cudaStream_t as void*) for all device work. */
 int cmpc_set_stream(cmpc_handle* h, void* cuda_stream);
 int cmpc_synchronize(cmpc_handle* h);

@@ -331,6 +331,52 @@ def gait_contact_table(mode_sequence, switching_times, t0, dt, N, L=4):
     return out
 
 
+def gait_switch_contact_table(gait_from, gait_to, t_tile, t_switch, stance_time, t0, dt, N, L=4):
+    """Contact table [L, N] of a mode schedule in which template gait_from = (mode_sequence, switching_times), tiled from
+    t_tile, is replaced at t_switch by gait_to with an intermediate stance phase.  The schedule is built EXPLICITLY, the
+    way the reference stack does: GaitSchedule::tileModeSequenceTemplate (GaitSchedule.cpp:107-137) and
+    GaitSchedule::insertModeSequenceTemplate (:47-72); mode at time t = modeSequence[lower_bound(eventTimes, t)]
+    (ocs2_core ModeSchedule::modeAtTime).  t_switch None / NaN: no switch."""
+    STANCE = 15
+
+    def tile(events, modes, tmpl, start, final):
+        seq, times = tmpl
+        seq = [MODE[x] if isinstance(x, str) else int(x) for x in seq]
+        if not seq:
+            return
+        if events and start <= events[-1]:
+            raise RuntimeError("The initial time for template-tiling is not greater than the last event time.")
+        events.append(start)
+        while events[-1] < final:
+            for i in range(len(seq)):
+                modes.append(seq[i])
+                events.append(events[-1] + (times[i + 1] - times[i]))
+        modes.append(STANCE)
+
+    t_end = t0 + N * dt
+    sw = t_switch is not None and np.isfinite(t_switch)
+    events, modes = [], [STANCE]
+    tile(events, modes, gait_from, float(t_tile), float(t_switch) if sw else t_end)
+    if sw:
+        index = int(np.searchsorted(events, t_switch, side="left"))
+        if index < len(events):
+            del events[index:]
+            del modes[index + 1:]
+        T = stance_time
+        if modes and modes[-1] == STANCE:
+            T = 0.0
+        if T > 0.0:
+            events.append(float(t_switch)); modes.append(STANCE)
+        tile(events, modes, gait_to, t_switch + T, t_end)
+    bit = [8, 4, 1, 2]  # {lf, rf, rh, lh} <- {LF, RF, RH, LH}
+    out = np.zeros((L, N))
+    for j in range(N):
+        k = int(np.searchsorted(events, t0 + j * dt, side="left"))
+        for i in range(L):
+            out[i, j] = 1.0 if modes[k] & bit[i] else 0.0
+    return out
+
+
 # ---------------------------------------------------------------------------- foot plan (a3 / a8)
 STEP_LB = np.array([-0.2, -0.2, -0.1])  # CentroidalMPC.cpp:30
 STEP_UB = np.array([0.2, 0.2, 0.1])     # CentroidalMPC.cpp:31

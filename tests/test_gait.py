@@ -128,3 +128,68 @@ def test_device_foot_plan_matches_mirror(pkg, wl):
     for b in range(B):
         assert np.abs(fp[b] - nm.foot_plan(cfg, st[b], di[b])).max() <= 1e-15
     m.close()
+
+
+def test_mirror_gait_switch_inserts_intermediate_stance_by_hand():
+    """GaitSchedule::insertModeSequenceTemplate (GaitSchedule.cpp:47-72) by hand, on a time grid that is exact in binary
+    (dt = 1/16): trot-like template [0, 0.375, 0.75] tiled from 0, switch to a pace-like template [0, 0.25, 0.5] at
+    t = 0.5 with 0.25 s of intermediate stance."""
+    trot = (["LF_RH", "RF_LH"], [0.0, 0.375, 0.75])
+    pace = (["LF_LH", "RF_RH"], [0.0, 0.25, 0.5])
+    dt = 0.0625
+    t = nm.gait_switch_contact_table(trot, pace, 0.0, 0.5, 0.25, 0.0, dt, 20)
+    # lower_bound: a step ON an event keeps the earlier mode.  j = 0 (t = 0 = the first event): the initial STANCE;
+    # j = 1..6 (.. 0.375): LF_RH; j = 7, 8 (0.4375, 0.5): RF_LH runs on until t_switch; j = 9..12 (.. 0.75): the inserted
+    # STANCE; the new template is tiled from 0.75: LF_LH on (0.75, 1.0], RF_RH on (1.0, 1.25]
+    exp_modes = [15] + [9] * 6 + [6] * 2 + [15] * 4 + [nm.MODE["LF_LH"]] * 4 + [nm.MODE["RF_RH"]] * 3
+    bit = [8, 4, 1, 2]
+    for i in range(4):
+        assert t[i].tolist() == [1.0 if m & bit[i] else 0.0 for m in exp_modes]
+    # switching while the running mode already is STANCE inserts no extra stance: stance template -> trot at 0.25
+    stance = (["STANCE"], [0.0, 0.5])
+    t2 = nm.gait_switch_contact_table(stance, trot, 0.0, 0.25, 0.25, 0.0, dt, 12)
+    exp2 = [15] * 5 + [9] * 6 + [6]
+    for i in range(4):
+        assert t2[i].tolist() == [1.0 if m & bit[i] else 0.0 for m in exp2]
+    # no switch: the plain tiling; a tiling that starts after the horizon is all initial stance
+    t3 = nm.gait_switch_contact_table(trot, pace, 0.0, None, 0.25, 0.0, dt, 16)
+    assert t3[0].tolist() == [1.0] + [1.0] * 6 + [0.0] * 6 + [1.0] * 3
+    assert nm.gait_switch_contact_table(trot, pace, 5.0, None, 0.25, 0.0, dt, 10).min() == 1.0
+
+
+@pytest.mark.gpu
+def test_device_gait_switch_bit_exact(pkg, orc, wl):
+    """cmpc_fill_contact_tables_switch against the explicit schedule construction of the mirror, bit for bit: random template
+    pairs, tiling starts, switch times (incl. steps that land exactly on events, switches before the tiling start, after
+    the horizon, NaN = none), stance times 0 / 0.15 / 0.4; the tables then solve with parity."""
+    names = ["stance", "trot", "standing_trot", "static_walk", "dynamic_walk", "amble", "standing_pace"]
+    gaits = [pkg.make_gait([nm.MODE[m] for m in nm.GAIT_INFO[n][0]], nm.GAIT_INFO[n][1]) for n in names]
+    for N, dt, Tst in ((10, 0.05, 0.4), (30, 0.02, 0.15), (16, 0.05, 0.0)):
+        cfg = wl.default_config(N, dt=dt)
+        B = 384
+        st, ds, di = wl.make_batch(cfg, B)
+        rng = np.random.default_rng(7 * N)
+        ga = rng.integers(0, len(names), B).astype(np.int32)
+        gb = rng.integers(0, len(names), B).astype(np.int32)
+        t0 = np.round(rng.uniform(0.0, 3.0, B) / dt) * dt            # steps on a dt grid: many land exactly on events
+        tt = t0 - np.round(rng.uniform(0.0, 2.0, B) / 0.05) * 0.05
+        ts = t0 + np.round(rng.uniform(-0.3, N * dt + 0.2, B) / 0.05) * 0.05
+        ts[::7] = np.nan
+        tt[5::11] = t0[5::11] + 0.3                                   # tiling starts inside the horizon
+        m = pkg.CentroidalMPC.from_dict(cfg)
+        m.SetupMPC(B)
+        out = m.FillContactTablesSwitch(gaits, ga, gb, tt, ts, Tst, t0, di)
+        exp = di.copy()
+        for b in range(B):
+            tab = nm.gait_switch_contact_table(nm.GAIT_INFO[names[ga[b]]], nm.GAIT_INFO[names[gb[b]]], tt[b],
+                                               None if np.isnan(ts[b]) else ts[b], Tst, t0[b], dt, N)
+            exp[b].reshape(4, 4 * N + 3)[:, :N] = tab
+        bad = np.nonzero((out != exp).any(axis=1))[0]
+        assert len(bad) == 0, (N, bad[:5], ga[bad[:5]], gb[bad[:5]], tt[bad[:5]], ts[bad[:5]], t0[bad[:5]])
+        assert (exp.reshape(B, 4, 4 * N + 3)[:, :, :N].sum(axis=1) > 0).all()   # these templates have no flight phase
+        res = m.UpdateMPCBatch(st, ds, out, want_lam=False)
+        ref = orc.solve_batch(m.cfg, st, ds, out, nthreads=8, want_lam=False)
+        assert np.array_equal(res["status"], ref["status"]) and (res["status"] == 0).all()
+        sc = np.abs(ref["forces"]).max(axis=1, keepdims=True)
+        assert (np.abs(res["forces"] - ref["forces"]) / sc).max() <= 1e-6
+        m.close()
