@@ -32,7 +32,8 @@ struct cmpc_handle {
   cudaEvent_t ev_span[4] = {}, ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {};
   // device buffers
   double *d_state = nullptr, *d_ds = nullptr, *d_di = nullptr, *d_forces = nullptr, *d_kkt = nullptr,
-         *d_lam = nullptr, *d_flog = nullptr, *d_hip = nullptr;
+         *d_lam = nullptr, *d_flog = nullptr, *d_hip = nullptr, *d_sqp = nullptr;
+  size_t flog_cap = 0;  // doubles of d_flog (cmpc_rollout's force log: grown on demand, kept across calls)
   int32_t *d_status = nullptr, *d_iters = nullptr, *d_iters_sum = nullptr, *d_status_or = nullptr;
   uint16_t* d_active = nullptr;
   void* d_stats = nullptr;
@@ -407,6 +408,34 @@ int fail(cmpc_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg;
   return code;
 }
+// Makes the handle's device current for the duration of an entry point and restores the caller's device afterwards
+// (a host thread may own handles on several GPUs or do its own CUDA work between calls).
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    const bool had = cudaGetDevice(&prev) == cudaSuccess;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+    if (!had) prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+// Temporary device buffer of the diagnostic / non-per-tick entry points: freed on every return path.
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8); }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+#define SET_DEVICE(h)                                                                          \
+  DeviceGuard device_guard_((h)->device);                                                      \
+  if (!device_guard_.ok) return fail(h, CMPC_ERR_CUDA, "cudaSetDevice failed")
+
 #define CUDA_TRY(h, expr)                                                                      \
   do {                                                                                         \
     cudaError_t e_ = (expr);                                                                   \
@@ -556,13 +585,6 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
   return launches;
 }
 
-SolveArgs base_args(cmpc_handle* h, int B) {
-  (void)h; (void)B;
-  SolveArgs a;
-  std::memset(&a, 0, sizeof(a));
-  return a;
-}
-
 // Fill a class plan: groups per CTA from the shared-memory budget, grid = one CTA per SM.
 int plan_class(cmpc_handle* h, cmpc_handle::ClassPlan& p, int W, int nbmax, int mode) {
   const int N = h->cfg.horizon, L = h->cfg.num_legs;
@@ -623,6 +645,34 @@ int collect_stats(cmpc_handle* h, int B, const int32_t* d_status, const int32_t*
 
 }  // namespace
 
+// Frees every device / pinned allocation, stream and event of the handle and returns it to the state after cmpc_create
+// (shared by cmpc_destroy and by a cmpc_setup that failed half-way).
+static void release_device_state(cmpc_handle* h) {
+  DeviceGuard g(h->device >= 0 ? h->device : 0);
+  cudaFree(h->d_state); cudaFree(h->d_ds); cudaFree(h->d_di); cudaFree(h->d_forces); cudaFree(h->d_kkt);
+  cudaFree(h->d_lam); cudaFree(h->d_hip); cudaFree(h->d_counts); cudaFree(h->d_perm); cudaFree(h->exp_plan.d_scratch);
+  for (auto& c : h->cls) { cudaFree(c.d_scratch); cudaFree(c.d_pre_scratch); c = cmpc_handle::ClassPlan(); }
+  h->exp_plan = cmpc_handle::ClassPlan();
+  cudaFree(h->d_ric_scratch); cudaFree(h->d_rip_scratch);
+  cudaFree(h->d_ready); cudaFreeHost(h->h_ready_vals); cudaFreeHost(h->h_error);
+  cudaFree(h->d_status); cudaFree(h->d_iters);
+  cudaFree(h->d_iters_sum); cudaFree(h->d_status_or); cudaFree(h->d_active); cudaFree(h->d_stats);
+  cudaFree(h->d_flog); cudaFree(h->d_sqp);
+  h->d_state = h->d_ds = h->d_di = h->d_forces = h->d_kkt = h->d_lam = h->d_flog = h->d_hip = h->d_sqp = nullptr;
+  h->d_status = h->d_iters = h->d_iters_sum = h->d_status_or = nullptr; h->d_active = nullptr; h->d_stats = nullptr;
+  h->d_counts = h->d_perm = nullptr; h->d_ric_scratch = h->d_rip_scratch = nullptr;
+  h->d_ready = nullptr; h->h_ready_vals = nullptr; h->h_error = nullptr; h->h_error_dev = nullptr;
+  for (auto& e : h->ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+  for (auto& e : h->ev_span) if (e) { cudaEventDestroy(e); e = nullptr; }
+  for (auto& e : h->ev_in) if (e) { cudaEventDestroy(e); e = nullptr; }
+  for (auto& e : h->ev_k) if (e) { cudaEventDestroy(e); e = nullptr; }
+  if (h->s_in) { cudaStreamDestroy(h->s_in); h->s_in = nullptr; }
+  if (h->s_out) { cudaStreamDestroy(h->s_out); h->s_out = nullptr; }
+  if (h->own_stream && h->stream) { cudaStreamDestroy(h->stream); h->stream = nullptr; h->own_stream = false; }
+  h->ric_used = h->rip_used = false;
+  h->ready = false; h->max_batch = 0; h->flog_cap = 0;
+}
+
 extern "C" {
 
 const char* cmpc_version(void) { return "cmpc_b200 0.3 (sm_100a)"; }
@@ -651,15 +701,9 @@ int cmpc_create(const cmpc_config* cfg, cmpc_handle** out) {
   return CMPC_OK;
 }
 
-int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
-  if (!h || max_batch < 1) return fail(h, CMPC_ERR_ARG, "cmpc_setup: bad arguments");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-    return fail(h, CMPC_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
-  if (device < 0 || device >= ndev) return fail(h, CMPC_ERR_ARG, "cmpc_setup: device out of range");
-  CUDA_TRY(h, cudaSetDevice(device));
-  if (h->ready) return fail(h, CMPC_ERR_STATE, "cmpc_setup called twice");
+static int setup_impl(cmpc_handle* h, int max_batch, int device) {
   h->device = device;
+  SET_DEVICE(h);
   cudaDeviceProp prop;
   CUDA_TRY(h, cudaGetDeviceProperties(&prop, device));
   h->num_sms = prop.multiProcessorCount;
@@ -681,6 +725,7 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
   CUDA_TRY(h, cudaMalloc(&h->d_kkt, B * 8));
   CUDA_TRY(h, cudaMalloc(&h->d_lam, B * 10 * L * N * 8));
   CUDA_TRY(h, cudaMalloc(&h->d_hip, B * 3 * L * 8));
+  CUDA_TRY(h, cudaMalloc(&h->d_sqp, B * (ndi + 17) * 8));   // cmpc_solve_batch_sqp: original inputs + defects (sqp_iters <= 16)
   CUDA_TRY(h, cudaMalloc(&h->d_status, B * 4));
   CUDA_TRY(h, cudaMalloc(&h->d_iters, B * 4));
   CUDA_TRY(h, cudaMalloc(&h->d_iters_sum, B * 4));
@@ -704,7 +749,9 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
   {
     const int nbfull = L * N;
     const int cap[kNumClasses] = {20, 42, 64, nbfull};
-    const int Wc[kNumClasses] = {getenv("CMPC_W0") ? atoi(getenv("CMPC_W0")) : 1, 4, 8, 8};
+    int w0 = getenv("CMPC_W0") ? atoi(getenv("CMPC_W0")) : 1;   // experiment knob: warps per instance of size class 0
+    if (w0 != 1 && w0 != 2 && w0 != 4 && w0 != 8) w0 = 1;        // (only these kernel variants exist)
+    const int Wc[kNumClasses] = {w0, 4, 8, 8};
     int b[kNumClasses];
     int lower = 0;
     for (int c = 0; c < kNumClasses; ++c) {
@@ -770,6 +817,22 @@ int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
   return CMPC_OK;
 }
 
+int cmpc_setup(cmpc_handle* h, int max_batch, int device) {
+  if (!h || max_batch < 1) return fail(h, CMPC_ERR_ARG, "cmpc_setup: bad arguments");
+  if (h->ready) return fail(h, CMPC_ERR_STATE, "cmpc_setup called twice");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(h, CMPC_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(h, CMPC_ERR_ARG, "cmpc_setup: device out of range");
+  const int rc = setup_impl(h, max_batch, device);
+  if (rc != CMPC_OK) {  // nothing half-allocated survives a failed setup: a retry starts from a clean handle
+    const std::string msg = h->err;
+    release_device_state(h);
+    h->err = msg;
+  }
+  return rc;
+}
+
 int cmpc_update_weights(cmpc_handle* h, const double* w, int n) {
   if (!h || !w || n != 9 + 9 * h->cfg.num_legs) return fail(h, CMPC_ERR_ARG, "cmpc_update_weights: need 9+9*num_legs weights");
   cmpc_config c = h->cfg;
@@ -782,6 +845,12 @@ int cmpc_update_weights(cmpc_handle* h, const double* w, int n) {
 
 int cmpc_set_stream(cmpc_handle* h, void* s) {
   if (!h) return CMPC_ERR_ARG;
+  if (h->ready && s) {  // the stream must live on the handle's device (before cmpc_setup it is checked by the first launch)
+    int dv = -1;
+    if (cudaStreamGetDevice((cudaStream_t)s, &dv) == cudaSuccess && dv != h->device)
+      return fail(h, CMPC_ERR_ARG, "cmpc_set_stream: the stream belongs to another device");
+    cudaGetLastError();
+  }
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   h->stream = (cudaStream_t)s;
   h->own_stream = false;
@@ -801,8 +870,8 @@ int cmpc_solve_batch_device(cmpc_handle* h, int B, const double* d_state, const 
   if (B < 0 || B > h->max_batch) return fail(h, CMPC_ERR_STATE, "batch exceeds max_batch given to cmpc_setup");
   if (!d_state || !d_des_state || !d_des_inputs || !d_forces || !d_status) return fail(h, CMPC_ERR_ARG, "null buffer");
   if (B == 0) { if (stats) std::memset(stats, 0, sizeof(*stats)); return CMPC_OK; }
-  CUDA_TRY(h, cudaSetDevice(h->device));
-  SolveArgs a = base_args(h, B);
+  SET_DEVICE(h);
+  SolveArgs a = SolveArgs();
   a.state = d_state; a.des_state = d_des_state; a.des_inputs = d_des_inputs;
   a.forces = d_forces; a.status = d_status;
   a.iters = d_iters ? d_iters : (stats ? h->d_iters : nullptr);
@@ -831,7 +900,7 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
   if (B < 0 || B > h->max_batch) return fail(h, CMPC_ERR_STATE, "batch exceeds max_batch given to cmpc_setup");
   if (!state || !des_state || !des_inputs || !forces || !status) return fail(h, CMPC_ERR_ARG, "null buffer");
   if (B == 0) { if (stats) std::memset(stats, 0, sizeof(*stats)); return CMPC_OK; }
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  SET_DEVICE(h);
   const int N = h->cfg.horizon, L = h->cfg.num_legs;
   const size_t ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = (size_t)L * (4 * N + 3), nf = (size_t)3 * L * N;
   cudaStream_t s = h->stream;
@@ -884,7 +953,7 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
   // Outputs: written in place over the bus when every output buffer is pinned (posted writes,
   // overlapped with the remaining compute); otherwise device buffers and one copy back.
   const bool zc_out = out_mapped && h->e2e_mode != 2 && !duplex;
-  SolveArgs a = base_args(h, B);
+  SolveArgs a = SolveArgs();
   a.state = zc_in ? (const double*)dp[0] : h->d_state;
   a.des_state = zc_in ? (const double*)dp[1] : h->d_ds;
   a.des_inputs = zc_in ? (const double*)dp[2] : h->d_di;
@@ -1013,17 +1082,18 @@ int cmpc_build_batch(cmpc_handle* h, int B, const double* state, const double* d
   if (B < 0 || B > h->max_batch) return fail(h, CMPC_ERR_STATE, "batch exceeds max_batch given to cmpc_setup");
   if (!state || !des_state || !des_inputs || !H || !g || !status) return fail(h, CMPC_ERR_ARG, "null buffer");
   if (B == 0) return CMPC_OK;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  SET_DEVICE(h);
   const int N = h->cfg.horizon, L = h->cfg.num_legs;
   const size_t ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = (size_t)L * (4 * N + 3), p = (size_t)3 * L * N;
   cudaStream_t s = h->stream;
-  double *dH = nullptr, *dg = nullptr;  // test/diagnostic path: temporary buffers are fine here
-  CUDA_TRY(h, cudaMalloc(&dH, (size_t)B * p * p * 8));
-  CUDA_TRY(h, cudaMalloc(&dg, (size_t)B * p * 8));
+  DevBuf bH, bg;  // test/diagnostic path: temporary buffers, released on every return path
+  CUDA_TRY(h, bH.alloc((size_t)B * p * p * 8));
+  CUDA_TRY(h, bg.alloc((size_t)B * p * 8));
+  double *dH = bH.as<double>(), *dg = bg.as<double>();
   CUDA_TRY(h, cudaMemcpyAsync(h->d_state, state, B * ns * 8, cudaMemcpyHostToDevice, s));
   CUDA_TRY(h, cudaMemcpyAsync(h->d_ds, des_state, B * nds * 8, cudaMemcpyHostToDevice, s));
   CUDA_TRY(h, cudaMemcpyAsync(h->d_di, des_inputs, B * ndi * 8, cudaMemcpyHostToDevice, s));
-  SolveArgs a = base_args(h, B);
+  SolveArgs a = SolveArgs();
   a.state = h->d_state; a.des_state = h->d_ds; a.des_inputs = h->d_di;
   a.status = h->d_status; a.Hout = dH; a.gout = dg; a.forces = h->d_forces;
   a.count = nullptr; a.count_imm = B; a.perm = nullptr; a.work = h->d_counts + kNumClasses;
@@ -1035,7 +1105,6 @@ int cmpc_build_batch(cmpc_handle* h, int B, const double* state, const double* d
     cudaMemcpyAsync(status, h->d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, s);
   }
   cudaError_t e = cudaStreamSynchronize(s);
-  cudaFree(dH); cudaFree(dg);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, cudaGetErrorString(e));
   return CMPC_OK;
@@ -1049,13 +1118,13 @@ int cmpc_stage_step_batch(cmpc_handle* h, int B, int mode, const double* state, 
   if ((mode != 1 && mode != 2) || !state || !des_state || !des_inputs || !hess || !rhs || !d_fused || !d_resolve || !grad)
     return fail(h, CMPC_ERR_ARG, "cmpc_stage_step_batch: bad arguments");
   if (B == 0) return CMPC_OK;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  SET_DEVICE(h);
   const int N = h->cfg.horizon, L = h->cfg.num_legs;
   const size_t ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = (size_t)L * (4 * N + 3), nf = (size_t)3 * L * N, nh = (size_t)6 * L * N;
   cudaStream_t s = h->stream;
-  double* tmp = nullptr;  // diagnostic path: a temporary buffer is fine here
-  CUDA_TRY(h, cudaMalloc(&tmp, (size_t)B * (nh + 4 * nf) * 8));
-  double *dh = tmp, *dr = dh + (size_t)B * nh, *o1 = dr + (size_t)B * nf, *o2 = o1 + (size_t)B * nf, *o3 = o2 + (size_t)B * nf;
+  DevBuf tbuf;  // diagnostic path: a temporary buffer, released on every return path
+  CUDA_TRY(h, tbuf.alloc((size_t)B * (nh + 4 * nf) * 8));
+  double *tmp = tbuf.as<double>(), *dh = tmp, *dr = dh + (size_t)B * nh, *o1 = dr + (size_t)B * nf, *o2 = o1 + (size_t)B * nf, *o3 = o2 + (size_t)B * nf;
   cudaMemcpyAsync(h->d_state, state, B * ns * 8, cudaMemcpyHostToDevice, s);
   cudaMemcpyAsync(h->d_ds, des_state, B * nds * 8, cudaMemcpyHostToDevice, s);
   cudaMemcpyAsync(h->d_di, des_inputs, B * ndi * 8, cudaMemcpyHostToDevice, s);
@@ -1072,7 +1141,6 @@ int cmpc_stage_step_batch(cmpc_handle* h, int B, int mode, const double* state, 
     cudaMemcpyAsync(grad, o3, (size_t)B * nf * 8, cudaMemcpyDeviceToHost, s);
     e = cudaStreamSynchronize(s);
   }
-  cudaFree(tmp);
   if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, std::string("cmpc_stage_step_batch: ") + cudaGetErrorString(e));
   return CMPC_OK;
 }
@@ -1082,7 +1150,7 @@ int cmpc_rollout(cmpc_handle* h, int B, int ticks, int warm_start, double* state
   if (!h || !h->ready) return fail(h, CMPC_ERR_STATE, "cmpc_rollout: call cmpc_setup first");
   if (B < 1 || B > h->max_batch || ticks < 1) return fail(h, CMPC_ERR_ARG, "cmpc_rollout: bad B or ticks");
   if (!state || !des_state || !des_inputs) return fail(h, CMPC_ERR_ARG, "null buffer");
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  SET_DEVICE(h);
   const int N = h->cfg.horizon, L = h->cfg.num_legs;
   const size_t ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = (size_t)L * (4 * N + 3);
   cudaStream_t s = h->stream;
@@ -1092,8 +1160,16 @@ int cmpc_rollout(cmpc_handle* h, int B, int ticks, int warm_start, double* state
   CUDA_TRY(h, cudaMemsetAsync(h->d_iters_sum, 0, (size_t)B * 4, s));
   CUDA_TRY(h, cudaMemsetAsync(h->d_status_or, 0, (size_t)B * 4, s));
   double* d_flog = nullptr;
-  if (force_log) CUDA_TRY(h, cudaMalloc(&d_flog, (size_t)ticks * B * 3 * L * 8));
-  SolveArgs a = base_args(h, B);
+  if (force_log) {  // the log buffer is kept across calls and only grows (no allocation on repeated roll-outs of the same size)
+    const size_t need = (size_t)ticks * B * 3 * L;
+    if (need > h->flog_cap) {
+      cudaFree(h->d_flog); h->d_flog = nullptr; h->flog_cap = 0;
+      CUDA_TRY(h, cudaMalloc(&h->d_flog, need * 8));
+      h->flog_cap = need;
+    }
+    d_flog = h->d_flog;
+  }
+  SolveArgs a = SolveArgs();
   a.state = h->d_state; a.des_state = h->d_ds; a.des_inputs = h->d_di;
   a.forces = h->d_forces; a.status = h->d_status; a.iters = h->d_iters; a.kkt = h->d_kkt;
   a.active = h->d_active;
@@ -1124,7 +1200,6 @@ int cmpc_rollout(cmpc_handle* h, int B, int ticks, int warm_start, double* state
     if (status_or) cudaMemcpyAsync(status_or, h->d_status_or, (size_t)B * 4, cudaMemcpyDeviceToHost, s);
   }
   cudaError_t e = cudaStreamSynchronize(s);
-  if (d_flog) cudaFree(d_flog);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, cudaGetErrorString(e));
   if (stats) {
@@ -1143,7 +1218,7 @@ int cmpc_foot_plan_batch(cmpc_handle* h, int B, const double* state, const doubl
   if (B < 0 || B > h->max_batch) return fail(h, CMPC_ERR_STATE, "batch exceeds max_batch given to cmpc_setup");
   if (!state || !des_inputs || !foot_pos) return fail(h, CMPC_ERR_ARG, "null buffer");
   if (B == 0) return CMPC_OK;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  SET_DEVICE(h);
   const int N = h->cfg.horizon, L = h->cfg.num_legs;
   const size_t ns = 9 + 3 * L, ndi = (size_t)L * (4 * N + 3), nfp = (size_t)3 * L * (N + 1);
   cudaStream_t s = h->stream;
@@ -1166,18 +1241,17 @@ int cmpc_solve_batch_sqp(cmpc_handle* h, int B, int sqp_iters, const double* sta
   if (sqp_iters < 0 || sqp_iters > 16) return fail(h, CMPC_ERR_ARG, "sqp_iters must be 0..16");
   if (!state || !des_state || !des_inputs || !forces || !status) return fail(h, CMPC_ERR_ARG, "null buffer");
   if (B == 0) return CMPC_OK;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  SET_DEVICE(h);
   const int N = h->cfg.horizon, L = h->cfg.num_legs;
   const size_t ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = (size_t)L * (4 * N + 3), nf = (size_t)3 * L * N;
   cudaStream_t s = h->stream;
-  double *d_di0 = nullptr, *d_def = nullptr;  // not on the per-tick path: temporaries are fine here
-  CUDA_TRY(h, cudaMalloc(&d_di0, B * ndi * 8));
-  CUDA_TRY(h, cudaMalloc(&d_def, (size_t)B * (sqp_iters + 1) * 8));
+  double* d_di0 = h->d_sqp;                              // [max_batch][ndi] original desired inputs, allocated by cmpc_setup
+  double* d_def = h->d_sqp + (size_t)h->max_batch * ndi;  // [max_batch][17] defects
   cudaMemcpyAsync(h->d_state, state, B * ns * 8, cudaMemcpyHostToDevice, s);
   cudaMemcpyAsync(h->d_ds, des_state, B * nds * 8, cudaMemcpyHostToDevice, s);
   cudaMemcpyAsync(h->d_di, des_inputs, B * ndi * 8, cudaMemcpyHostToDevice, s);
   cudaMemcpyAsync(d_di0, h->d_di, B * ndi * 8, cudaMemcpyDeviceToDevice, s);
-  SolveArgs a = base_args(h, B);
+  SolveArgs a = SolveArgs();
   a.state = h->d_state; a.des_state = h->d_ds; a.des_inputs = h->d_di;
   a.forces = h->d_forces; a.status = h->d_status; a.iters = h->d_iters; a.kkt = h->d_kkt;
   int rc = CMPC_OK;
@@ -1193,7 +1267,6 @@ int cmpc_solve_batch_sqp(cmpc_handle* h, int B, int sqp_iters, const double* sta
     if (defect) cudaMemcpyAsync(defect, d_def, (size_t)B * (sqp_iters + 1) * 8, cudaMemcpyDeviceToHost, s);
   }
   cudaError_t e = cudaStreamSynchronize(s);
-  cudaFree(d_di0); cudaFree(d_def);
   if (rc < 0) return rc;
   if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, cudaGetErrorString(e));
   return CMPC_OK;
@@ -1222,7 +1295,7 @@ int cmpc_fill_contact_tables_device(cmpc_handle* h, int B, const cmpc_gait* gait
   int rc = check_gaits(h, gaits, num_gaits, &tab);
   if (rc) return rc;
   if (B == 0) return CMPC_OK;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  SET_DEVICE(h);
   const int total = B * h->cfg.horizon;
   gait_kernel<<<(total + 255) / 256, 256, 0, h->stream>>>(h->dev, B, tab, d_gait_id, d_t0, d_des_inputs);
   CUDA_TRY(h, cudaGetLastError());
@@ -1235,7 +1308,7 @@ int cmpc_fill_contact_tables(cmpc_handle* h, int B, const cmpc_gait* gaits, int 
   if (B < 0 || B > h->max_batch) return fail(h, CMPC_ERR_STATE, "batch exceeds max_batch given to cmpc_setup");
   if (!gait_id || !t0 || !des_inputs) return fail(h, CMPC_ERR_ARG, "null buffer");
   if (B == 0) return CMPC_OK;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  SET_DEVICE(h);
   const size_t ndi = (size_t)h->cfg.num_legs * (4 * h->cfg.horizon + 3);
   cudaStream_t s = h->stream;
   // the handle's per-instance scratch arrays double as staging: status (int32) and kkt (double)
@@ -1259,7 +1332,7 @@ int cmpc_fill_contact_tables_switch_device(cmpc_handle* h, int B, const cmpc_gai
   int rc = check_gaits(h, gaits, num_gaits, &tab);
   if (rc) return rc;
   if (B == 0) return CMPC_OK;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  SET_DEVICE(h);
   gait_switch_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(h->dev, B, tab, d_gait_from, d_gait_to, d_t_tile, d_t_switch, stance_time, d_t0, d_des_inputs);
   CUDA_TRY(h, cudaGetLastError());
   return CMPC_OK;
@@ -1272,7 +1345,7 @@ int cmpc_fill_contact_tables_switch(cmpc_handle* h, int B, const cmpc_gait* gait
   if (B < 0 || B > h->max_batch) return fail(h, CMPC_ERR_STATE, "batch exceeds max_batch given to cmpc_setup");
   if (!gait_from || !gait_to || !t_tile || !t_switch || !t0 || !des_inputs) return fail(h, CMPC_ERR_ARG, "null buffer");
   if (B == 0) return CMPC_OK;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  SET_DEVICE(h);
   const size_t ndi = (size_t)h->cfg.num_legs * (4 * h->cfg.horizon + 3);
   cudaStream_t s = h->stream;
   // the handle's per-instance arrays double as staging: status / iters (int32), kkt and two rows of the force buffer (double)
@@ -1293,44 +1366,30 @@ int cmpc_fill_contact_tables_switch(cmpc_handle* h, int B, const cmpc_gait* gait
 
 int cmpc_measure_fp64_peak(cmpc_handle* h, double* tflops) {
   if (!h || !h->ready || !tflops) return fail(h, CMPC_ERR_STATE, "not set up");
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  SET_DEVICE(h);
   const int blocks = h->num_sms * 8, threads = 256, iters = 4096;
-  double* d = nullptr;
-  CUDA_TRY(h, cudaMalloc(&d, (size_t)blocks * threads * 8));
+  DevBuf dbuf;
+  CUDA_TRY(h, dbuf.alloc((size_t)blocks * threads * 8));
+  double* d = dbuf.as<double>();
   double best = 0;
   for (int rep = 0; rep < 5; ++rep) {
     cudaEventRecord(h->ev[0], h->stream);
     fp64_peak_kernel<<<blocks, threads, 0, h->stream>>>(d, iters);
     cudaEventRecord(h->ev[1], h->stream);
     cudaError_t e = cudaStreamSynchronize(h->stream);
-    if (e != cudaSuccess) { cudaFree(d); return fail(h, CMPC_ERR_CUDA, cudaGetErrorString(e)); }
+    if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, cudaGetErrorString(e));
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
     const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
     if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
   }
-  cudaFree(d);
   *tflops = best;
   return CMPC_OK;
 }
 
 void cmpc_destroy(cmpc_handle* h) {
   if (!h) return;
-  if (h->device >= 0) cudaSetDevice(h->device);
-  cudaFree(h->d_state); cudaFree(h->d_ds); cudaFree(h->d_di); cudaFree(h->d_forces); cudaFree(h->d_kkt);
-  cudaFree(h->d_lam); cudaFree(h->d_hip); cudaFree(h->d_counts); cudaFree(h->d_perm); cudaFree(h->exp_plan.d_scratch);
-  for (auto& c : h->cls) { cudaFree(c.d_scratch); cudaFree(c.d_pre_scratch); }
-  cudaFree(h->d_ric_scratch); cudaFree(h->d_rip_scratch);
-  cudaFree(h->d_ready); cudaFreeHost(h->h_ready_vals); cudaFreeHost(h->h_error);
-  cudaFree(h->d_status); cudaFree(h->d_iters);
-  cudaFree(h->d_iters_sum); cudaFree(h->d_status_or); cudaFree(h->d_active); cudaFree(h->d_stats);
-  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
-  for (auto& e : h->ev_span) if (e) cudaEventDestroy(e);
-  for (auto& e : h->ev_in) if (e) cudaEventDestroy(e);
-  for (auto& e : h->ev_k) if (e) cudaEventDestroy(e);
-  if (h->s_in) cudaStreamDestroy(h->s_in);
-  if (h->s_out) cudaStreamDestroy(h->s_out);
-  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  release_device_state(h);
   delete h;
 }
 

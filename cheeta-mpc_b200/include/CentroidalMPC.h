@@ -45,6 +45,12 @@ struct CentroidalMPCOptions {
   int polish = 1;        // active-set polish after the interior-point iteration
   int max_iter = 50;
   double ipm_tol = 1e-9;
+  // Model knob.  0 (default): the convex QP with the lever arms frozen at des_foot_pos - des_com_pos.  k > 0: k
+  // re-linearisations of the arms about the centre-of-mass path of the previous solution (cmpc_solve_batch_sqp), which
+  // makes the QP's dynamics reproduce the reference's nonlinear Euler plant (CentroidalMPC.cpp:85-92); on the reference
+  // driver's fixture the forces then sit 0.012 % from the optimum of the reference's own NLP instead of 0.6 %
+  // (tests/golden/make_nlp_pin.py).  Costs one more solve per iteration.
+  int sqp_iters = 0;
 };
 
 class CentroidalMPC {
@@ -66,7 +72,7 @@ class CentroidalMPC {
   CentroidalMPC(double mass, int num_legs, int predict_horizon, double time_step, const double* weights,
                 size_t n_weights, const double* mu, size_t n_mu, IPOPT_SOLVER = IPOPT_SOLVER::MA97, int device = 0,
                 const Options& opt = Options())
-      : num_legs_(num_legs), horizon_(predict_horizon), device_(device) {
+      : num_legs_(num_legs), horizon_(predict_horizon), device_(device), sqp_iters_(opt.sqp_iters) {
     if (!(mass > 0) || num_legs <= 0 || predict_horizon <= 0)
       throw std::runtime_error("CentroidalMPC: mass > 0 && num_legs > 0 && predict_horizon > 0 required");
     if (n_mu != (size_t)num_legs) throw std::runtime_error("CentroidalMPC: mu.size() == num_legs required");
@@ -83,18 +89,28 @@ class CentroidalMPC {
       : CentroidalMPC(mass, num_legs, predict_horizon, time_step, weights.data(), weights.size(), mu.data(), mu.size(), s, device, opt) {}
 #ifdef CMPC_HAVE_EIGEN
   CentroidalMPC(double mass, int num_legs, int predict_horizon, double time_step, const Eigen::VectorXd& weights,
-                const Eigen::VectorXd& mu, IPOPT_SOLVER s = IPOPT_SOLVER::MA97)
-      : CentroidalMPC(mass, num_legs, predict_horizon, time_step, weights.data(), (size_t)weights.size(), mu.data(), (size_t)mu.size(), s) {}
+                const Eigen::VectorXd& mu, IPOPT_SOLVER s = IPOPT_SOLVER::MA97, int device = 0, const Options& opt = Options())
+      : CentroidalMPC(mass, num_legs, predict_horizon, time_step, weights.data(), (size_t)weights.size(), mu.data(), (size_t)mu.size(), s, device, opt) {}
 #endif
   ~CentroidalMPC() { cmpc_destroy(h_); }
 
-  /* reference SetupMPC() (CentroidalMPC.cpp:102): one-off device allocation for up to max_batch instances */
+  /* reference SetupMPC() (CentroidalMPC.cpp:102): one-off device allocation for up to max_batch instances.  Calling it
+   * again with a larger batch re-creates the handle (device buffers are sized once per handle). */
   void SetupMPC(int max_batch = 1) {
+    if (max_batch_ > 0) {
+      if (max_batch <= max_batch_) return;
+      cmpc_destroy(h_);
+      h_ = nullptr;
+      if (cmpc_create(&cfg_, &h_) != CMPC_OK) throw std::runtime_error("CentroidalMPC: invalid constructor arguments");
+    }
     check(cmpc_setup(h_, max_batch, device_));
     max_batch_ = max_batch;
   }
   /* reference NonlinearMPC::UpdateWeights */
-  void UpdateWeights(const double* w, size_t n) { check(cmpc_update_weights(h_, w, (int)n)); }
+  void UpdateWeights(const double* w, size_t n) {
+    check(cmpc_update_weights(h_, w, (int)n));
+    for (size_t i = 0; i < n && i < (size_t)CMPC_NUM_WEIGHTS; ++i) cfg_.weights[i] = w[i];  // survives a handle re-creation
+  }
   void UpdateWeights(const std::vector<double>& w) { UpdateWeights(w.data(), w.size()); }
 
   size_t state_size() const { return 9 + 3 * (size_t)num_legs_; }
@@ -134,12 +150,17 @@ class CentroidalMPC {
 
   /* B instances, instance-major host buffers (layouts in include/cmpc.h) */
   BatchResult UpdateMPCBatch(int B, const double* states, const double* des_states, const double* des_inputs) {
-    if (max_batch_ == 0) SetupMPC(B);
+    if (B > max_batch_) SetupMPC(B);   // first call, or a batch larger than any before: (re)allocate
     BatchResult r;
     r.forces.resize((size_t)B * forces_size());
     r.status.resize(B); r.iters.resize(B); r.kkt.resize(B);
-    check(cmpc_solve_batch(h_, B, states, des_states, des_inputs, r.forces.data(), r.status.data(), r.iters.data(),
-                           r.kkt.data(), nullptr, nullptr, &r.stats));
+    if (sqp_iters_ > 0) {
+      r.stats = cmpc_stats();
+      check(cmpc_solve_batch_sqp(h_, B, sqp_iters_, states, des_states, des_inputs, r.forces.data(), r.status.data(), nullptr));
+    } else {
+      check(cmpc_solve_batch(h_, B, states, des_states, des_inputs, r.forces.data(), r.status.data(), r.iters.data(),
+                             r.kkt.data(), nullptr, nullptr, &r.stats));
+    }
     return r;
   }
 
@@ -152,6 +173,6 @@ class CentroidalMPC {
   }
   cmpc_config cfg_{};
   cmpc_handle* h_ = nullptr;
-  int num_legs_, horizon_, device_, max_batch_ = 0;
+  int num_legs_, horizon_, device_, sqp_iters_ = 0, max_batch_ = 0;
   double current_time_ = 0.0;
 };

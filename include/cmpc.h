@@ -104,7 +104,10 @@ int cmpc_create(const cmpc_config* cfg, cmpc_handle** out);
 
 /* Replaces SetupMPC() (CentroidalMPC.cpp:102-276): one-off allocation of device buffers
  * for up to max_batch instances on CUDA device `device`, upload of constants. No
- * allocation happens in the solve calls afterwards. */
+ * allocation happens afterwards in cmpc_solve_batch[_device], cmpc_solve_batch_sqp, cmpc_foot_plan_batch or the
+ * contact-table calls; cmpc_rollout grows its force-log buffer on demand and keeps it; the parity entries
+ * (cmpc_build_batch, cmpc_stage_step_batch) and cmpc_measure_fp64_peak use temporaries.  A failed setup releases
+ * everything it had allocated, so it can be retried.  Every entry point restores the caller's current device. */
 int cmpc_setup(cmpc_handle* h, int max_batch, int device);
 
 /* Replaces NonlinearMPC::UpdateWeights (NonlinearMPC.h:103-105). n = 9+9*num_legs. */
@@ -225,7 +228,9 @@ int cmpc_fill_contact_tables_switch_device(cmpc_handle* h, int B, const cmpc_gai
                                            const double* d_t_switch, double stance_time, const double* d_t0,
                                            double* d_des_inputs);
 
-/* Use an externally owned CUDA stream (cudaStream_t as void*) for all device work. */
+/* Use an externally owned CUDA stream (cudaStream_t as void*) for all device work.  The stream must belong to the
+ * handle's device (checked once the handle is set up).  NULL before cmpc_setup means "let the library create its own
+ * non-blocking stream"; NULL after cmpc_setup selects the legacy default stream. */
 int cmpc_set_stream(cmpc_handle* h, void* cuda_stream);
 int cmpc_synchronize(cmpc_handle* h);
 
