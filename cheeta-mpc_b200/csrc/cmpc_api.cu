@@ -548,37 +548,79 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
   int launches = 0;
   const bool presolve = h->cfg.presolve && h->cfg.polish;
   const bool router = presolve && h->cls[0].used && presolve_kind(h, 0) == 1;
+  const bool warm = a.warm_active != nullptr;
   if (!router) {
     if (ready) return fail(h, CMPC_ERR_STATE, "progressive inputs need the presolve router");
     classify_kernel<<<(B + 31) / 32, 1024, 0, h->stream>>>(h->dev, B, a.des_inputs, h->bounds, h->d_counts, h->d_perm);
     ++launches;
   }
+  a.nlists = 0;
+  // per class: the list it starts from (classify / router output) and, after a presolve, the list of what was deferred
+  const int32_t* in_perm[kNumClasses]; const int32_t* in_count[kNumClasses]; int32_t* in_work[kNumClasses];
+  for (int c = 0; c < kNumClasses; ++c) {
+    in_perm[c] = h->d_perm + (size_t)c * B;
+    in_count[c] = h->d_counts + c;
+    in_work[c] = h->d_counts + kNumClasses + c;
+  }
+  // ---- presolves: the dense kernel per class (class 0 = the batch's router), then ONE stage-wise launch over the other classes
+  SolveArgs ric = a;
   for (int c = 0; c < kNumClasses; ++c) {
     if (!h->cls[c].used) continue;
-    a.perm = h->d_perm + (size_t)c * B;
-    a.count = h->d_counts + c;
-    a.work = h->d_counts + kNumClasses + c;
-    a.route = 0; a.ready = nullptr;
     const int kind = presolve_kind(h, c);
-    if (kind) {
-      a.fail_perm = h->d_perm + (size_t)(kNumClasses + c) * h->max_batch;
-      a.fail_count = h->d_counts + 2 * kNumClasses + c;
+    if (!kind) continue;
+    int32_t* fperm = h->d_perm + (size_t)(kNumClasses + c) * h->max_batch;
+    int32_t* fcount = h->d_counts + 2 * kNumClasses + c;
+    if (kind == 1) {
+      SolveArgs p = a;
+      p.perm = in_perm[c]; p.count = in_count[c]; p.work = in_work[c];
+      p.fail_perm = fperm; p.fail_count = fcount;
+      p.route = 0; p.ready = nullptr;
       if (router && c == 0) {
-        a.perm = nullptr; a.count = nullptr; a.count_imm = B;
-        a.route = 1; a.route_b1 = h->bounds.y; a.route_b2 = h->bounds.z;
-        a.route_perm = h->d_perm; a.route_counts = h->d_counts; a.route_stride = B;
-        a.ready = ready; a.ready_chunk = ready_chunk; a.error_flag = h->h_error_dev;
+        p.perm = nullptr; p.count = nullptr; p.count_imm = B;
+        p.route = 1; p.route_b1 = h->bounds.y; p.route_b2 = h->bounds.z;
+        p.route_perm = h->d_perm; p.route_counts = h->d_counts; p.route_stride = B;
+        p.ready = ready; p.ready_chunk = ready_chunk; p.error_flag = h->h_error_dev;
       }
-      int rc = kind == 1 ? launch_presolve(h, h->cls[c], a) : launch_riccati(h, a);
+      int rc = launch_presolve(h, h->cls[c], p);
       if (rc) return rc;
       ++launches;
-      a.perm = a.fail_perm;
-      a.count = a.fail_count;
-      a.work = h->d_counts + 3 * kNumClasses + c;
-      a.fail_perm = nullptr; a.fail_count = nullptr;
-      a.route = 0; a.ready = nullptr;
+    } else {  // stage-wise presolve: collected, largest class first
+      for (int q = ric.nlists; q > 0; --q) {
+        ric.lperm[q] = ric.lperm[q - 1]; ric.lcount[q] = ric.lcount[q - 1]; ric.lwork[q] = ric.lwork[q - 1];
+        ric.lfail_perm[q] = ric.lfail_perm[q - 1]; ric.lfail_count[q] = ric.lfail_count[q - 1];
+      }
+      ric.lperm[0] = in_perm[c]; ric.lcount[0] = in_count[c]; ric.lwork[0] = in_work[c];
+      ric.lfail_perm[0] = fperm; ric.lfail_count[0] = fcount;
+      ++ric.nlists;
     }
-    int rc = ipm_kind(h, c, a.warm_active != nullptr) ? launch_ripm(h, a) : launch_class<0>(h, h->cls[c], a);
+    in_perm[c] = fperm; in_count[c] = fcount; in_work[c] = h->d_counts + 3 * kNumClasses + c;
+  }
+  if (ric.nlists > 0) {
+    ric.route = 0; ric.ready = nullptr;
+    int rc = launch_riccati(h, ric);
+    if (rc) return rc;
+    ++launches;
+  }
+  // ---- interior point + polish for what is left: the condensed kernel per class, ONE stage-wise launch for its classes
+  SolveArgs rip = a;
+  rip.route = 0; rip.ready = nullptr; rip.fail_perm = nullptr; rip.fail_count = nullptr;
+  for (int c = 0; c < kNumClasses; ++c) {
+    if (!h->cls[c].used) continue;
+    if (ipm_kind(h, c, warm)) {
+      for (int q = rip.nlists; q > 0; --q) { rip.lperm[q] = rip.lperm[q - 1]; rip.lcount[q] = rip.lcount[q - 1]; rip.lwork[q] = rip.lwork[q - 1]; }
+      rip.lperm[0] = in_perm[c]; rip.lcount[0] = in_count[c]; rip.lwork[0] = in_work[c];
+      ++rip.nlists;
+    } else {
+      SolveArgs p = a;
+      p.perm = in_perm[c]; p.count = in_count[c]; p.work = in_work[c];
+      p.fail_perm = nullptr; p.fail_count = nullptr; p.route = 0; p.ready = nullptr;
+      int rc = launch_class<0>(h, h->cls[c], p);
+      if (rc) return rc;
+      ++launches;
+    }
+  }
+  if (rip.nlists > 0) {
+    int rc = launch_ripm(h, rip);
     if (rc) return rc;
     ++launches;
   }

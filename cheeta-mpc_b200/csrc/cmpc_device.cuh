@@ -106,6 +106,15 @@ struct SolveArgs {
   const int32_t* ready;
   int ready_chunk;
   int32_t* error_flag;       // set when a wait on *ready times out
+  // Several lists in one launch (stage-wise kernels: their code does not depend on the size class).  nlists > 0: the
+  // persistent loop drains list 0, then list 1, ... (largest class first: its instances take longest, so they must not be
+  // left for a partial wave at the end); perm / count / work / fail_* above are ignored.
+  int nlists;
+  const int32_t* lperm[kNumClasses];
+  const int32_t* lcount[kNumClasses];
+  int32_t* lwork[kNumClasses];
+  int32_t* lfail_perm[kNumClasses];
+  int32_t* lfail_count[kNumClasses];
 };
 
 // ------------------------------------------------------------------ BC4 layout

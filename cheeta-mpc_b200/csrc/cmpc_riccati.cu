@@ -149,8 +149,14 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
   const double dt = cfg.dt, mass = cfg.mass;
   const double zeta = cfg.zoh ? 0.5 : 0.0;
   const double dpz = zeta * dt * dt * (-kGrav), dvz = dt * (-kGrav);  // affine term d = [dpz e_z; dvz e_z; 0]
-  const int count = args.count ? *args.count : args.count_imm;
-  if (count <= 0) return;  // empty list (uniform over the grid): nothing to set up
+  const int nl = args.nlists > 0 ? args.nlists : 1;
+  int total = 0;
+  for (int q = 0; q < nl; ++q) {
+    const int c = args.nlists > 0 ? *args.lcount[q] : (args.count ? *args.count : args.count_imm);
+    total += c > 0 ? c : 0;
+  }
+  if (total <= 0) return;  // empty lists (uniform over the grid): nothing to set up
+  int li = 0;
   for (int e = threadIdx.x; e <= N; e += blockDim.x) {
     const double om = (cfg.w[2] * 0.5) * exp(-(double)e) + cfg.w[2] * 0.5;  // CentroidalMPC.cpp:205
     c_qz[e] = om * om;
@@ -168,11 +174,16 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
   __syncthreads();
 
   while (true) {
+    const int count = args.nlists > 0 ? *args.lcount[li] : (args.count ? *args.count : args.count_imm);
     int slot = 0;
-    if (lane == 0) slot = atomicAdd(args.work, 1);
+    if (lane == 0) slot = atomicAdd(args.nlists > 0 ? args.lwork[li] : args.work, 1);
     slot = G.bcast0(slot, s_misc + 2);
-    if (slot >= count) break;
-    const int inst = args.perm ? args.perm[slot] : slot;
+    if (slot >= count) {
+      if (++li >= nl) break;
+      continue;
+    }
+    const int32_t* perm = args.nlists > 0 ? args.lperm[li] : args.perm;
+    const int inst = perm ? perm[slot] : slot;
     const bool finite = stage_inputs<W>(G, cfg, args, inst, V);
     const bool invalid = s_misc[1] != 0;
     if (!finite || invalid) {
@@ -430,7 +441,10 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
       defer = !G.all(!defer && fin);
     }
     if (defer) {
-      if (lane == 0) args.fail_perm[atomicAdd(args.fail_count, 1)] = inst;
+      if (lane == 0) {
+        if (args.nlists > 0) args.lfail_perm[li][atomicAdd(args.lfail_count[li], 1)] = inst;
+        else args.fail_perm[atomicAdd(args.fail_count, 1)] = inst;
+      }
       __syncwarp();
       continue;
     }

@@ -36,6 +36,13 @@ constexpr int kOffL = kNF * kYS;              // stage factors in the slab: Y | 
 constexpr int kOffD = kOffL + kNF * kNF;      //   also on swing-leg rows / columns: the vector sweeps run unmasked), 1 / l_aa [12]
 constexpr int kFac = kOffD + kNF;
 constexpr unsigned kFull = 0xffffffffu;
+// The polish's first working set: rows with kGuess z / gs > s / us.  The condensed kernel and the oracle use 1 (a row is
+// guessed active when its scaled multiplier exceeds its scaled slack); here the guess is generous, because a weakly
+// active row that is missed costs a whole correction pass (two gradient sweeps and a factor sweep) while a row guessed
+// in vain only shows up with a negative multiplier in the same pass that would have been needed anyway.  The accepted
+// point is the verified KKT point either way (unique optimum); measured on the tracking-heavy horizon-30 workload the
+// polish takes 1.5 instead of 2.2 passes per instance, results identical.
+constexpr double kGuess = 100.0;
 
 // CTA-shared header (constants every sweep needs; read with broadcast LDS instead of through the kernel parameters,
 // which a separately compiled device function can only reach with generic loads)
@@ -640,16 +647,28 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
   const double* const s_tab = smem + y_.tab;
   uint16_t* const s_act = reinterpret_cast<uint16_t*>(smem + y_.act);
   const double mass = cfg.mass;
-  const int count = args.count ? *args.count : args.count_imm;
-  if (count <= 0) return;
+  // work lists: one (perm / count / work) or several drained in order (SolveArgs::nlists)
+  const int nl = args.nlists > 0 ? args.nlists : 1;
+  int total = 0;
+  for (int q = 0; q < nl; ++q) {
+    const int c = args.nlists > 0 ? *args.lcount[q] : (args.count ? *args.count : args.count_imm);
+    total += c > 0 ? c : 0;
+  }
+  if (total <= 0) return;  // nothing to do (uniform over the grid)
   fill_header(cfg);
+  int li = 0;
 
   while (true) {
+    const int count = args.nlists > 0 ? *args.lcount[li] : (args.count ? *args.count : args.count_imm);
     int slot = 0;
-    if (lane == 0) slot = atomicAdd(args.work, 1);
+    if (lane == 0) slot = atomicAdd(args.nlists > 0 ? args.lwork[li] : args.work, 1);
     slot = __shfl_sync(kFull, slot, 0);
-    if (slot >= count) break;
-    const int inst = args.perm ? args.perm[slot] : slot;
+    if (slot >= count) {
+      if (++li >= nl) break;
+      continue;
+    }
+    const int32_t* perm = args.nlists > 0 ? args.lperm[li] : args.perm;
+    const int inst = perm ? perm[slot] : slot;
     bool invalid = false;
     int nb = 0;
     const bool finite = stage_instance(cfg, args, y_, inst, lane, invalid, nb);
@@ -711,13 +730,22 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
     __syncwarp();
 
     int status = CMPC_STATUS_MAX_ITER, it = 0, npolish = 0;
-    bool numerical = false, ipm_ok = false, grad_fresh = true;  // rd holds H u + g of the current u
+    bool numerical = false, ipm_ok = false;
+    bool grad_fresh = true, grad_exact = true;  // rd holds H u + g of the current u / it comes from a sweep, not from an update
     double us = 1.0;
 #pragma unroll 1
     for (it = 0; it <= cfg.max_iter; ++it) {
-      if (!grad_fresh) stage_gradient(N, L, gb, lane, y_.u, s_rd);
+      if (!grad_fresh) { stage_gradient(N, L, gb, lane, y_.u, s_rd); grad_exact = true; }
       grad_fresh = false;
-      double rmax = 0.0, umax = 0.0, gap = 0.0;
+      double rmax = 0.0, umax = 0.0, gap = 0.0, mu = 0.0;
+      bool conv_mu = false;
+      // H u + g is carried from iteration to iteration by the update  H (u + a du) + g = (H u + g) + a H du  with
+      // H du = rhs - C'SC du read off the Newton system (no sweep).  Every decision that ends the iteration (polish,
+      // termination) is taken on a residual from a fresh roll-out + adjoint sweep: once the gap is converged the
+      // gradient is recomputed and the test repeated.
+#pragma unroll 1
+      for (int attempt = 0; attempt < 2; ++attempt) {
+      rmax = 0.0; umax = 0.0; gap = 0.0;
 #pragma unroll 1
       for (int tb = lane; tb < nbfull; tb += 32) {
         const int k = tb / L, i = tb - k * L;
@@ -746,9 +774,13 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
         gap += __shfl_xor_sync(kFull, gap, o);
       }
       __syncwarp();
-      const double mu = gap / (2.0 * (double)m);
+      mu = gap / (2.0 * (double)m);
       us = 1.0 + umax;
-      const bool conv_mu = mu <= cfg.tol * gs * us;
+      conv_mu = mu <= cfg.tol * gs * us;
+      if (grad_exact || !conv_mu) break;
+      stage_gradient(N, L, gb, lane, y_.u, s_rd);
+      grad_exact = true;
+      }
       const bool strict = conv_mu && rmax <= cfg.tol * gs;
       const bool ready = conv_mu && rmax <= 1e4 * cfg.tol * gs;
       ipm_ok = conv_mu && rmax <= 10.0 * cfg.tol * gs;
@@ -767,8 +799,8 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
             for (int q = 0; q < 5; ++q) {
               const int t = 5 * tb + q;
               const double sl = ys[q], su = (q < 4 ? ubxy : ubz) - sl;
-              if (g_zl[t] * us > sl * gs) a |= (uint16_t)(1u << q);
-              if (g_zu[t] * us > su * gs) a |= (uint16_t)(1u << (5 + q));
+              if (kGuess * g_zl[t] * us > sl * gs) a |= (uint16_t)(1u << q);
+              if (kGuess * g_zu[t] * us > su * gs) a |= (uint16_t)(1u << (5 + q));
             }
           }
           s_act[tb] = a;
@@ -1026,6 +1058,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
         cmul5(mub, s_u + 3 * tb, ys);  // slacks at the current point (before the update)
         cmul5(mub, s_du + 3 * tb, yd);
         cmul5(mub, g_dua + 3 * tb, ya);
+        double wo[5], hq[5], o1[3], o2[3];
         for (int q = 0; q < 5; ++q) {
           const int t = 5 * tb + q;
           const double sl = ys[q], su = (q < 4 ? ubxy : ubz) - sl, zl = g_zl[t], zu = g_zu[t];
@@ -1033,17 +1066,24 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
           const double dla = (-sl * zl - zl * ya[q]) * isl, dua_ = (-su * zu + zu * ya[q]) * isu;
           const double rcl = -sl * zl + sigma * mu - ya[q] * dla;
           const double rcu = -su * zu + sigma * mu + ya[q] * dua_;
+          wo[q] = zl - zu;                                                   // C'(zl - zu): dual residual -> gradient
+          hq[q] = (rcl * isl - rcu * isu) - (zl * isl + zu * isu) * yd[q];   // corrector right-hand side rows minus S C du
           g_zl[t] = zl + alpha * (rcl - zl * yd[q]) * isl;
           g_zu[t] = zu + alpha * (rcu + zu * yd[q]) * isu;
         }
+        ctmul5(mub, wo, o1);
+        ctmul5(mub, hq, o2);
         for (int q = 0; q < 3; ++q) {
           const double v = s_u[3 * tb + q] + alpha * s_du[3 * tb + q];
           s_u[3 * tb + q] = v; fin = fin && isfinite(v);
+          const double rdv = s_rd[3 * tb + q];                              // (H + C'SC) du = -rd + C' rows  =>  H du = -rd + o2
+          s_rd[3 * tb + q] = rdv + o1[q] + alpha * (o2[q] - rdv);            // H u_new + g
         }
       }
       __syncwarp();
       fin = __all_sync(kFull, fin);
       if (!fin) { numerical = true; break; }
+      grad_fresh = true; grad_exact = false;
     }
     if (numerical) status = CMPC_STATUS_NUMERICAL;
     else if (status != CMPC_STATUS_OK) status = ipm_ok ? CMPC_STATUS_OK_IPM : CMPC_STATUS_MAX_ITER;
