@@ -20,6 +20,7 @@ struct cmpc_handle {
   DevConfig dev;
   int device = -1;
   int max_batch = 0;
+  int max_batch_plan = 0;  // max_batch while cmpc_setup is planning (max_batch itself is set when setup has succeeded)
   int num_sms = 0;
   bool ready = false;
   cudaStream_t stream = nullptr;
@@ -43,6 +44,8 @@ struct cmpc_handle {
     int W = 1, groups = 1, grid = 0, nbmax = 0, n4max = 0, m_in_smem = 1;
     size_t smem_bytes = 0, scratch_per_group = 0;
     double* d_scratch = nullptr;
+    double* d_xstate = nullptr;   // phase-split interior point: one iterate slot per instance (u | zl | zu | it)
+    int xstride = 0;
     // presolve kernel of the class (cmpc_presolve_kernel): more groups per CTA, H-only scratch
     bool pre_used = false;
     int pre_groups = 0;
@@ -72,7 +75,13 @@ struct cmpc_handle {
   int tune_calls = 0, tune_batch = 0;
   float tune_best[3] = {1e30f, 1e30f, 1e30f};  // [0] zero-copy, [1] pipelined, [2] full duplex: best span in ms
   char route[96] = "none";           // what the last cmpc_solve_batch call did (cmpc_last_route)
-  int32_t *d_counts = nullptr, *d_perm = nullptr;  // counts[4], work[4], then the presolve's deferred counts[4], work[4]; perm [2][4][B]
+  int32_t *d_counts = nullptr, *d_perm = nullptr;  // counts / work of: class lists, deferred lists, polish lists, fall-back lists (4 each); perm [4][4][B]
+  int32_t* h_hint = nullptr;      // pinned + mapped [4]: instances the last call's interior-point launch of each class found (0 = skip the split kernels)
+  int32_t* h_hint_dev = nullptr;
+  int32_t* d_hint_shadow = nullptr;
+  bool split = true;              // CMPC_SPLIT=0: never use the phase-split kernels
+  int split_maxw = 2;             // CMPC_SPLIT_MAXW: widest warp group that uses them (measured: a gain for one warp per instance, a loss for four)
+  int rip_minclass = 1;           // CMPC_RIPM_MINCLASS: smallest size class the stage-wise interior point takes in automatic mode
   std::string err;
 };
 
@@ -472,12 +481,13 @@ void fill_dev(cmpc_handle* h) {
 }
 
 template <int MODE>
-int launch_class(cmpc_handle* h, const cmpc_handle::ClassPlan& p, SolveArgs a) {
+int launch_class(cmpc_handle* h, const cmpc_handle::ClassPlan& p, SolveArgs a, int phase = 0) {
   a.scratch = p.d_scratch; a.scratch_per_group = p.scratch_per_group;
+  a.xstate = p.d_xstate; a.xstride = p.xstride;
   a.nbmax = p.nbmax; a.n4max = p.n4max; a.m_in_smem = p.m_in_smem; a.groups = p.groups;
   a.plan = make_plan(h->cfg.horizon, h->cfg.num_legs, p.m_in_smem ? p.W : 8, p.nbmax, p.n4max, p.m_in_smem);
   const int W = (MODE == 1 || !p.m_in_smem) ? 8 : p.W;
-  const cudaError_t e = launch_solve_kernel(W, MODE, p.m_in_smem != 0, p.grid, 32 * W * p.groups, p.smem_bytes, h->stream, h->dev, a);
+  const cudaError_t e = launch_solve_kernel(W, MODE, p.m_in_smem != 0, phase, p.grid, 32 * W * p.groups, p.smem_bytes, h->stream, h->dev, a);
   if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
   return CMPC_OK;
 }
@@ -520,7 +530,7 @@ int ipm_kind(const cmpc_handle* h, int c, bool warm) {
   if (h->rip_mode == 2) return 1;
   if (h->cfg.qp_backend == 1) return 0;
   if (h->cfg.qp_backend == 2) return 1;
-  return c >= 2 ? 1 : 0;
+  return c >= h->rip_minclass ? 1 : 0;
 }
 
 // which presolve kernel settles size class c: 0 none, 1 dense (cmpc_presolve.cu), 2 Riccati (cmpc_riccati.cu)
@@ -543,7 +553,7 @@ int presolve_kind(const cmpc_handle* h, int c) {
 //    ready_chunk instances) and the router waits per instance for its chunk.
 //  * presolve off: classify kernel, then one interior-point kernel per class.
 int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = nullptr, int ready_chunk = 0) {
-  if (cudaMemsetAsync(h->d_counts, 0, 4 * kNumClasses * sizeof(int32_t), h->stream) != cudaSuccess)
+  if (cudaMemsetAsync(h->d_counts, 0, 8 * kNumClasses * sizeof(int32_t), h->stream) != cudaSuccess)
     return fail(h, CMPC_ERR_CUDA, "memset counts");
   int launches = 0;
   const bool presolve = h->cfg.presolve && h->cfg.polish;
@@ -611,10 +621,35 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
       rip.lperm[0] = in_perm[c]; rip.lcount[0] = in_count[c]; rip.lwork[0] = in_work[c];
       ++rip.nlists;
     } else {
+      // Condensed route.  Behind the presolve (what is left then is the constrained part of the batch: iteration counts
+      // and polish passes differ from instance to instance, so the warps of an SM drift through different phases of
+      // the fused kernel and thrash the instruction cache), and when the previous call found instances on this class's
+      // list, the interior point and the polish run as two lean kernels (each hot loop fits the instruction cache); the fused kernel always follows as the
+      // catch-all: it shares the list's work counter (so it finds it drained) and takes the fall-back list.  With no
+      // instances expected only the fused kernel is launched, as before -- the result never depends on the guess.
       SolveArgs p = a;
-      p.perm = in_perm[c]; p.count = in_count[c]; p.work = in_work[c];
       p.fail_perm = nullptr; p.fail_count = nullptr; p.route = 0; p.ready = nullptr;
-      int rc = launch_class<0>(h, h->cls[c], p);
+      int32_t* pol_perm = h->d_perm + (size_t)(2 * kNumClasses + c) * h->max_batch;
+      int32_t* fb_perm = h->d_perm + (size_t)(3 * kNumClasses + c) * h->max_batch;
+      int32_t* pol_count = h->d_counts + 4 * kNumClasses + c; int32_t* pol_work = h->d_counts + 5 * kNumClasses + c;
+      int32_t* fb_count = h->d_counts + 6 * kNumClasses + c; int32_t* fb_work = h->d_counts + 7 * kNumClasses + c;
+      const cmpc_handle::ClassPlan& cp = h->cls[c];
+      if (h->split && presolve && !warm && h->cfg.polish && cp.m_in_smem && cp.W <= h->split_maxw && cp.d_xstate && h->h_hint[c] > 0) {
+        SolveArgs q = p;
+        q.perm = in_perm[c]; q.count = in_count[c]; q.work = in_work[c];
+        q.pol_perm = pol_perm; q.pol_count = pol_count; q.fb_perm = fb_perm; q.fb_count = fb_count;
+        int rc = launch_class<0>(h, cp, q, 1);
+        if (rc) return rc;
+        q.perm = pol_perm; q.count = pol_count; q.work = pol_work;
+        rc = launch_class<0>(h, cp, q, 2);
+        if (rc) return rc;
+        launches += 2;
+      }
+      p.nlists = 2;
+      p.lperm[0] = in_perm[c]; p.lcount[0] = in_count[c]; p.lwork[0] = in_work[c];
+      p.lperm[1] = fb_perm; p.lcount[1] = fb_count; p.lwork[1] = fb_work;
+      p.hint_out = h->h_hint_dev + c; p.hint_shadow = h->d_hint_shadow + c;
+      int rc = launch_class<0>(h, cp, p);
       if (rc) return rc;
       ++launches;
     }
@@ -643,6 +678,10 @@ int plan_class(cmpc_handle* h, cmpc_handle::ClassPlan& p, int W, int nbmax, int 
   // H (and the factor when it does not fit on chip) + the polish's null-space bases (9 doubles per leg-step)
   p.scratch_per_group = (size_t)mat_region_doubles(N, L, p.n4max) * (p.m_in_smem ? 1 : 2) + (size_t)((9 * p.nbmax + 1) & ~1);
   CUDA_TRY(h, cudaMalloc(&p.d_scratch, p.scratch_per_group * 8 * (size_t)p.grid * p.groups));
+  if (mode == 0 && p.m_in_smem) {  // iterate slots of the phase-split interior point
+    p.xstride = (p.n4max + 10 * p.nbmax + 2 + 1) & ~1;
+    CUDA_TRY(h, cudaMalloc(&p.d_xstate, (size_t)h->max_batch_plan * p.xstride * 8));
+  }
   p.used = true;
   if (mode == 0 && p.m_in_smem) {  // presolve variant: the matrix and one vector per group (make_pre_plan)
     const PrePlan pp = make_pre_plan(N, L, W, p.nbmax, p.n4max);
@@ -693,7 +732,9 @@ static void release_device_state(cmpc_handle* h) {
   DeviceGuard g(h->device >= 0 ? h->device : 0);
   cudaFree(h->d_state); cudaFree(h->d_ds); cudaFree(h->d_di); cudaFree(h->d_forces); cudaFree(h->d_kkt);
   cudaFree(h->d_lam); cudaFree(h->d_hip); cudaFree(h->d_counts); cudaFree(h->d_perm); cudaFree(h->exp_plan.d_scratch);
-  for (auto& c : h->cls) { cudaFree(c.d_scratch); cudaFree(c.d_pre_scratch); c = cmpc_handle::ClassPlan(); }
+  for (auto& c : h->cls) { cudaFree(c.d_scratch); cudaFree(c.d_pre_scratch); cudaFree(c.d_xstate); c = cmpc_handle::ClassPlan(); }
+  cudaFreeHost(h->h_hint); h->h_hint = nullptr; h->h_hint_dev = nullptr;
+  cudaFree(h->d_hint_shadow); h->d_hint_shadow = nullptr;
   h->exp_plan = cmpc_handle::ClassPlan();
   cudaFree(h->d_ric_scratch); cudaFree(h->d_rip_scratch);
   cudaFree(h->d_ready); cudaFreeHost(h->h_ready_vals); cudaFreeHost(h->h_error);
@@ -745,6 +786,7 @@ int cmpc_create(const cmpc_config* cfg, cmpc_handle** out) {
 
 static int setup_impl(cmpc_handle* h, int max_batch, int device) {
   h->device = device;
+  h->max_batch_plan = max_batch;
   SET_DEVICE(h);
   cudaDeviceProp prop;
   CUDA_TRY(h, cudaGetDeviceProperties(&prop, device));
@@ -784,8 +826,16 @@ static int setup_impl(cmpc_handle* h, int max_batch, int device) {
   if (const char* m = getenv("CMPC_E2E_MODE")) h->e2e_mode = atoi(m);
   if (const char* m = getenv("CMPC_E2E_CHUNK")) h->e2e_chunk = atoi(m);
   h->debug_tune = getenv("CMPC_DEBUG_TUNE") != nullptr;
-  CUDA_TRY(h, cudaMalloc(&h->d_counts, 4 * kNumClasses * sizeof(int32_t)));
-  CUDA_TRY(h, cudaMalloc(&h->d_perm, (size_t)2 * kNumClasses * B * sizeof(int32_t)));
+  CUDA_TRY(h, cudaMalloc(&h->d_counts, 8 * kNumClasses * sizeof(int32_t)));
+  CUDA_TRY(h, cudaMalloc(&h->d_perm, (size_t)4 * kNumClasses * B * sizeof(int32_t)));
+  CUDA_TRY(h, cudaHostAlloc(&h->h_hint, kNumClasses * sizeof(int32_t), cudaHostAllocMapped));
+  for (int c = 0; c < kNumClasses; ++c) h->h_hint[c] = 0;
+  CUDA_TRY(h, cudaHostGetDevicePointer((void**)&h->h_hint_dev, h->h_hint, 0));
+  CUDA_TRY(h, cudaMalloc(&h->d_hint_shadow, kNumClasses * sizeof(int32_t)));
+  CUDA_TRY(h, cudaMemset(h->d_hint_shadow, 0, kNumClasses * sizeof(int32_t)));
+  if (const char* m = getenv("CMPC_SPLIT")) h->split = atoi(m) != 0;
+  if (const char* m = getenv("CMPC_SPLIT_MAXW")) h->split_maxw = atoi(m);
+  if (const char* m = getenv("CMPC_RIPM_MINCLASS")) h->rip_minclass = atoi(m);
   // size classes by number of free 3-blocks: n4 <= 64 -> one warp per instance, n4 <= 128 ->
   // four warps, larger -> a whole 256-thread CTA; the factor lives in shared memory whenever it fits
   {

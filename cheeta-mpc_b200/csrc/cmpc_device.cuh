@@ -115,6 +115,15 @@ struct SolveArgs {
   int32_t* lwork[kNumClasses];
   int32_t* lfail_perm[kNumClasses];
   int32_t* lfail_count[kNumClasses];
+  // condensed interior-point kernel split into phases (cmpc_solve.cu): iterate hand-over and lists
+  double* xstate;            // [slot][xstride]: u (n4max) | zl (5 nbmax) | zu (5 nbmax) | it
+  int xstride;
+  int32_t* pol_perm;         // phase 1 -> phase 2: instances whose interior-point iterate is ready for the polish
+  int32_t* pol_count;
+  int32_t* fb_perm;          // phase 1 / 2 -> fused kernel: everything the split does not finish itself
+  int32_t* fb_count;
+  int32_t* hint_shadow;      // device copy of *hint_out (the host word is only written when the value changes)
+  int32_t* hint_out;         // mapped host word: how many instances this launch found on its lists (next call's launch plan)
 };
 
 // ------------------------------------------------------------------ BC4 layout
@@ -1024,7 +1033,7 @@ __host__ __device__ inline RicPlan make_ric_plan(int N, int L) {
 
 // ------------------------------------------------------------------ kernel launchers (one translation unit per kernel family)
 // cmpc_solve.cu: W in {1, 2, 4, 8}; mode 0 = solve, 1 = build-export; ms = factor in shared memory
-cudaError_t launch_solve_kernel(int W, int mode, bool ms, int grid, int block, size_t smem, cudaStream_t stream,
+cudaError_t launch_solve_kernel(int W, int mode, bool ms, int phase, int grid, int block, size_t smem, cudaStream_t stream,
                                 const DevConfig& cfg, const SolveArgs& args);
 cudaError_t set_solve_kernel_smem(int W, int mode, bool ms, size_t bytes);
 // cmpc_presolve.cu: W in {1, 4, 8}

@@ -5,8 +5,18 @@ namespace cmpc {
 
 // ------------------------------------------------------------------ the fused kernel
 // MODE 0: solve.  MODE 1: build-export (H, g in the full 3LN layout to global memory).
-template <int W, int MODE, bool MS>
-__global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solve_kernel(const DevConfig cfg, const SolveArgs args) {
+// PHASE splits the solve so that each kernel's hot loop fits the instruction cache (the fused kernel is 30 k SASS
+// instructions; with the resident warps of an SM in different phases of different instances more than half of its stall
+// cycles on the constrained workload were instruction fetch):
+//   0  fused: build + interior point + polish + outputs (every path; also the catch-all for what the split hands back)
+//   1  interior point only: build, start point, Mehrotra iterations until the polish would be attempted; the iterate
+//      (u, zl, zu, gs, it) goes to a state slot and the instance to the polish list.  Any other way out of the loop
+//      (iteration cap, numerical trouble) hands the instance to the fall-back list, which the fused kernel solves from
+//      scratch -- deterministically the same result.
+//   2  polish only: build, load the iterate, the verified active-set polish, outputs; a rejected polish (rare: the
+//      fused kernel would go back to the interior point) hands the instance to the fall-back list.
+template <int W, int MODE, bool MS, int PHASE>
+__global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256), 1) cmpc_solve_kernel(const DevConfig cfg, const SolveArgs args) {
   extern __shared__ __align__(128) double smem[];
   constexpr int GT = Group<W>::GT;
   const int N = cfg.N, L = cfg.L, nu = 3 * L;
@@ -56,17 +66,32 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solv
   double* g_Zt = Hm + (size_t)mat_region_doubles(N, L, args.n4max) * (MS ? 1 : 2);
 
   const double mass = cfg.mass;
-  const int count = args.count ? *args.count : args.count_imm;
-  if (count <= 0) return;  // empty list (uniform over the grid): nothing to set up
+  // work lists: one (perm / count / work) or several drained in order (SolveArgs::nlists)
+  const int nl = args.nlists > 0 ? args.nlists : 1;
+  int total = 0;
+  for (int q = 0; q < nl; ++q) {
+    const int c = args.nlists > 0 ? *args.lcount[q] : (args.count ? *args.count : args.count_imm);
+    total += c > 0 ? c : 0;
+  }
+  // for the host's next launch plan: a word in mapped host memory, written only when the value changes (a device-side
+  // shadow tells): in steady state no launch touches the bus for it
+  if (args.hint_out && blockIdx.x == 0 && threadIdx.x == 0 && *args.hint_shadow != total) { *args.hint_shadow = total; *args.hint_out = total; }
+  if (total <= 0) return;  // empty lists (uniform over the grid): nothing to set up
   if ((int)threadIdx.x < N) fill_z_tables(cfg, c_z1, c_z2, threadIdx.x);
   __syncthreads();
+  int li = 0;
 
   while (true) {
+    const int count = args.nlists > 0 ? *args.lcount[li] : (args.count ? *args.count : args.count_imm);
     int slot = 0;
-    if (gtid == 0) slot = atomicAdd(args.work, 1);
+    if (gtid == 0) slot = atomicAdd(args.nlists > 0 ? args.lwork[li] : args.work, 1);
     slot = G.bcast0(slot, s_misc + 2);
-    if (slot >= count) break;
-    const int inst = args.perm ? args.perm[slot] : slot;
+    if (slot >= count) {
+      if (++li >= nl) break;
+      continue;
+    }
+    const int32_t* lperm = args.nlists > 0 ? args.lperm[li] : args.perm;
+    const int inst = lperm ? lperm[slot] : slot;
     BuildView V;
     V.Mm = Mm; V.ce = s_ce; V.fz = s_fz; V.arm = s_arm; V.eq = s_eq; V.qz = s_qz; V.g = s_g;
     V.misc = s_misc; V.tb = s_tb; V.blk_j = s_blk_j; V.blk_i = s_blk_i; V.blk_of = s_blk_of;
@@ -117,13 +142,19 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solv
       continue;
     }
 
-    // ---- strictly feasible start f = (0, 0, fz0); centred duals
+    // ---- strictly feasible start f = (0, 0, fz0); centred duals  (phase 2: the interior-point kernel's iterate)
+    const double* xs = nullptr;
+    if constexpr (PHASE == 2) xs = args.xstate + (size_t)slot * args.xstride;
     for (int b = gtid; b < nb; b += GT) {
-      const double mub = cfg.mu[s_blk_i[b]];
-      double fz = s_fz[b];
-      fz = fmin(fz, 0.5 * mass * kGrav * (double)L * s_ce[b]);
-      fz = fmin(fz, 0.5 * kFricUb * s_ce[b] / mub);
-      s_u[3 * b] = 0.0; s_u[3 * b + 1] = 0.0; s_u[3 * b + 2] = fz;
+      if constexpr (PHASE == 2) {
+        s_u[3 * b] = __ldcg(xs + 3 * b); s_u[3 * b + 1] = __ldcg(xs + 3 * b + 1); s_u[3 * b + 2] = __ldcg(xs + 3 * b + 2);
+      } else {
+        const double mub = cfg.mu[s_blk_i[b]];
+        double fz = s_fz[b];
+        fz = fmin(fz, 0.5 * mass * kGrav * (double)L * s_ce[b]);
+        fz = fmin(fz, 0.5 * kFricUb * s_ce[b] / mub);
+        s_u[3 * b] = 0.0; s_u[3 * b + 1] = 0.0; s_u[3 * b + 2] = fz;
+      }
     }
     if (gtid < n4 - n) s_u[n + gtid] = 0.0;
     if constexpr (!MS) copy_mat<W>(G, Mm, Hm, matd);
@@ -138,24 +169,32 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solv
     const double gs = 1.0 + gmax;
     const double mu0 = fmax(1e-2, r0max);
     for (int b = gtid; b < nb; b += GT) {
-      const double mub = cfg.mu[s_blk_i[b]];
-      const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];  // :183,199
-      double y[5];
-      cmul5(mub, s_u + 3 * b, y);
-      for (int q = 0; q < 5; ++q) {
-        const double ub = q < 4 ? ubxy : ubz;
-        s_zl[5 * b + q] = mu0 / y[q]; s_zu[5 * b + q] = mu0 / (ub - y[q]);
+      if constexpr (PHASE == 2) {
+        for (int q = 0; q < 5; ++q) {
+          s_zl[5 * b + q] = __ldcg(xs + args.n4max + 5 * b + q); s_zu[5 * b + q] = __ldcg(xs + args.n4max + mmax + 5 * b + q);
+        }
+      } else {
+        const double mub = cfg.mu[s_blk_i[b]];
+        const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];  // :183,199
+        double y[5];
+        cmul5(mub, s_u + 3 * b, y);
+        for (int q = 0; q < 5; ++q) {
+          const double ub = q < 4 ? ubxy : ubz;
+          s_zl[5 * b + q] = mu0 / y[q]; s_zu[5 * b + q] = mu0 / (ub - y[q]);
+        }
       }
     }
     G.sync();
 
     int status = CMPC_STATUS_MAX_ITER, it = 0, npolish = 0;
-    bool numerical = false, ipm_ok = false, m_is_h = true, warm_done = false;
+    bool numerical = false, ipm_ok = false, m_is_h = true, warm_done = false, handed_over = false;
     double us = 1.0;
-    for (it = 0; it <= cfg.max_iter; ++it) {
+    if constexpr (PHASE == 2) it = (int)__ldcg(xs + args.n4max + 2 * mmax);
+    const int it_first = it, it_last = PHASE == 2 ? it : cfg.max_iter;
+    for (it = it_first; it <= it_last; ++it) {
       // ---- residuals (M holds a fresh copy of H here)
       if (!m_is_h) { copy_mat<W>(G, Mm, Hm, matd); G.sync(); m_is_h = true; }
-      if (it > 0) symv_bc4<W>(G, Mm, n4, nblk, s_u, s_rd);  // it == 0: rd still holds H u0 from the start point
+      if (it > 0 || PHASE == 2) symv_bc4<W>(G, Mm, n4, nblk, s_u, s_rd);  // fused, it == 0: rd still holds H u0 from the start point
       double rmax = 0.0, umax = 0.0, gap = 0.0;
       for (int b = gtid; b < nb; b += GT) {
         const double ubxy = kFricUb * s_ce[b], ubz = mass * kGrav * (double)L * s_ce[b];
@@ -182,12 +221,27 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solv
       // as soon as the gap is converged and the residual is merely small.
       const bool conv_mu = mu <= cfg.tol * gs * us;
       const bool strict = conv_mu && rmax <= cfg.tol * gs;
-      const bool ready = conv_mu && rmax <= 1e4 * cfg.tol * gs;
+      const bool ready = PHASE == 2 || (conv_mu && rmax <= 1e4 * cfg.tol * gs);  // (phase 2 exists because phase 1 saw `ready`)
       ipm_ok = conv_mu && rmax <= 10.0 * cfg.tol * gs;
       // Warm start (closed loop): before the first factorisation, try the previous tick's
       // active set, shifted by one step, as the polish's guess. The polish verifies the KKT
       // conditions, so a wrong guess only costs its correction passes and the IPM runs cold.
       const bool warm_now = cfg.polish && args.warm_active != nullptr && it == 0 && !warm_done;
+      if constexpr (PHASE == 1) {
+        if (ready) {
+          // hand the iterate to the polish kernel: state slot = position in its list
+          int ps = 0;
+          if (gtid == 0) ps = atomicAdd(args.pol_count, 1);
+          ps = G.bcast0(ps, s_misc + 2);
+          double* xo = args.xstate + (size_t)ps * args.xstride;
+          for (int t = gtid; t < n4; t += GT) __stcg(xo + t, s_u[t]);
+          for (int t = gtid; t < m; t += GT) { __stcg(xo + args.n4max + t, s_zl[t]); __stcg(xo + args.n4max + mmax + t, s_zu[t]); }
+          if (gtid == 0) { __stcg(xo + args.n4max + 2 * mmax, (double)it); args.pol_perm[ps] = inst; }
+          handed_over = true;
+          break;
+        }
+      }
+      if constexpr (PHASE != 1)
       if (cfg.polish && ((ready && npolish < 3) || warm_now)) {
         bool any_act = false;
         if (warm_now) {
@@ -398,6 +452,7 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solv
           break;
         }
         G.sync();
+        if constexpr (PHASE == 2) break;  // not accepted: the fused kernel takes the instance from scratch (fall-back list)
         // polish not accepted: rd was used as f0 scratch -> recompute the residual
         if (!m_is_h) { copy_mat<W>(G, Mm, Hm, matd); G.sync(); m_is_h = true; }
         symv_bc4<W>(G, Mm, n4, nblk, s_u, s_rd);
@@ -412,6 +467,7 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solv
       if (strict && (!cfg.polish || npolish >= 3)) break;
       if (mu <= 1e-8 * cfg.tol * gs * us) break;  // far past convergence: stop before 0/0
       if (it == cfg.max_iter) break;
+      if constexpr (PHASE != 2) {
 
       // ---- M = H + C' diag(zl/sl + zu/su) C  (only the 3x3 diagonal blocks change), and the
       // affine (predictor) right-hand side  -rd + C'(rcl/sl - rcu/su)  with rc = -s z
@@ -548,6 +604,15 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solv
       }
       fin = G.all(fin);
       if (!fin) { numerical = true; break; }
+      }  // PHASE != 2
+    }
+    if constexpr (PHASE != 0) {
+      // split kernels: phase 1 never writes outputs; phase 2 only for an accepted polish.  Everything else goes to the
+      // fall-back list of the fused kernel.
+      if ((PHASE == 1 && !handed_over) || (PHASE == 2 && status != CMPC_STATUS_OK)) {
+        if (gtid == 0) args.fb_perm[atomicAdd(args.fb_count, 1)] = inst;
+      }
+      if (PHASE == 1 || status != CMPC_STATUS_OK) { G.sync(); continue; }
     }
     if (numerical) status = CMPC_STATUS_NUMERICAL;
     else if (status != CMPC_STATUS_OK) status = ipm_ok ? CMPC_STATUS_OK_IPM : CMPC_STATUS_MAX_ITER;
@@ -646,38 +711,55 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256)) cmpc_solv
 
 
 namespace {
-template <int W, int MODE, bool MS>
+template <int W, int MODE, bool MS, int PHASE>
 cudaError_t launch_t(int grid, int block, size_t smem, cudaStream_t stream, const DevConfig& cfg, const SolveArgs& args) {
-  cmpc_solve_kernel<W, MODE, MS><<<grid, block, smem, stream>>>(cfg, args);
+  cmpc_solve_kernel<W, MODE, MS, PHASE><<<grid, block, smem, stream>>>(cfg, args);
   return cudaGetLastError();
 }
-template <int W, int MODE, bool MS>
+template <int W, int MODE, bool MS, int PHASE>
 cudaError_t attr_t(size_t bytes) {
-  return cudaFuncSetAttribute(cmpc_solve_kernel<W, MODE, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return cudaFuncSetAttribute(cmpc_solve_kernel<W, MODE, MS, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+template <int W>
+cudaError_t launch_w(int phase, int grid, int block, size_t smem, cudaStream_t stream, const DevConfig& cfg, const SolveArgs& args) {
+  switch (phase) {
+    case 0: return launch_t<W, 0, true, 0>(grid, block, smem, stream, cfg, args);
+    case 1: return launch_t<W, 0, true, 1>(grid, block, smem, stream, cfg, args);
+    case 2: return launch_t<W, 0, true, 2>(grid, block, smem, stream, cfg, args);
+  }
+  return cudaErrorInvalidValue;
+}
+template <int W>
+cudaError_t attr_w(size_t bytes) {
+  cudaError_t e = attr_t<W, 0, true, 0>(bytes);
+  if (e == cudaSuccess) e = attr_t<W, 0, true, 1>(bytes);
+  if (e == cudaSuccess) e = attr_t<W, 0, true, 2>(bytes);
+  return e;
 }
 }  // namespace
 
-cudaError_t launch_solve_kernel(int W, int mode, bool ms, int grid, int block, size_t smem, cudaStream_t stream,
+// phase: 0 fused, 1 interior point only, 2 polish only (the split exists for the shared-memory-factor variants)
+cudaError_t launch_solve_kernel(int W, int mode, bool ms, int phase, int grid, int block, size_t smem, cudaStream_t stream,
                                 const DevConfig& cfg, const SolveArgs& args) {
-  if (mode == 1) return launch_t<8, 1, false>(grid, block, smem, stream, cfg, args);
-  if (!ms) return launch_t<8, 0, false>(grid, block, smem, stream, cfg, args);
+  if (mode == 1) return launch_t<8, 1, false, 0>(grid, block, smem, stream, cfg, args);
+  if (!ms) return launch_t<8, 0, false, 0>(grid, block, smem, stream, cfg, args);
   switch (W) {
-    case 1: return launch_t<1, 0, true>(grid, block, smem, stream, cfg, args);
-    case 2: return launch_t<2, 0, true>(grid, block, smem, stream, cfg, args);
-    case 4: return launch_t<4, 0, true>(grid, block, smem, stream, cfg, args);
-    case 8: return launch_t<8, 0, true>(grid, block, smem, stream, cfg, args);
+    case 1: return launch_w<1>(phase, grid, block, smem, stream, cfg, args);
+    case 2: return launch_w<2>(phase, grid, block, smem, stream, cfg, args);
+    case 4: return launch_w<4>(phase, grid, block, smem, stream, cfg, args);
+    case 8: return launch_w<8>(phase, grid, block, smem, stream, cfg, args);
   }
   return cudaErrorInvalidValue;
 }
 
 cudaError_t set_solve_kernel_smem(int W, int mode, bool ms, size_t bytes) {
-  if (mode == 1) return attr_t<8, 1, false>(bytes);
-  if (!ms) return attr_t<8, 0, false>(bytes);
+  if (mode == 1) return attr_t<8, 1, false, 0>(bytes);
+  if (!ms) return attr_t<8, 0, false, 0>(bytes);
   switch (W) {
-    case 1: return attr_t<1, 0, true>(bytes);
-    case 2: return attr_t<2, 0, true>(bytes);
-    case 4: return attr_t<4, 0, true>(bytes);
-    case 8: return attr_t<8, 0, true>(bytes);
+    case 1: return attr_w<1>(bytes);
+    case 2: return attr_w<2>(bytes);
+    case 4: return attr_w<4>(bytes);
+    case 8: return attr_w<8>(bytes);
   }
   return cudaErrorInvalidValue;
 }
