@@ -457,7 +457,7 @@ def main():
         fp64_peak = mpc.measure_fp64_peak()
         traffic = None
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
             if B == 4096 and args.horizon == 10 and gaits == ("trot",):
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         except Exception:
