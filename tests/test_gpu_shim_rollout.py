@@ -163,13 +163,13 @@ def test_weights_update_and_zoh_mode(pkg, orc, wl):
     mz.close()
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
 def test_host_buffer_paths_agree(pkg, wl, mode, monkeypatch):
     """cmpc_solve_batch with host buffers: mode 0 = automatic (pipelined chunks for big batches, else
     zero-copy), 1 = zero-copy reads of pinned inputs (outputs written in place when pinned), 2 = copy in /
     compute / copy out, 3 = progressive (chunked DMA copy-in overlapped with the router kernel that polls
-    for its chunk), 4 = pipelined (chunk c computes while chunk c + 1 is copied).  Pageable and pinned
-    buffers, every mode: bit-identical results (mixed gaits, so the router also forwards the stand
+    for its chunk), 4 = pipelined (chunk c computes while chunk c + 1 is copied), 5 = full duplex (pipelined,
+    and each chunk's outputs leave by the copy engine on a third stream).  Pageable and pinned buffers, every mode: bit-identical results (mixed gaits, so the router also forwards the stand
     instances to their size class)."""
     import ctypes as C
     import torch
@@ -197,8 +197,12 @@ def test_host_buffer_paths_agree(pkg, wl, mode, monkeypatch):
         assert np.array_equal(f.numpy(), pageable["forces"])
         assert np.array_equal(s.numpy(), pageable["status"]) and np.array_equal(it.numpy(), pageable["iters"])
         assert np.array_equal(act.numpy().view(np.uint16), pageable["active"])
-    if mode != 2:
+    if mode not in (2, 5):
         assert stats.d2h_ms < 0.05                              # pinned outputs are written in place
+    route = m.last_route()
+    assert isinstance(route, str) and route and route != "none"
+    if mode in (4, 5):
+        assert ("duplex" in route) == (mode == 5), route
     # device-resident reference
     dev = torch.device("cuda", 0)
     d = [torch.from_numpy(a).to(dev) for a in (st, ds, di)]
