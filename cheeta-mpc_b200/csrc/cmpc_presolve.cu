@@ -114,6 +114,125 @@ __device__ __forceinline__ bool chol_cm(const Group<W>& G, const CM<TT>& cm, dou
   return true;
 }
 
+// D(8x8) += A(8x4) B(4x8) on the FP64 tensor-core path.  Lane l holds A[l >> 2][l & 3], B[l & 3][l >> 2] and
+// D[l >> 2][2 (l & 3) + {0, 1}].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// Tensor-core update of NI vertically stacked 8-row blocks (tile rows r0 + 2i + {0, 1}) of the tile columns c0 (and
+// c0 + 1 when TWO):  C -= sum_{kk in [k0, k1)} L(rows, kk) L(c0.., kk)'.  The blocks stay in the accumulator
+// registers (two doubles per lane) over all k1 - k0 mma steps and are read and written once.  A / B fragments come
+// straight out of the chunk-major tiles: lane l reads element (row (l >> 2) & 3, column l & 3) of tile t + (l >> 4);
+// with T = 1 (mod 8) the 32 addresses fall into distinct banks.  A tile row past the end of the matrix reads
+// whatever follows in the chunk (T > number of tiles keeps it inside the matrix region) and only feeds output rows /
+// columns that are not stored.
+template <int NI, bool TWO, int TT>
+__device__ __forceinline__ void mma_update(const CM<TT>& cm, double2* M2, int nblk, int lane, int r0, int c0, int k0, int k1) {
+  const int T = cm.T();
+  const int fa = (lane >> 2) & 3, fhi = lane >> 4, ctc = (lane & 3) >> 1;
+  // C fragment: row lane >> 2 of the 8, columns 2 (lane & 3) + {0, 1}: tile (row fhi, column ctc), chunk 2 fa + (lane & 1)
+  const int tcol = c0 + ctc;
+  const int cbase = (2 * fa + (lane & 1)) * T + tcol * nblk - ((tcol * (tcol - 1)) >> 1) - tcol;  // + tile row
+  const bool colok = TWO ? tcol < nblk : ctc == 0;
+  double acc[NI][2];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int trow = r0 + 2 * i + fhi;
+    acc[i][0] = 0.0; acc[i][1] = 0.0;
+    if (colok && trow < nblk && trow >= tcol) { const double2 c = M2[cbase + trow]; acc[i][0] = c.x; acc[i][1] = c.y; }
+  }
+  // fragment element inside the tile pair (t, t + 1)
+  const double* pb = reinterpret_cast<const double*>(M2) + 2 * ((2 * fa + ctc) * T + fhi) + (lane & 1)
+                     + 2 * (k0 * nblk - ((k0 * (k0 - 1)) >> 1) - k0);  // + 2 (tile row): column k0
+  for (int kk = k0; kk < k1; ++kk) {
+    const double b = pb[2 * c0];
+    const double bn = -b;
+    double a[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) a[i] = (i == 0) ? b : pb[2 * (r0 + 2 * i)];  // r0 == c0: the first block row is the B block
+#pragma unroll
+    for (int i = 0; i < NI; ++i) dmma884(acc[i][0], acc[i][1], a[i], bn);
+    pb += 2 * (nblk - kk - 1);
+  }
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int trow = r0 + 2 * i + fhi;
+    if (colok && trow < nblk && trow >= tcol) M2[cbase + trow] = make_double2(acc[i][0], acc[i][1]);
+  }
+}
+
+template <bool TWO, int TT>
+__device__ __forceinline__ void mma_update_n(int ni, const CM<TT>& cm, double2* M2, int nblk, int lane, int r0, int c0, int k0, int k1) {
+  switch (ni) {
+    case 1: mma_update<1, TWO, TT>(cm, M2, nblk, lane, r0, c0, k0, k1); break;
+    case 2: mma_update<2, TWO, TT>(cm, M2, nblk, lane, r0, c0, k0, k1); break;
+    case 3: mma_update<3, TWO, TT>(cm, M2, nblk, lane, r0, c0, k0, k1); break;
+    case 4: mma_update<4, TWO, TT>(cm, M2, nblk, lane, r0, c0, k0, k1); break;
+    case 5: mma_update<5, TWO, TT>(cm, M2, nblk, lane, r0, c0, k0, k1); break;
+    case 6: mma_update<6, TWO, TT>(cm, M2, nblk, lane, r0, c0, k0, k1); break;
+    case 7: mma_update<7, TWO, TT>(cm, M2, nblk, lane, r0, c0, k0, k1); break;
+    case 8: mma_update<8, TWO, TT>(cm, M2, nblk, lane, r0, c0, k0, k1); break;
+    default: break;
+  }
+}
+
+// One-warp variant of chol_cm (n4 <= 64): LEFT-looking over 8-wide block columns, the rank-k part on the FP64 tensor
+// cores.  Before the tile columns 2J, 2J + 1 are factored, the block column gets its whole update from the columns
+// to its left in one go (mma_update) -- the right-looking sweep re-reads and re-writes every trailing tile at every
+// step, which was 59 % of the kernel's shared-memory wavefronts.  Inside the pair of tile columns the odd column
+// gets its rank-4 update from the even one the same way.  Forward substitution fused as in chol_cm.
+template <int TT>
+__device__ __forceinline__ bool chol_cm_mma(const Group<1>& G, const CM<TT>& cm, double2* M2, int nblk, double (&xr)[2],
+                                            double* x, double* exch) {
+  const int lane = G.gtid;
+  const int n4 = nblk << 2;
+  const int T = cm.T();
+  bool ok = true;
+  int col0 = 0;  // storage index of the diagonal tile of column kb
+  for (int kb = 0; kb < nblk; ++kb) {
+    const int nrows = nblk - kb;
+    if (kb > 0) {
+      if (kb & 1) mma_update_n<false, TT>((nrows + 1) >> 1, cm, M2, nblk, lane, kb, kb, kb - 1, kb);
+      else mma_update_n<true, TT>((nrows + 1) >> 1, cm, M2, nblk, lane, kb, kb, 0, kb);
+      G.sync();
+    }
+    double d[16], a[16];
+    cm.ld(M2, col0, a);  // broadcast loads: every lane factors the same tile
+    ok = potrf4(a, d) && ok;
+    // TRSM: X = A L^-T, one panel ROW per thread (rows 4(kb+1) .. n4-1)
+    for (int r = 4 * (kb + 1) + lane; r < n4; r += 32) {
+      double2* p = cm.row(M2, col0 + (r >> 2) - kb, r & 3);
+      const double2 u = p[0], v = p[T];
+      double x0, x1, x2, x3;
+      linv4(d, u.x, u.y, v.x, v.y, x0, x1, x2, x3);
+      p[0] = make_double2(x0, x1); p[T] = make_double2(x2, x3);
+    }
+    double b0, b1, b2, b3, y0, y1, y2, y3;
+    pivot4<1>(G, xr, kb, exch, b0, b1, b2, b3);
+    linv4(d, b0, b1, b2, b3, y0, y1, y2, y3);
+    if (lane == 0) {
+      double2* o2 = reinterpret_cast<double2*>(x + 4 * kb);
+      o2[0] = make_double2(y0, y1); o2[1] = make_double2(y2, y3);
+    }
+    ok = G.all(ok);  // also the barrier between the panel and what reads it
+    if (!ok) return false;
+    if (lane == 0) cm.st(M2, col0, d);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int r = lane + s * 32;
+      if (r >= 4 * (kb + 1) && r < n4) {
+        const double2* p = cm.row(M2, col0 + (r >> 2) - kb, r & 3);
+        const double2 u = p[0], v = p[T];
+        xr[s] -= u.x * y0 + u.y * y1 + v.x * y2 + v.y * y3;
+      }
+    }
+    G.sync();
+    col0 += nrows;
+  }
+  return true;
+}
+
 // Backward substitution x = L^-T y, y read from the shared vector x, result written back to it.
 template <int W, int TT>
 __device__ __forceinline__ void bwd_cm(const Group<W>& G, const CM<TT>& cm, const double2* M2, int nblk, double* x, double* exch) {
@@ -451,7 +570,9 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
         for (int t = gtid; t < nd2; t += GT) __stcg(dst + t, M2[t]);
         G.sync();  // the factorisation overwrites M2 from its first panel on
       }
-      bool ok = chol_cm<W, TT>(G, cm, M2, nblk, s_tb, xr, s_x, s_exch);
+      bool ok;
+      if constexpr (W == 1) ok = chol_cm_mma<TT>(G, cm, M2, nblk, xr, s_x, s_exch);
+      else ok = chol_cm<W, TT>(G, cm, M2, nblk, s_tb, xr, s_x, s_exch);
       if (ok) {
         bwd_cm<W, TT>(G, cm, M2, nblk, s_x, s_exch);
         const int nd2 = 8 * cm.T();
