@@ -82,6 +82,7 @@ struct cmpc_handle {
   bool split = true;              // CMPC_SPLIT=0: never use the phase-split kernels
   int split_maxw = 2;             // CMPC_SPLIT_MAXW: widest warp group that uses them (measured: a gain for one warp per instance, a loss for four)
   int rip_minclass = 1;           // CMPC_RIPM_MINCLASS: smallest size class the stage-wise interior point takes in automatic mode
+  bool pdl = true;                // CMPC_PDL=0: plain stream order between the kernels of a call
   std::string err;
 };
 
@@ -559,6 +560,10 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
   const bool presolve = h->cfg.presolve && h->cfg.polish;
   const bool router = presolve && h->cls[0].used && presolve_kind(h, 0) == 1;
   const bool warm = a.warm_active != nullptr;
+  // every solver kernel after the first one of the call is launched with programmatic stream serialisation
+  // (pdl_prologue, cmpc_device.cuh): a kernel that finds its list empty then costs about a microsecond instead of four
+  a.pdl = 0;
+  auto chained = [&](SolveArgs& x) { x.pdl = (h->pdl && launches > 0) ? 1 : 0; };
   if (!router) {
     if (ready) return fail(h, CMPC_ERR_STATE, "progressive inputs need the presolve router");
     classify_kernel<<<(B + 31) / 32, 1024, 0, h->stream>>>(h->dev, B, a.des_inputs, h->bounds, h->d_counts, h->d_perm);
@@ -591,6 +596,7 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
         p.route_perm = h->d_perm; p.route_counts = h->d_counts; p.route_stride = B;
         p.ready = ready; p.ready_chunk = ready_chunk; p.error_flag = h->h_error_dev;
       }
+      chained(p);
       int rc = launch_presolve(h, h->cls[c], p);
       if (rc) return rc;
       ++launches;
@@ -607,6 +613,7 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
   }
   if (ric.nlists > 0) {
     ric.route = 0; ric.ready = nullptr;
+    chained(ric);
     int rc = launch_riccati(h, ric);
     if (rc) return rc;
     ++launches;
@@ -638,23 +645,28 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
         SolveArgs q = p;
         q.perm = in_perm[c]; q.count = in_count[c]; q.work = in_work[c];
         q.pol_perm = pol_perm; q.pol_count = pol_count; q.fb_perm = fb_perm; q.fb_count = fb_count;
+        chained(q);
         int rc = launch_class<0>(h, cp, q, 1);
         if (rc) return rc;
+        ++launches;
         q.perm = pol_perm; q.count = pol_count; q.work = pol_work;
+        chained(q);
         rc = launch_class<0>(h, cp, q, 2);
         if (rc) return rc;
-        launches += 2;
+        ++launches;
       }
       p.nlists = 2;
       p.lperm[0] = in_perm[c]; p.lcount[0] = in_count[c]; p.lwork[0] = in_work[c];
       p.lperm[1] = fb_perm; p.lcount[1] = fb_count; p.lwork[1] = fb_work;
       p.hint_out = h->h_hint_dev + c; p.hint_shadow = h->d_hint_shadow + c;
+      chained(p);
       int rc = launch_class<0>(h, cp, p);
       if (rc) return rc;
       ++launches;
     }
   }
   if (rip.nlists > 0) {
+    chained(rip);
     int rc = launch_ripm(h, rip);
     if (rc) return rc;
     ++launches;
@@ -836,6 +848,7 @@ static int setup_impl(cmpc_handle* h, int max_batch, int device) {
   if (const char* m = getenv("CMPC_SPLIT")) h->split = atoi(m) != 0;
   if (const char* m = getenv("CMPC_SPLIT_MAXW")) h->split_maxw = atoi(m);
   if (const char* m = getenv("CMPC_RIPM_MINCLASS")) h->rip_minclass = atoi(m);
+  if (const char* m = getenv("CMPC_PDL")) h->pdl = atoi(m) != 0;
   // size classes by number of free 3-blocks: n4 <= 64 -> one warp per instance, n4 <= 128 ->
   // four warps, larger -> a whole 256-thread CTA; the factor lives in shared memory whenever it fits
   {

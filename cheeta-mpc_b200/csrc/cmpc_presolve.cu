@@ -318,6 +318,7 @@ constexpr int kOutMap = 4;  // force-output slots per thread whose (step, leg, c
 template <int W, int TT>
 __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const DevConfig cfg, const SolveArgs args) {
   extern __shared__ __align__(128) double smem[];
+  pdl_prologue();
   constexpr int GT = Group<W>::GT;
   const int N = cfg.N, L = cfg.L;
   const int nf = 3 * L * N, nbfull = L * N, mfull = 5 * nbfull;
@@ -660,8 +661,7 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
 namespace {
 template <int W, int TT>
 cudaError_t launch_t(int grid, int block, size_t smem, cudaStream_t stream, const DevConfig& cfg, const SolveArgs& args) {
-  cmpc_presolve_kernel<W, TT><<<grid, block, smem, stream>>>(cfg, args);
-  return cudaGetLastError();
+  return launch_ex(cmpc_presolve_kernel<W, TT>, grid, block, smem, stream, args.pdl != 0, cfg, args);
 }
 }  // namespace
 

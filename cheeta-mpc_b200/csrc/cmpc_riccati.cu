@@ -109,6 +109,7 @@ __device__ __forceinline__ void tri_bwd(const double* Lf, double (&y)[kMu]) {
 
 __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, const SolveArgs args) {
   extern __shared__ __align__(128) double smem[];
+  pdl_prologue();
   constexpr int W = 1, GT = 32;
   const int N = cfg.N, L = cfg.L;
   const int nf = 3 * L, nz = 9 + nf, nfN = nf * N, nbfull = L * N, mfull = 5 * nbfull;
@@ -481,8 +482,7 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
 
 cudaError_t launch_riccati_kernel(int grid, int block, size_t smem, cudaStream_t stream, const DevConfig& cfg,
                                   const SolveArgs& args) {
-  cmpc_riccati_kernel<<<grid, block, smem, stream>>>(cfg, args);
-  return cudaGetLastError();
+  return launch_ex(cmpc_riccati_kernel, grid, block, smem, stream, args.pdl != 0, cfg, args);
 }
 
 cudaError_t set_riccati_kernel_smem(size_t bytes) {

@@ -631,6 +631,7 @@ __device__ __forceinline__ bool stage_instance(const DevConfig& cfg, const Solve
 }  // namespace
 
 __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant__ DevConfig cfg, const __grid_constant__ SolveArgs args) {
+  pdl_prologue();
   const int N = cfg.N, L = cfg.L;
   const int nf = 3 * L, nfN = nf * N, nbfull = L * N, mfull = 5 * nbfull;
   const int lane = threadIdx.x & 31, gid = threadIdx.x >> 5;
@@ -1233,8 +1234,7 @@ void ripm_sizes(int N, int L, int* group_doubles, int* cta_doubles, int* slab_do
 }
 
 cudaError_t launch_ripm_kernel(int grid, int block, size_t smem_bytes, cudaStream_t stream, const DevConfig& cfg, const SolveArgs& args) {
-  cmpc_ripm_kernel<<<grid, block, smem_bytes, stream>>>(cfg, args);
-  return cudaGetLastError();
+  return launch_ex(cmpc_ripm_kernel, grid, block, smem_bytes, stream, args.pdl != 0, cfg, args);
 }
 
 cudaError_t set_ripm_kernel_smem(size_t bytes) {

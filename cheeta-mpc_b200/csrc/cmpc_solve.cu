@@ -18,6 +18,7 @@ namespace cmpc {
 template <int W, int MODE, bool MS, int PHASE>
 __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256), 1) cmpc_solve_kernel(const DevConfig cfg, const SolveArgs args) {
   extern __shared__ __align__(128) double smem[];
+  pdl_prologue();
   constexpr int GT = Group<W>::GT;
   const int N = cfg.N, L = cfg.L, nu = 3 * L;
   const int nf = 3 * L * N;
@@ -713,8 +714,7 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256), 1) cmpc_s
 namespace {
 template <int W, int MODE, bool MS, int PHASE>
 cudaError_t launch_t(int grid, int block, size_t smem, cudaStream_t stream, const DevConfig& cfg, const SolveArgs& args) {
-  cmpc_solve_kernel<W, MODE, MS, PHASE><<<grid, block, smem, stream>>>(cfg, args);
-  return cudaGetLastError();
+  return launch_ex(cmpc_solve_kernel<W, MODE, MS, PHASE>, grid, block, smem, stream, args.pdl != 0, cfg, args);
 }
 template <int W, int MODE, bool MS, int PHASE>
 cudaError_t attr_t(size_t bytes) {
