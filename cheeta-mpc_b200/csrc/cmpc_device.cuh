@@ -350,6 +350,13 @@ __device__ __forceinline__ void pivot4(const Group<W>& G, const double (&xr)[2],
                                        double& b0, double& b1, double& b2, double& b3) {
   constexpr int GT = Group<W>::GT;
   const int r0 = 4 * kb;
+  if constexpr (W == 1) {  // one warp: straight out of the owners' registers
+    const double v = (r0 >= 32) ? xr[1] : xr[0];
+    const int l0 = r0 & 31;
+    b0 = __shfl_sync(0xffffffffu, v, l0); b1 = __shfl_sync(0xffffffffu, v, l0 + 1);
+    b2 = __shfl_sync(0xffffffffu, v, l0 + 2); b3 = __shfl_sync(0xffffffffu, v, l0 + 3);
+    return;
+  }
   double* buf = exch + ((kb & 1) << 2);  // double-buffered: one barrier per step
   const int q0 = G.gtid - (r0 % GT);
   if (q0 >= 0 && q0 < 4) buf[q0] = (r0 >= GT) ? xr[1] : xr[0];
@@ -1005,8 +1012,8 @@ __host__ __device__ inline PrePlan make_pre_plan(int N, int L, int W, int nbmax,
   PrePlan p;
   const int tiles = bc4_tiles(n4max);
   p.T = tiles | 1;
-  // CTA-shared tables: z1[N], z2[N] (z-weighted power-stacking sums), wf[3L], wr[3L]
-  p.cta = (2 * N + 6 * L + 1) & ~1;
+  // CTA-shared tables: z1[N], z2[N] (z-weighted power-stacking sums), s1[N], s2[N] (unit weights), wf[3L], wr[3L]
+  p.cta = (4 * N + 6 * L + 1) & ~1;
   int o = 0;
   auto take = [&](int cnt) { int r = o; o += (cnt + 1) & ~1; return r; };
   p.x = take(n4max);          // rhs staging, lever arms during the build, then y and the solution

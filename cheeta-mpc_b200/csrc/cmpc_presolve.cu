@@ -333,7 +333,9 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
   // CTA-shared tables
   double* c_z1 = smem;            // z1[j] = sum_{k >= j} (k - j + zeta) qz_k
   double* c_z2 = c_z1 + N;        // z2[j] = sum_{k >= j} (k - j + zeta)^2 qz_k
-  double* c_wf = c_z2 + N;        // force-tracking weights  (CentroidalMPC.cpp:223-225)
+  double* c_s1 = c_z2 + N;        // s1[j], s2[j]: the same sums with unit weights (x and y)
+  double* c_s2 = c_s1 + N;
+  double* c_wf = c_s2 + N;        // force-tracking weights  (CentroidalMPC.cpp:223-225)
   double* c_wr = c_wf + 3 * L;    // force-rate weights      (:227-231)
   double* base = smem + P.cta + (size_t)G.gid * P.total;
   G.red = base + P.red;
@@ -377,6 +379,9 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
       z1 += al * om * om; z2 += al * al * om * om;
     }
     c_z1[j] = z1; c_z2[j] = z2;
+    const double cnt = (double)(N - j);
+    c_s1[j] = 0.5 * cnt * (cnt - 1.0) + zeta * cnt;
+    c_s2[j] = (cnt - 1.0) * cnt * (2.0 * cnt - 1.0) * (1.0 / 6.0) + zeta * cnt * (cnt - 1.0) + zeta * zeta * cnt;
   }
   if ((int)threadIdx.x < 3 * L) {
     c_wf[threadIdx.x] = cfg.w[9 + 3 * L + threadIdx.x];
@@ -442,28 +447,39 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
     if (!defer) {
       // ---- g = 2 Bqp' L (Aqp x0 + dqp - Xref) - 2 W_f Uref: thread b owns block b (nb <= GT), adjoint
       // sums over the staged errors; the lever arm stays in registers until the staged inputs are dead
+      // suffix sums of the staged errors, in place: eq[9k + q] <- sum_{k' >= k} eq[9k' + q] for the velocity and
+      // angular-momentum rows, sum_{k' >= k} (k' - k + zeta) eq[9k' + q] for the position rows (lane q, serial in k)
+      if (gtid < 9) {
+        double S = 0.0, Pw = 0.0;
+        for (int k = N - 1; k >= 0; --k) {
+          const double e = V.eq[9 * k + gtid];
+          Pw += S + zeta * e;
+          S += e;
+          V.eq[9 * k + gtid] = gtid < 3 ? Pw : S;
+        }
+      }
+      G.sync();
       double arm[3] = {0.0, 0.0, 0.0};
       if (gtid < nb) {
         const int b = gtid, j = s_blk_j[b], i = s_blk_i[b];
         const double ce = s_ce[b];
         for (int q = 0; q < 3; ++q) arm[q] = Mm[ns + nds + i * (4 * N + 3) + N + 3 * j + q] - Mm[ns + 3 * j + q];
-        double sp[3] = {0, 0, 0}, sv[3] = {0, 0, 0}, sl3[3] = {0, 0, 0};
-        for (int k = j; k < N; ++k) {
-          const double al = (double)(k - j) + zeta;
-          for (int q = 0; q < 3; ++q) { sp[q] += al * V.eq[9 * k + q]; sv[q] += V.eq[9 * k + 3 + q]; sl3[q] += V.eq[9 * k + 6 + q]; }
-        }
+        const double* e9 = V.eq + 9 * j;
+        const double sl3[3] = {e9[6], e9[7], e9[8]};
         const double cmass = ce / mass;
         const double cr[3] = {sl3[1] * arm[2] - sl3[2] * arm[1], sl3[2] * arm[0] - sl3[0] * arm[2], sl3[0] * arm[1] - sl3[1] * arm[0]};
         for (int q = 0; q < 3; ++q) {
-          double gq = 2.0 * (cmass * (dt * dt * sp[q] + dt * sv[q]) + dt * ce * cr[q]);
+          double gq = 2.0 * (cmass * (dt * dt * e9[q] + dt * e9[3 + q]) + dt * ce * cr[q]);
           if (q == 2) gq -= 2.0 * c_wf[3 * i + 2] * V.fz[b];
           s_x[3 * b + q] = gq;
         }
       }
       if (gtid < n4 - n) s_x[n + gtid] = 0.0;
-      for (int bj = gtid; bj < nblk; bj += GT) {
-        const int o = blkoff(bj, bj, nblk);
-        for (int bi = bj; bi < nblk; ++bi) s_tb[o + bi - bj] = (uint16_t)(bi | (bj << 8));
+      if constexpr (W > 1) {  // tile table of the right-looking sweep (the one-warp sweep does not use it)
+        for (int bj = gtid; bj < nblk; bj += GT) {
+          const int o = blkoff(bj, bj, nblk);
+          for (int bi = bj; bi < nblk; ++bi) s_tb[o + bi - bj] = (uint16_t)(bi | (bj << 8));
+        }
       }
       G.sync();
 #pragma unroll
@@ -501,9 +517,7 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
           const double r0 = s_x[3 * b], r1 = s_x[3 * b + 1], r2 = s_x[3 * b + 2];
           const double p0 = s_x[3 * b2], p1 = s_x[3 * b2 + 1], p2 = s_x[3 * b2 + 2];
           const double cnt = (double)(N - j), dd = (double)(j - j2);
-          const double s1 = 0.5 * cnt * (cnt - 1.0) + zeta * cnt;
-          const double s2 = (cnt - 1.0) * cnt * (2.0 * cnt - 1.0) * (1.0 / 6.0) + zeta * cnt * (cnt - 1.0) + zeta * zeta * cnt;
-          const double s0 = s2 + dd * s1, sz = c_z2[j] + dd * c_z1[j];
+          const double s0 = c_s2[j] + dd * c_s1[j], sz = c_z2[j] + dd * c_z1[j];
           const double cc = ce * ce2;
           const double sc = cnt * dt2 * cc, cmm = cc * im2;
           double blk[3][3];
@@ -546,11 +560,13 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
           }
         };
         const int nfar = nb >= 3 ? ((nb - 1) * (nb - 2)) >> 1 : 0;
-        for (int idx = gtid; idx < nfar; idx += GT) {
-          int a = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
-          while (((a + 1) * (a + 2)) >> 1 <= idx) ++a;
-          while ((a * (a + 1)) >> 1 > idx) --a;
-          do_pair(a + 2, idx - ((a * (a + 1)) >> 1), std::true_type{});
+        {  // pair idx = a (a + 1) / 2 + rem, 0 <= rem <= a: block row a + 2, block column rem; decoded incrementally
+          int a = 0, rem = gtid;
+          for (int idx = gtid; idx < nfar; idx += GT) {
+            while (rem > a) { rem -= a + 1; ++a; }
+            do_pair(a + 2, rem, std::true_type{});
+            rem += GT;
+          }
         }
         for (int idx = gtid; idx < 2 * nb - 1; idx += GT) {
           const int b = (idx + 1) >> 1;
