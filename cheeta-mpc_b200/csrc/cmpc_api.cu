@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <string>
@@ -72,6 +73,7 @@ struct cmpc_handle {
   // wins depends on the box: DMA 35-56 GB/s vs ~26 GB/s SM-issued reads), then the faster one is kept
   int e2e_chunk = 0;                 // CMPC_E2E_CHUNK: instances per copy chunk (0: default of the route)
   bool debug_tune = false;           // CMPC_DEBUG_TUNE: print the route timings of the tuning calls
+  bool debug_timeline = false;       // CMPC_DEBUG_TIMELINE: print where the events of a host-buffer call fell (ms from its start)
   int tune_calls = 0, tune_batch = 0;
   float tune_best[3] = {1e30f, 1e30f, 1e30f};  // [0] zero-copy, [1] pipelined, [2] full duplex: best span in ms
   char route[96] = "none";           // what the last cmpc_solve_batch call did (cmpc_last_route)
@@ -838,6 +840,7 @@ static int setup_impl(cmpc_handle* h, int max_batch, int device) {
   if (const char* m = getenv("CMPC_E2E_MODE")) h->e2e_mode = atoi(m);
   if (const char* m = getenv("CMPC_E2E_CHUNK")) h->e2e_chunk = atoi(m);
   h->debug_tune = getenv("CMPC_DEBUG_TUNE") != nullptr;
+  h->debug_timeline = getenv("CMPC_DEBUG_TIMELINE") != nullptr;
   CUDA_TRY(h, cudaMalloc(&h->d_counts, 8 * kNumClasses * sizeof(int32_t)));
   CUDA_TRY(h, cudaMalloc(&h->d_perm, (size_t)4 * kNumClasses * B * sizeof(int32_t)));
   CUDA_TRY(h, cudaHostAlloc(&h->h_hint, kNumClasses * sizeof(int32_t), cudaHostAllocMapped));
@@ -1005,6 +1008,7 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
   if (B < 0 || B > h->max_batch) return fail(h, CMPC_ERR_STATE, "batch exceeds max_batch given to cmpc_setup");
   if (!state || !des_state || !des_inputs || !forces || !status) return fail(h, CMPC_ERR_ARG, "null buffer");
   if (B == 0) { if (stats) std::memset(stats, 0, sizeof(*stats)); return CMPC_OK; }
+  const auto t_enter = std::chrono::steady_clock::now();
   SET_DEVICE(h);
   const int N = h->cfg.horizon, L = h->cfg.num_legs;
   const size_t ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = (size_t)L * (4 * N + 3), nf = (size_t)3 * L * N;
@@ -1155,10 +1159,20 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
     if (active) CUDA_TRY(h, cudaMemcpyAsync(active, h->d_active, (size_t)B * L * N * 2, cudaMemcpyDeviceToHost, s));
   }
   CUDA_TRY(h, cudaEventRecord(h->ev_span[3], s));
+  const auto t_enq = std::chrono::steady_clock::now();
   if (progressive || pipelined) CUDA_TRY(h, cudaStreamSynchronize(h->s_in));
   if (duplex) CUDA_TRY(h, cudaStreamSynchronize(h->s_out));
   CUDA_TRY(h, cudaStreamSynchronize(s));
   if (*h->h_error) { *h->h_error = 0; return fail(h, CMPC_ERR_CUDA, "cmpc_solve_batch: input chunk did not arrive (copy stream stalled)"); }
+  if (h->debug_timeline) {
+    const auto t_done = std::chrono::steady_clock::now();
+    auto us = [&](std::chrono::steady_clock::time_point a_, std::chrono::steady_clock::time_point b_) { return std::chrono::duration<double, std::micro>(b_ - a_).count(); };
+    fprintf(stderr, "[cmpc] timeline: host enqueue %.0f us, host total %.0f us; device (us from start):", us(t_enter, t_enq), us(t_enter, t_done));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev_span[0], h->ev_span[1]); fprintf(stderr, " copy-in-end %.0f", ms * 1e3f);
+    cudaEventElapsedTime(&ms, h->ev_span[0], h->ev_span[2]); fprintf(stderr, " kernels-end %.0f", ms * 1e3f);
+    cudaEventElapsedTime(&ms, h->ev_span[0], h->ev_span[3]); fprintf(stderr, " end %.0f\n", ms * 1e3f);
+  }
   if (tunable && h->tune_calls < 8) {
     float span = 0;
     CUDA_TRY(h, cudaEventElapsedTime(&span, h->ev_span[0], h->ev_span[3]));
