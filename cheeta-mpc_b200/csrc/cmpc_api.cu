@@ -84,6 +84,12 @@ struct cmpc_handle {
   bool split = true;              // CMPC_SPLIT=0: never use the phase-split kernels
   int split_maxw = 2;             // CMPC_SPLIT_MAXW: widest warp group that uses them (measured: a gain for one warp per instance, a loss for four)
   int rip_minclass = 1;           // CMPC_RIPM_MINCLASS: smallest size class the stage-wise interior point takes in automatic mode
+  int rip_phase_lock = -1;        // CMPC_RIPM_LOCK (-1: automatic, on from horizon 20): CTA barrier in front of every factor sweep of the stage-wise interior point
+  int pdl_trigger = -1;           // CMPC_PDL_TRIGGER: which kernels let their dependents be scheduled from their first instruction on
+                                  // (0 none: as their CTAs retire; 1 the presolve kernels; 2 all; -1 automatic).  Measured: 2 is best on the
+                                  // headline (the three empty kernels are resident and gone by the time the presolve ends: +1.5 % over 0),
+                                  // 1 and 2 cost 4 % at horizon 30 where the stage-wise presolve does the work (config 3): automatic = 2
+                                  // below horizon 20, else 0
   bool pdl = true;                // CMPC_PDL=0: plain stream order between the kernels of a call
   std::string err;
 };
@@ -518,6 +524,8 @@ int launch_ripm(cmpc_handle* h, SolveArgs a) {
   a.scratch = h->d_rip_scratch;
   a.scratch_per_group = h->rip_slab;
   a.nbmax = h->cfg.horizon * h->cfg.num_legs; a.n4max = 0; a.m_in_smem = 1; a.groups = h->rip_groups;
+  // measured: +13 % at horizon 30 (instruction fetch is what the warps of an SM compete for), -2 % at horizon 10
+  a.phase_lock = h->rip_phase_lock >= 0 ? h->rip_phase_lock : (h->cfg.horizon >= 20 ? 1 : 0);
   const cudaError_t e = launch_ripm_kernel(h->num_sms, 32 * h->rip_groups, h->rip_smem_bytes, h->stream, h->dev, a);
   if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, std::string("stage-wise interior-point launch: ") + cudaGetErrorString(e));
   return CMPC_OK;
@@ -565,6 +573,7 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
   // every solver kernel after the first one of the call is launched with programmatic stream serialisation
   // (pdl_prologue, cmpc_device.cuh): a kernel that finds its list empty then costs about a microsecond instead of four
   a.pdl = 0;
+  a.pdl_trigger = h->pdl_trigger >= 0 ? h->pdl_trigger : (h->cfg.horizon < 20 ? 2 : 0);
   auto chained = [&](SolveArgs& x) { x.pdl = (h->pdl && launches > 0) ? 1 : 0; };
   if (!router) {
     if (ready) return fail(h, CMPC_ERR_STATE, "progressive inputs need the presolve router");
@@ -852,6 +861,8 @@ static int setup_impl(cmpc_handle* h, int max_batch, int device) {
   if (const char* m = getenv("CMPC_SPLIT_MAXW")) h->split_maxw = atoi(m);
   if (const char* m = getenv("CMPC_RIPM_MINCLASS")) h->rip_minclass = atoi(m);
   if (const char* m = getenv("CMPC_PDL")) h->pdl = atoi(m) != 0;
+  if (const char* m = getenv("CMPC_PDL_TRIGGER")) h->pdl_trigger = atoi(m);
+  if (const char* m = getenv("CMPC_RIPM_LOCK")) h->rip_phase_lock = atoi(m);
   // size classes by number of free 3-blocks: n4 <= 64 -> one warp per instance, n4 <= 128 ->
   // four warps, larger -> a whole 256-thread CTA; the factor lives in shared memory whenever it fits
   {

@@ -110,6 +110,8 @@ struct SolveArgs {
   // Several lists in one launch (stage-wise kernels: their code does not depend on the size class).  nlists > 0: the
   // persistent loop drains list 0, then list 1, ... (largest class first: its instances take longest, so they must not be
   // left for a partial wave at the end); perm / count / work / fail_* above are ignored.
+  int phase_lock;  // stage-wise interior point: CTA barrier in front of every factor sweep (instruction-cache sharing)
+  int pdl_trigger;  // the kernel lets its dependents be scheduled from its first instruction on (1: presolve kernels, 2: all); else as its CTAs retire
   int pdl;  // host side only: launch with programmatic stream serialisation (the kernel before it on the stream is one of ours)
   int nlists;
   const int32_t* lperm[kNumClasses];
@@ -159,8 +161,8 @@ __host__ __device__ inline int mat_region_doubles(int N, int L, int n4max) {
 // be scheduled early (its CTAs become resident as this grid's CTAs retire instead of after a full drain) and waits until
 // the kernel before it has completed and its writes are visible.  Both are no-ops for a launch without the attribute.
 // A headline step launches three kernels that find their lists empty; back to back they cost 11 us of a 137 us step.
-__device__ __forceinline__ void pdl_prologue() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+__device__ __forceinline__ void pdl_prologue(bool trigger = true) {
+  if (trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 

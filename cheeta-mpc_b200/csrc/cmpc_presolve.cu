@@ -318,7 +318,7 @@ constexpr int kOutMap = 4;  // force-output slots per thread whose (step, leg, c
 template <int W, int TT>
 __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const DevConfig cfg, const SolveArgs args) {
   extern __shared__ __align__(128) double smem[];
-  pdl_prologue();
+  pdl_prologue(args.pdl_trigger != 0);
   constexpr int GT = Group<W>::GT;
   const int N = cfg.N, L = cfg.L;
   const int nf = 3 * L * N, nbfull = L * N, mfull = 5 * nbfull;

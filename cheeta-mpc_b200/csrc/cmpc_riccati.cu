@@ -109,7 +109,7 @@ __device__ __forceinline__ void tri_bwd(const double* Lf, double (&y)[kMu]) {
 
 __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, const SolveArgs args) {
   extern __shared__ __align__(128) double smem[];
-  pdl_prologue();
+  pdl_prologue(args.pdl_trigger > 1);
   constexpr int W = 1, GT = 32;
   const int N = cfg.N, L = cfg.L;
   const int nf = 3 * L, nz = 9 + nf, nfN = nf * N, nbfull = L * N, mfull = 5 * nbfull;

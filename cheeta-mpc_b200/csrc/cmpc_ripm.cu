@@ -631,7 +631,7 @@ __device__ __forceinline__ bool stage_instance(const DevConfig& cfg, const Solve
 }  // namespace
 
 __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant__ DevConfig cfg, const __grid_constant__ SolveArgs args) {
-  pdl_prologue();
+  pdl_prologue(args.pdl_trigger > 1);
   const int N = cfg.N, L = cfg.L;
   const int nf = 3 * L, nfN = nf * N, nbfull = L * N, mfull = 5 * nbfull;
   const int lane = threadIdx.x & 31, gid = threadIdx.x >> 5;
@@ -844,6 +844,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
           stage_gradient(N, L, gb, lane, y_.rd, g_dua);  // H f0 + g
           for (int t = lane; t < nfN; t += 32) s_du[t] = -g_dua[t];
           __syncwarp();
+          if (args.phase_lock) __syncthreads_and(0);
           if (!lqr_factor(N, L, gb, lane, 2, fac, g_Rs)) break;
           lqr_forward(N, L, gb, lane, fac, y_.du);
           for (int t = lane; t < nfN; t += 32) s_du[t] += s_rd[t];  // candidate point up = f0 + Z t
@@ -950,6 +951,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
         for (int q = 0; q < 3; ++q) s_du[3 * tb + q] = -s_rd[3 * tb + q] + o[q];
       }
       __syncwarp();
+      if (args.phase_lock) __syncthreads_and(0);
       if (!lqr_factor(N, L, gb, lane, 1, fac, g_Rs)) { numerical = true; break; }
 
       double tmax = 0.0, sigma = 0.0;
@@ -1176,6 +1178,9 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
     }
     __syncwarp();
   }
+  // phase lock: the warps of the CTA enter the factor sweep (half of all instructions) together, so that they share its
+  // instruction fetches; a warp that has run out of work keeps the others' barriers company until everybody is done
+  if (args.phase_lock) while (!__syncthreads_and(1)) {}
 }
 
 // Diagnostic / parity entry (cmpc_stage_step_batch): the stage-wise linear algebra alone.  For every instance:

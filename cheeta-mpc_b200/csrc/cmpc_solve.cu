@@ -18,7 +18,7 @@ namespace cmpc {
 template <int W, int MODE, bool MS, int PHASE>
 __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256), 1) cmpc_solve_kernel(const DevConfig cfg, const SolveArgs args) {
   extern __shared__ __align__(128) double smem[];
-  pdl_prologue();
+  pdl_prologue(args.pdl_trigger > 1);
   constexpr int GT = Group<W>::GT;
   const int N = cfg.N, L = cfg.L, nu = 3 * L;
   const int nf = 3 * L * N;
