@@ -31,6 +31,11 @@ struct cmpc_handle {
   // progressive host-buffer path of cmpc_solve_batch: chunked copy-in on its own stream
   static constexpr int kMaxChunks = 8;
   cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaStream_t s_aux = nullptr;      // launch_solve: the stage-wise interior point next to the condensed kernels (fork / join by events)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap = true;               // CMPC_OVERLAP=0: one stream, the routes one after the other
+  bool overlap_trim = true;          // CMPC_OVERLAP_TRIM=0: full grid for the interior-point phase kernel next to the stage-wise kernel
+  int overlap_pct = 100;             // CMPC_OVERLAP_PCT: CTAs of the stage-wise kernel in percent of what its expected instances fill
   cudaEvent_t ev_span[4] = {}, ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {};
   // device buffers
   double *d_state = nullptr, *d_ds = nullptr, *d_di = nullptr, *d_forces = nullptr, *d_kkt = nullptr,
@@ -73,6 +78,7 @@ struct cmpc_handle {
   // wins depends on the box: DMA 35-56 GB/s vs ~26 GB/s SM-issued reads), then the faster one is kept
   int e2e_chunk = 0;                 // CMPC_E2E_CHUNK: instances per copy chunk (0: default of the route)
   bool debug_tune = false;           // CMPC_DEBUG_TUNE: print the route timings of the tuning calls
+  bool debug_plan = false;           // CMPC_DEBUG_PLAN: print the launch plan of every call
   bool debug_timeline = false;       // CMPC_DEBUG_TIMELINE: print where the events of a host-buffer call fell (ms from its start)
   int tune_calls = 0, tune_batch = 0;
   float tune_best[3] = {1e30f, 1e30f, 1e30f};  // [0] zero-copy, [1] pipelined, [2] full duplex: best span in ms
@@ -84,6 +90,9 @@ struct cmpc_handle {
   bool split = true;              // CMPC_SPLIT=0: never use the phase-split kernels
   int split_maxw = 2;             // CMPC_SPLIT_MAXW: widest warp group that uses them (measured: a gain for one warp per instance, a loss for four)
   int rip_minclass = 1;           // CMPC_RIPM_MINCLASS: smallest size class the stage-wise interior point takes in automatic mode
+  int dense_lock = 4;             // CMPC_DENSE_LOCK: bit p = CTA barrier in front of every polish pass of the phase-p condensed kernel (bit 3: and
+                                  // in front of the reduced factorisation).  Measured on the constrained horizon-10 workload: polish kernel
+                                  // (bit 2) +4.5 %, the fused kernel (bit 0) -2 % on ipm_only, second barrier +0.7 %
   int rip_phase_lock = -1;        // CMPC_RIPM_LOCK (-1: automatic, on from horizon 20): CTA barrier in front of every factor sweep of the stage-wise interior point
   int pdl_trigger = -1;           // CMPC_PDL_TRIGGER: which kernels let their dependents be scheduled from their first instruction on
                                   // (0 none: as their CTAs retire; 1 the presolve kernels; 2 all; -1 automatic).  Measured: 2 is best on the
@@ -490,13 +499,14 @@ void fill_dev(cmpc_handle* h) {
 }
 
 template <int MODE>
-int launch_class(cmpc_handle* h, const cmpc_handle::ClassPlan& p, SolveArgs a, int phase = 0) {
+int launch_class(cmpc_handle* h, const cmpc_handle::ClassPlan& p, SolveArgs a, int phase = 0, int grid = 0) {
   a.scratch = p.d_scratch; a.scratch_per_group = p.scratch_per_group;
   a.xstate = p.d_xstate; a.xstride = p.xstride;
   a.nbmax = p.nbmax; a.n4max = p.n4max; a.m_in_smem = p.m_in_smem; a.groups = p.groups;
   a.plan = make_plan(h->cfg.horizon, h->cfg.num_legs, p.m_in_smem ? p.W : 8, p.nbmax, p.n4max, p.m_in_smem);
+  a.phase_lock = (MODE == 0 && ((h->dense_lock >> phase) & 1)) ? 1 + ((h->dense_lock >> 3) & 1) : 0;
   const int W = (MODE == 1 || !p.m_in_smem) ? 8 : p.W;
-  const cudaError_t e = launch_solve_kernel(W, MODE, p.m_in_smem != 0, phase, p.grid, 32 * W * p.groups, p.smem_bytes, h->stream, h->dev, a);
+  const cudaError_t e = launch_solve_kernel(W, MODE, p.m_in_smem != 0, phase, grid > 0 ? grid : p.grid, 32 * W * p.groups, p.smem_bytes, h->stream, h->dev, a);
   if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
   return CMPC_OK;
 }
@@ -520,13 +530,14 @@ int launch_riccati(cmpc_handle* h, SolveArgs a) {
   return CMPC_OK;
 }
 
-int launch_ripm(cmpc_handle* h, SolveArgs a) {
+int launch_ripm(cmpc_handle* h, SolveArgs a, int grid = 0, cudaStream_t stream = nullptr) {
   a.scratch = h->d_rip_scratch;
   a.scratch_per_group = h->rip_slab;
   a.nbmax = h->cfg.horizon * h->cfg.num_legs; a.n4max = 0; a.m_in_smem = 1; a.groups = h->rip_groups;
   // measured: +13 % at horizon 30 (instruction fetch is what the warps of an SM compete for), -2 % at horizon 10
   a.phase_lock = h->rip_phase_lock >= 0 ? h->rip_phase_lock : (h->cfg.horizon >= 20 ? 1 : 0);
-  const cudaError_t e = launch_ripm_kernel(h->num_sms, 32 * h->rip_groups, h->rip_smem_bytes, h->stream, h->dev, a);
+  a.hint_out = h->h_hint_dev + kNumClasses; a.hint_shadow = h->d_hint_shadow + kNumClasses;
+  const cudaError_t e = launch_ripm_kernel(grid > 0 ? grid : h->num_sms, 32 * h->rip_groups, h->rip_smem_bytes, stream ? stream : h->stream, h->dev, a);
   if (e != cudaSuccess) return fail(h, CMPC_ERR_CUDA, std::string("stage-wise interior-point launch: ") + cudaGetErrorString(e));
   return CMPC_OK;
 }
@@ -632,6 +643,7 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
   // ---- interior point + polish for what is left: the condensed kernel per class, ONE stage-wise launch for its classes
   SolveArgs rip = a;
   rip.route = 0; rip.ready = nullptr; rip.fail_perm = nullptr; rip.fail_count = nullptr;
+  int dense_expected = 0;
   for (int c = 0; c < kNumClasses; ++c) {
     if (!h->cls[c].used) continue;
     if (ipm_kind(h, c, warm)) {
@@ -639,6 +651,32 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
       rip.lperm[0] = in_perm[c]; rip.lcount[0] = in_count[c]; rip.lwork[0] = in_work[c];
       ++rip.nlists;
     } else {
+      dense_expected += h->h_hint[c];
+    }
+  }
+  // Both routes busy (by the previous call's counts): the stage-wise kernel is latency-bound -- a few hundred stand
+  // instances are one wave of 1.9 ms on half of the SMs -- so it runs on its own stream on just the CTAs it can fill,
+  // next to the condensed kernels (whose CTAs are persistent: the ones that find their SM taken start late and join the
+  // work loop).  A wrong guess only costs time.
+  int rip_grid = 0;
+  if (h->overlap && rip.nlists > 0 && dense_expected > 0 && h->h_hint[kNumClasses] > 0) {
+    rip_grid = ((h->h_hint[kNumClasses] + h->rip_groups - 1) / h->rip_groups * h->overlap_pct + 99) / 100;
+    if (rip_grid > (h->num_sms * 5) / 8) rip_grid = 0;  // it would take most of the device anyway
+  }
+  if (h->debug_plan) fprintf(stderr, "[cmpc] plan: hints dense %d stage-wise %d -> stage-wise grid %d%s\n", dense_expected, h->h_hint[kNumClasses], rip_grid, rip_grid > 0 ? " (own stream)" : "");
+  if (rip_grid > 0) {
+    if (cudaEventRecord(h->ev_fork, h->stream) != cudaSuccess || cudaStreamWaitEvent(h->s_aux, h->ev_fork, 0) != cudaSuccess)
+      return fail(h, CMPC_ERR_CUDA, "fork to the auxiliary stream");
+    rip.pdl = 0;
+    int rc = launch_ripm(h, rip, rip_grid, h->s_aux);
+    if (rc) return rc;
+    ++launches;
+    if (cudaEventRecord(h->ev_join, h->s_aux) != cudaSuccess) return fail(h, CMPC_ERR_CUDA, "join event");
+  }
+  bool first_dense = true;
+  for (int c = 0; c < kNumClasses; ++c) {
+    if (!h->cls[c].used || ipm_kind(h, c, warm)) continue;
+    {
       // Condensed route.  Behind the presolve (what is left then is the constrained part of the batch: iteration counts
       // and polish passes differ from instance to instance, so the warps of an SM drift through different phases of
       // the fused kernel and thrash the instruction cache), and when the previous call found instances on this class's
@@ -652,16 +690,20 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
       int32_t* pol_count = h->d_counts + 4 * kNumClasses + c; int32_t* pol_work = h->d_counts + 5 * kNumClasses + c;
       int32_t* fb_count = h->d_counts + 6 * kNumClasses + c; int32_t* fb_work = h->d_counts + 7 * kNumClasses + c;
       const cmpc_handle::ClassPlan& cp = h->cls[c];
+      // (next to the stage-wise kernel no early trigger: the resident-but-waiting CTAs of the next kernel would take the SMs
+      // the stage-wise kernel is meant to get -- whichever arrived first won, and the routes ran one after the other)
+      auto chain = [&](SolveArgs& x) { chained(x); if (rip_grid > 0) { x.pdl_trigger = 0; if (first_dense) x.pdl = 0; } first_dense = false; };
       if (h->split && presolve && !warm && h->cfg.polish && cp.m_in_smem && cp.W <= h->split_maxw && cp.d_xstate && h->h_hint[c] > 0) {
         SolveArgs q = p;
         q.perm = in_perm[c]; q.count = in_count[c]; q.work = in_work[c];
         q.pol_perm = pol_perm; q.pol_count = pol_count; q.fb_perm = fb_perm; q.fb_count = fb_count;
-        chained(q);
-        int rc = launch_class<0>(h, cp, q, 1);
+        chain(q);
+        // (next to the stage-wise kernel: only the CTAs that find a free SM, so that the polish does not wait for late-comers)
+        int rc = launch_class<0>(h, cp, q, 1, rip_grid > 0 && h->overlap_trim ? std::max(1, h->num_sms - rip_grid) : 0);
         if (rc) return rc;
         ++launches;
         q.perm = pol_perm; q.count = pol_count; q.work = pol_work;
-        chained(q);
+        chain(q);
         rc = launch_class<0>(h, cp, q, 2);
         if (rc) return rc;
         ++launches;
@@ -670,13 +712,15 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
       p.lperm[0] = in_perm[c]; p.lcount[0] = in_count[c]; p.lwork[0] = in_work[c];
       p.lperm[1] = fb_perm; p.lcount[1] = fb_count; p.lwork[1] = fb_work;
       p.hint_out = h->h_hint_dev + c; p.hint_shadow = h->d_hint_shadow + c;
-      chained(p);
+      chain(p);
       int rc = launch_class<0>(h, cp, p);
       if (rc) return rc;
       ++launches;
     }
   }
-  if (rip.nlists > 0) {
+  if (rip_grid > 0) {
+    if (cudaStreamWaitEvent(h->stream, h->ev_join, 0) != cudaSuccess) return fail(h, CMPC_ERR_CUDA, "join the auxiliary stream");
+  } else if (rip.nlists > 0) {
     chained(rip);
     int rc = launch_ripm(h, rip);
     if (rc) return rc;
@@ -774,6 +818,9 @@ static void release_device_state(cmpc_handle* h) {
   for (auto& e : h->ev_k) if (e) { cudaEventDestroy(e); e = nullptr; }
   if (h->s_in) { cudaStreamDestroy(h->s_in); h->s_in = nullptr; }
   if (h->s_out) { cudaStreamDestroy(h->s_out); h->s_out = nullptr; }
+  if (h->s_aux) { cudaStreamDestroy(h->s_aux); h->s_aux = nullptr; }
+  if (h->ev_fork) { cudaEventDestroy(h->ev_fork); h->ev_fork = nullptr; }
+  if (h->ev_join) { cudaEventDestroy(h->ev_join); h->ev_join = nullptr; }
   if (h->own_stream && h->stream) { cudaStreamDestroy(h->stream); h->stream = nullptr; h->own_stream = false; }
   h->ric_used = h->rip_used = false;
   h->ready = false; h->max_batch = 0; h->flog_cap = 0;
@@ -818,6 +865,12 @@ static int setup_impl(cmpc_handle* h, int max_batch, int device) {
   for (auto& e : h->ev) CUDA_TRY(h, cudaEventCreate(&e));
   CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
   CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+  CUDA_TRY(h, cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking));
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  if (const char* m = getenv("CMPC_OVERLAP")) h->overlap = atoi(m) != 0;
+  if (const char* m = getenv("CMPC_OVERLAP_TRIM")) h->overlap_trim = atoi(m) != 0;
+  if (const char* m = getenv("CMPC_OVERLAP_PCT")) h->overlap_pct = std::max(25, std::min(400, atoi(m)));
   for (auto& e : h->ev_k) CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : h->ev_span) CUDA_TRY(h, cudaEventCreate(&e));
   for (auto& e : h->ev_in) CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -850,19 +903,21 @@ static int setup_impl(cmpc_handle* h, int max_batch, int device) {
   if (const char* m = getenv("CMPC_E2E_CHUNK")) h->e2e_chunk = atoi(m);
   h->debug_tune = getenv("CMPC_DEBUG_TUNE") != nullptr;
   h->debug_timeline = getenv("CMPC_DEBUG_TIMELINE") != nullptr;
+  h->debug_plan = getenv("CMPC_DEBUG_PLAN") != nullptr;
   CUDA_TRY(h, cudaMalloc(&h->d_counts, 8 * kNumClasses * sizeof(int32_t)));
   CUDA_TRY(h, cudaMalloc(&h->d_perm, (size_t)4 * kNumClasses * B * sizeof(int32_t)));
-  CUDA_TRY(h, cudaHostAlloc(&h->h_hint, kNumClasses * sizeof(int32_t), cudaHostAllocMapped));
-  for (int c = 0; c < kNumClasses; ++c) h->h_hint[c] = 0;
+  CUDA_TRY(h, cudaHostAlloc(&h->h_hint, (kNumClasses + 1) * sizeof(int32_t), cudaHostAllocMapped));  // [kNumClasses]: the stage-wise interior point's lists
+  for (int c = 0; c <= kNumClasses; ++c) h->h_hint[c] = 0;
   CUDA_TRY(h, cudaHostGetDevicePointer((void**)&h->h_hint_dev, h->h_hint, 0));
-  CUDA_TRY(h, cudaMalloc(&h->d_hint_shadow, kNumClasses * sizeof(int32_t)));
-  CUDA_TRY(h, cudaMemset(h->d_hint_shadow, 0, kNumClasses * sizeof(int32_t)));
+  CUDA_TRY(h, cudaMalloc(&h->d_hint_shadow, (kNumClasses + 1) * sizeof(int32_t)));
+  CUDA_TRY(h, cudaMemset(h->d_hint_shadow, 0, (kNumClasses + 1) * sizeof(int32_t)));
   if (const char* m = getenv("CMPC_SPLIT")) h->split = atoi(m) != 0;
   if (const char* m = getenv("CMPC_SPLIT_MAXW")) h->split_maxw = atoi(m);
   if (const char* m = getenv("CMPC_RIPM_MINCLASS")) h->rip_minclass = atoi(m);
   if (const char* m = getenv("CMPC_PDL")) h->pdl = atoi(m) != 0;
   if (const char* m = getenv("CMPC_PDL_TRIGGER")) h->pdl_trigger = atoi(m);
   if (const char* m = getenv("CMPC_RIPM_LOCK")) h->rip_phase_lock = atoi(m);
+  if (const char* m = getenv("CMPC_DENSE_LOCK")) h->dense_lock = atoi(m);
   // size classes by number of free 3-blocks: n4 <= 64 -> one warp per instance, n4 <= 128 ->
   // four warps, larger -> a whole 256-thread CTA; the factor lives in shared memory whenever it fits
   {

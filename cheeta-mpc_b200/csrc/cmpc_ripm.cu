@@ -655,6 +655,8 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
     const int c = args.nlists > 0 ? *args.lcount[q] : (args.count ? *args.count : args.count_imm);
     total += c > 0 ? c : 0;
   }
+  // launch planning: the host reads this word before the next call (written only when it changes)
+  if (args.hint_out && blockIdx.x == 0 && threadIdx.x == 0 && *args.hint_shadow != total) { *args.hint_shadow = total; *args.hint_out = total; }
   if (total <= 0) return;  // nothing to do (uniform over the grid)
   fill_header(cfg);
   int li = 0;

@@ -277,6 +277,7 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256), 1) cmpc_s
         // ---- active-set polish with correction passes
         bool accepted = false;
         for (int pass = 0; pass < 6 && !accepted; ++pass) {
+          if (args.phase_lock) __syncthreads_and(0);  // the groups of the CTA enter a polish pass together (shared instruction fetch)
           int nr, nblk_r;
           if (none_active) {
             // no active row: Z = I, f0 = 0, the reduced system is (H, -g) itself
@@ -371,6 +372,7 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256), 1) cmpc_s
           }
           m_is_h = false;
           bool fact_ok = true;
+          if (args.phase_lock > 1) __syncthreads_and(0);
           if (nr > 0) {
             fact_ok = chol_bc4<W>(G, Mm, nblk_r, s_tb, s_tv, s_exch);  // forward pass fused
             if (fact_ok) chol_bwd_bc4<W>(G, Mm, nblk_r, s_tv, s_exch);
@@ -708,6 +710,7 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256), 1) cmpc_s
     }
     G.sync();
   }
+  if (args.phase_lock) while (!__syncthreads_and(1)) {}  // keep the other groups' barriers company until everybody is done
 }
 
 

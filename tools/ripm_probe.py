@@ -59,23 +59,25 @@ def stage(pkg, wl, N):
     m.close()
 
 
-def timed(pkg, cfg, st, ds, di, steps=10, warmup=3):
+def timed(pkg, cfg, st, ds, di, steps=10, warmup=3, default_stream=False):
     import torch
     B = len(st)
     mpc = pkg.CentroidalMPC.from_dict(cfg); mpc.SetupMPC(B)
-    mpc.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.current_stream() if default_stream else torch.cuda.Stream()
+    mpc.set_stream(stream.cuda_stream)
     dev = torch.device("cuda", 0)
     d = [torch.from_numpy(a).to(dev) for a in (st, ds, di)]
     f = torch.zeros(B, mpc.n_forces, dtype=torch.float64, device=dev)
     s = torch.zeros(B, dtype=torch.int32, device=dev); it = torch.zeros(B, dtype=torch.int32, device=dev)
     k = torch.zeros(B, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
     run = lambda: mpc.solve_device(B, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), f.data_ptr(), s.data_ptr(), it.data_ptr(), k.data_ptr())
     for _ in range(warmup):
         run()
     ms = []
     for _ in range(steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); run(); e1.record(); torch.cuda.synchronize()
+        e0.record(stream); run(); e1.record(stream); torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
     r = dict(ms=float(np.median(ms)), solves_per_s=B / float(np.median(ms)) * 1e3, iters=float(it.float().mean()),
              status=np.bincount(s.cpu().numpy(), minlength=5).tolist())
