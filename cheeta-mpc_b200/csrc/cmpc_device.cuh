@@ -373,6 +373,62 @@ __device__ __forceinline__ void pivot4(const Group<W>& G, const double (&xr)[2],
 // when the resident warps are in different phases of different instances the instruction cache thrashes --
 // 8.4 stall cycles per issued instruction waiting for instructions on the tracking-heavy workload, 5.7 with
 // the calls.  The 4- and 8-warp variants keep them inline: out of line they spill.)
+// D(8x8) += A(8x4) B(4x8) on the FP64 tensor-core path.  Lane l holds A[l >> 2][l & 3], B[l & 3][l >> 2] and
+// D[l >> 2][2 (l & 3) + {0, 1}].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// Tensor-core update of NI vertically stacked 8-row blocks (tile rows r0 + 2i + {0, 1}, r0 = c0) of the tile columns c0
+// (and c0 + 1 when `two`) in BC4 layout:  C -= sum_{kk in [k0, k1)} L(rows, kk) L(c0.., kk)'.  The blocks stay in the
+// accumulator registers over all k1 - k0 mma steps and are read and written once (see chol_cm_mma in cmpc_presolve.cu for
+// the chunk-major twin).  Fragment element of lane l: row (l >> 2) & 3, column l & 3 of tile t + (l >> 4) -- two
+// wavefronts per load, no bank conflict at kTS = 18.  A tile row past the end reads the next column's first tile (inside
+// the matrix) and only feeds output rows / columns that are not stored.
+template <int NI>
+__device__ __forceinline__ void mma_update_bc4(double* M, int nblk, int lane, bool two, int c0, int k0, int k1) {
+  const int fa = (lane >> 2) & 3, fhi = lane >> 4, ctc = (lane & 3) >> 1;
+  const int tcol = c0 + ctc;
+  double* cbase = M + (tcol * nblk - ((tcol * (tcol - 1)) >> 1) - tcol) * kTS + 4 * fa + 2 * (lane & 1);  // + kTS (tile row)
+  const bool colok = two ? tcol < nblk : ctc == 0;
+  double acc[NI][2];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int trow = c0 + 2 * i + fhi;
+    acc[i][0] = 0.0; acc[i][1] = 0.0;
+    if (colok && trow < nblk && trow >= tcol) { const double2 c = *reinterpret_cast<const double2*>(cbase + trow * kTS); acc[i][0] = c.x; acc[i][1] = c.y; }
+  }
+  const double* pb = M + fhi * kTS + 4 * fa + (lane & 3) + (k0 * nblk - ((k0 * (k0 - 1)) >> 1) - k0) * kTS;  // + kTS (tile row): column k0
+  for (int kk = k0; kk < k1; ++kk) {
+    const double b = pb[kTS * c0];
+    const double bn = -b;
+    double a[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) a[i] = (i == 0) ? b : pb[kTS * (c0 + 2 * i)];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) dmma884(acc[i][0], acc[i][1], a[i], bn);
+    pb += kTS * (nblk - kk - 1);
+  }
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int trow = c0 + 2 * i + fhi;
+    if (colok && trow < nblk && trow >= tcol) *reinterpret_cast<double2*>(cbase + trow * kTS) = make_double2(acc[i][0], acc[i][1]);
+  }
+}
+__device__ __forceinline__ void mma_update_bc4_n(int ni, double* M, int nblk, int lane, bool two, int c0, int k0, int k1) {
+  switch (ni) {
+    case 1: mma_update_bc4<1>(M, nblk, lane, two, c0, k0, k1); break;
+    case 2: mma_update_bc4<2>(M, nblk, lane, two, c0, k0, k1); break;
+    case 3: mma_update_bc4<3>(M, nblk, lane, two, c0, k0, k1); break;
+    case 4: mma_update_bc4<4>(M, nblk, lane, two, c0, k0, k1); break;
+    case 5: mma_update_bc4<5>(M, nblk, lane, two, c0, k0, k1); break;
+    case 6: mma_update_bc4<6>(M, nblk, lane, two, c0, k0, k1); break;
+    case 7: mma_update_bc4<7>(M, nblk, lane, two, c0, k0, k1); break;
+    case 8: mma_update_bc4<8>(M, nblk, lane, two, c0, k0, k1); break;
+    default: break;
+  }
+}
+
 // Tiled right-looking Cholesky in BC4 layout, in place; the whole group calls it.
 // tb[t] = bi | bj << 8 for storage tile t.  Diagonal tiles end up in solve form (potrf4).
 // If rhs != nullptr the forward substitution  y = L^-1 rhs  is fused into the sweep (rows
@@ -390,9 +446,16 @@ __device__ __forceinline__ bool chol_bc4_impl(const Group<W> G, double* M, int n
     if (gtid + GT < n4) xr[1] = rhs[gtid + GT];
   }
   bool ok = true;
+  // one warp, n4 <= 64: left-looking over 8-wide block columns, rank-k part on the FP64 tensor cores (mma_update_bc4)
+  const bool left = W == 1 && nblk <= 16;
   for (int kb = 0; kb < nblk; ++kb) {
     const int col0 = blkoff(kb, kb, nblk);  // storage index of the diagonal tile of column kb
     const int nrows = nblk - kb;
+    if (W == 1 && left && kb > 0) {
+      if (kb & 1) mma_update_bc4_n((nrows + 1) >> 1, M, nblk, gtid, false, kb, kb - 1, kb);
+      else mma_update_bc4_n((nrows + 1) >> 1, M, nblk, gtid, true, kb, 0, kb);
+      G.sync();
+    }
     double d[16], a[16];
     ld_tile(M + col0 * kTS, a);             // broadcast loads: every lane factors the same tile
     ok = potrf4(a, d) && ok;
@@ -430,7 +493,7 @@ __device__ __forceinline__ bool chol_bc4_impl(const Group<W> G, double* M, int n
     }
     // trailing update: storage tiles of columns kb+1.. are contiguous
     const int t0 = col0 + nrows;
-    for (int t = t0 + gtid; t < ntiles; t += GT) {
+    for (int t = t0 + gtid; t < (left ? 0 : ntiles); t += GT) {
       const int bi = tb[t] & 0xff, bj = tb[t] >> 8;
       double li[16], lj[16], c[16];
       double* C = M + t * kTS;

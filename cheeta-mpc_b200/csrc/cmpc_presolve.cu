@@ -114,12 +114,6 @@ __device__ __forceinline__ bool chol_cm(const Group<W>& G, const CM<TT>& cm, dou
   return true;
 }
 
-// D(8x8) += A(8x4) B(4x8) on the FP64 tensor-core path.  Lane l holds A[l >> 2][l & 3], B[l & 3][l >> 2] and
-// D[l >> 2][2 (l & 3) + {0, 1}].
-__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
-
 // Tensor-core update of NI vertically stacked 8-row blocks (tile rows r0 + 2i + {0, 1}) of the tile columns c0 (and
 // c0 + 1 when TWO):  C -= sum_{kk in [k0, k1)} L(rows, kk) L(c0.., kk)'.  The blocks stay in the accumulator
 // registers (two doubles per lane) over all k1 - k0 mma steps and are read and written once.  A / B fragments come
