@@ -340,12 +340,21 @@ __device__ __noinline__ bool lqr_factor(int N, int L, int gb, int lane, int mode
 #pragma unroll
         for (int a = 0; a < kNF; ++a) { Y[a * kYS + col] = y[a]; __stcg(fk + a * kYS + col, y[a]); }
       }
-      for (int e = lane; e < kNF * kNF + kNF; e += 32) {
-        const int r = e / kNF, c = e - kNF * r;
-        double v;
-        if (e < kNF * kNF) v = (((mask >> (r / 3)) & (mask >> (c / 3)) & 1u) && c < r) ? Lm[e] : 0.0;
-        else v = ((mask >> (c / 3)) & 1u) ? Lm[c * kNF + c] : 1.0;
-        __stcg(fk + kOffL + e, v);
+      // L to the slab, one row per lane: strictly lower part with zeros for swing legs, 1 / l_aa (1 for a swing leg) behind it
+      if (lane < kNF) {
+        const bool ra = (mask >> (lane / 3)) & 1u;
+        const double2* row = reinterpret_cast<const double2*>(Lm + lane * kNF);
+        double2* dst = reinterpret_cast<double2*>(fk + kOffL + lane * kNF);
+        double dinv = 1.0;
+#pragma unroll
+        for (int c = 0; c < kNF; c += 2) {
+          double2 v = row[c >> 1];
+          if (c == (lane & ~1)) dinv = (lane & 1) ? v.y : v.x;
+          v.x = (ra && c < lane && ((mask >> (c / 3)) & 1u)) ? v.x : 0.0;
+          v.y = (ra && c + 1 < lane && ((mask >> ((c + 1) / 3)) & 1u)) ? v.y : 0.0;
+          __stcg(dst + (c >> 1), v);
+        }
+        __stcg(fk + kOffL + kNF * kNF + lane, ra ? dinv : 1.0);
       }
     }
     __syncwarp();
@@ -367,18 +376,22 @@ __device__ __noinline__ bool lqr_factor(int N, int L, int gb, int lane, int mode
       if (lane < 9) pn = ps[lane] + ((lane >= 3 && lane < 6) ? dt * ps[lane - 3] : 0.0);
       const int cl = lane < kNZ ? lane : 0;
 #pragma unroll 1
-      for (int a = 0; a < kNF; ++a) {
-        if (!((mask >> (a / 3)) & 1u)) continue;
-        const double ya = Y[a * kYS + cl];
-        const double2* Y2 = reinterpret_cast<const double2*>(Y + a * kYS);
+      for (int ia = 0; ia < 4; ++ia) {  // one leg (three rows of Y) per trip: the stance test once per leg
+        if (!((mask >> ia) & 1u)) continue;
+        const double* Ya = Y + 3 * ia * kYS;
 #pragma unroll
-        for (int c = 0; c < 10; ++c) {
-          const double2 yy = Y2[c];
-          P[2 * c] = fma(-ya, yy.x, P[2 * c]); P[2 * c + 1] = fma(-ya, yy.y, P[2 * c + 1]);
+        for (int qa = 0; qa < 3; ++qa) {
+          const double ya = Ya[qa * kYS + cl];
+          const double2* Y2 = reinterpret_cast<const double2*>(Ya + qa * kYS);
+#pragma unroll
+          for (int c = 0; c < 10; ++c) {
+            const double2 yy = Y2[c];
+            P[2 * c] = fma(-ya, yy.x, P[2 * c]); P[2 * c + 1] = fma(-ya, yy.y, P[2 * c + 1]);
+          }
+          const double2 yl = Y2[10];  // column 20 and y0
+          P[20] = fma(-ya, yl.x, P[20]);
+          pn = fma(-ya, yl.y, pn);
         }
-        const double2 yl = Y2[10];  // column 20 and y0
-        P[20] = fma(-ya, yl.x, P[20]);
-        pn = fma(-ya, yl.y, pn);
       }
       pv = pn;
     }
