@@ -757,8 +757,7 @@ int plan_class(cmpc_handle* h, cmpc_handle::ClassPlan& p, int W, int nbmax, int 
     p.pre_groups = (int)std::min<size_t>((size_t)pgmax, room / (size_t)pp.total);
     if (p.pre_groups >= 1) {
       p.pre_smem_bytes = ((size_t)pp.cta + (size_t)pp.total * p.pre_groups) * 8;
-      p.pre_scratch_per_group = (size_t)pp.mat;
-      CUDA_TRY(h, cudaMalloc(&p.d_pre_scratch, p.pre_scratch_per_group * 8 * (size_t)p.grid * p.pre_groups));
+      p.pre_scratch_per_group = 0;  // (the presolve kernel needs no L2 scratch any more: its verification does not use H)
       p.pre_used = true;
     }
   }

@@ -1077,8 +1077,8 @@ __host__ __device__ inline PrePlan make_pre_plan(int N, int L, int W, int nbmax,
   PrePlan p;
   const int tiles = bc4_tiles(n4max);
   p.T = tiles | 1;
-  // CTA-shared tables: z1[N], z2[N] (z-weighted power-stacking sums), s1[N], s2[N] (unit weights), wf[3L], wr[3L]
-  p.cta = (4 * N + 6 * L + 1) & ~1;
+  // CTA-shared tables: z1[N], z2[N] (z-weighted power-stacking sums), s1[N], s2[N] (unit weights), qz[N], wf[3L], wr[3L]
+  p.cta = (5 * N + 6 * L + 1) & ~1;
   int o = 0;
   auto take = [&](int cnt) { int r = o; o += (cnt + 1) & ~1; return r; };
   p.x = take(n4max);          // rhs staging, lever arms during the build, then y and the solution

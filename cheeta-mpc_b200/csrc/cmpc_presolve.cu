@@ -3,8 +3,9 @@
 // Most ticks of a legged MPC have no friction or force-limit row active (the reference's weights make
 // force tracking dominate, CentoidMPCTest.cpp:19-33), and then the optimum of the condensed QP is the
 // unconstrained minimiser -H^-1 g.  This kernel settles exactly those instances with ONE Cholesky of
-// H: build, factor (forward substitution fused), back-substitute, then verify on the original H --
-// stationarity |H u + g| <= 1e-9 gs and every row of 0 <= F f <= ub satisfied to -1e-9 us, i.e. the
+// H: build, factor (forward substitution fused), back-substitute, then verify on the problem itself --
+// stationarity |H u + g| <= 1e-9 gs with H u from a roll-out / adjoint sweep over the dynamics and weights (not
+// from the matrix that was factored) and every row of 0 <= F f <= ub satisfied to -1e-9 us, i.e. the
 // polish's own acceptance test with an empty working set -- and write the outputs (status OK, iters
 // 0, multipliers 0).  Anything else (a violated row, a warm-start guess with active rows, a failed
 // pivot) is appended to fail_perm and goes through the interior-point kernel (cmpc_solve.cu).
@@ -265,40 +266,6 @@ __device__ __forceinline__ void bwd_cm(const Group<W>& G, const CM<TT>& cm, cons
   G.sync();
 }
 
-// (H x)[row] for the rows gtid + s GT of a symmetric H (diagonal tiles hold both triangles).
-template <int W, int TT>
-__device__ __forceinline__ void symv_cm(const Group<W>& G, const CM<TT>& cm, const double2* M2, int n4, int nblk, const double* x,
-                                        double (&y)[2]) {
-  constexpr int GT = Group<W>::GT;
-  const int T = cm.T();
-#pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    const int row = G.gtid + s * GT;
-    y[s] = 0.0;
-    if (row >= n4) continue;
-    const int bi = row >> 2, ri = row & 3;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int t = bi;  // tile (bi, 0); tile (bi, bj + 1) = tile (bi, bj) + nblk - bj - 1
-    for (int bj = 0; bj <= bi; ++bj) {
-      const double2* p = cm.row(M2, t, ri);
-      const double2* x2 = reinterpret_cast<const double2*>(x + (bj << 2));
-      const double2 u = p[0], v = p[T], xa = x2[0], xb = x2[1];
-      s0 = fma(u.x, xa.x, s0); s1 = fma(u.y, xa.y, s1);
-      s2 = fma(v.x, xb.x, s2); s3 = fma(v.y, xb.y, s3);
-      t += nblk - bj - 1;
-    }
-    // here t = tile (bi, bi) + nblk - bi - 1 + ... : recompute the diagonal tile of column bi
-    t = bi * nblk - ((bi * (bi - 1)) >> 1) + 1;  // tile (bi + 1, bi); the column's tiles are consecutive
-    for (int bj = bi + 1; bj < nblk; ++bj, ++t) {
-      const double2* x2 = reinterpret_cast<const double2*>(x + (bj << 2));
-      const double2 xa = x2[0], xb = x2[1];
-      s0 = fma(*cm.elem(M2, t, 0, ri), xa.x, s0); s1 = fma(*cm.elem(M2, t, 1, ri), xa.y, s1);
-      s2 = fma(*cm.elem(M2, t, 2, ri), xb.x, s2); s3 = fma(*cm.elem(M2, t, 3, ri), xb.y, s3);
-    }
-    y[s] = (s0 + s1) + (s2 + s3);
-  }
-}
-
 __device__ __forceinline__ int ld_acquire(const int32_t* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -329,7 +296,8 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
   double* c_z2 = c_z1 + N;        // z2[j] = sum_{k >= j} (k - j + zeta)^2 qz_k
   double* c_s1 = c_z2 + N;        // s1[j], s2[j]: the same sums with unit weights (x and y)
   double* c_s2 = c_s1 + N;
-  double* c_wf = c_s2 + N;        // force-tracking weights  (CentroidalMPC.cpp:223-225)
+  double* c_qz = c_s2 + N;        // qz[k]: z-position weight of node k + 1 (:205)
+  double* c_wf = c_qz + N;        // force-tracking weights  (CentroidalMPC.cpp:223-225)
   double* c_wr = c_wf + 3 * L;    // force-rate weights      (:227-231)
   double* base = smem + P.cta + (size_t)G.gid * P.total;
   G.red = base + P.red;
@@ -344,7 +312,6 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
   int8_t* s_blk_of = reinterpret_cast<int8_t*>(s_blk_i + nbmax);
   double* Mm = base + P.M;
   double2* M2 = reinterpret_cast<double2*>(Mm);
-  double* Hm = args.scratch + (size_t)(blockIdx.x * args.groups + G.gid) * args.scratch_per_group;
   const int ns = 9 + 3 * L, nds = 9 * (N + 1), ndi = L * (4 * N + 3);
   const int nin = (ns + nds + ndi + 1) & ~1;
   BuildView V;
@@ -373,6 +340,7 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
       z1 += al * om * om; z2 += al * al * om * om;
     }
     c_z1[j] = z1; c_z2[j] = z2;
+    { const double om = (cfg.w[2] * 0.5) * exp(-(double)(j + 1)) + cfg.w[2] * 0.5; c_qz[j] = om * om; }
     const double cnt = (double)(N - j);
     c_s1[j] = 0.5 * cnt * (cnt - 1.0) + zeta * cnt;
     c_s2[j] = (cnt - 1.0) * cnt * (2.0 * cnt - 1.0) * (1.0 / 6.0) + zeta * cnt * (cnt - 1.0) + zeta * zeta * cnt;
@@ -403,8 +371,8 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
     }
     bool defer = false;
     int nb = 0, n = 0, nblk = 0, n4 = 0;
-    double gr[2] = {0.0, 0.0};  // gradient rows gtid, gtid + GT
     double xr[2] = {0.0, 0.0};
+    double arm[3] = {0.0, 0.0, 0.0}, gb[3] = {0.0, 0.0, 0.0};  // lever arm and gradient g of block gtid (the verification needs them again)
     {
       const bool finite = stage_inputs<W>(G, cfg, args, inst, V);
       nb = s_misc[0];
@@ -453,7 +421,6 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
         }
       }
       G.sync();
-      double arm[3] = {0.0, 0.0, 0.0};
       if (gtid < nb) {
         const int b = gtid, j = s_blk_j[b], i = s_blk_i[b];
         const double ce = s_ce[b];
@@ -466,6 +433,7 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
           double gq = 2.0 * (cmass * (dt * dt * e9[q] + dt * e9[3 + q]) + dt * ce * cr[q]);
           if (q == 2) gq -= 2.0 * c_wf[3 * i + 2] * V.fz[b];
           s_x[3 * b + q] = gq;
+          gb[q] = gq;
         }
       }
       if (gtid < n4 - n) s_x[n + gtid] = 0.0;
@@ -479,7 +447,7 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         const int r = gtid + s * GT;
-        if (r < n4) { gr[s] = s_x[r]; xr[s] = -gr[s]; }
+        if (r < n4) xr[s] = -s_x[r];
       }
       G.sync();
       if (gtid < nb) { s_x[3 * gtid] = arm[0]; s_x[3 * gtid + 1] = arm[1]; s_x[3 * gtid + 2] = arm[2]; }
@@ -501,8 +469,8 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
         auto Rof = [&](int g) { return 4 * (g & 3) * T + 2 * (g >> 2); };
         auto Cof = [&](int g) { const int tj = g >> 2; return 2 * T * ((g & 3) >> 1) + 2 * (tj * nblk - ((tj * (tj + 1)) >> 1)) + (g & 1); };
         // One block pair.  FAR (b2 <= b - 2): all nine elements lie strictly below the diagonal tiles,
-        // separable addressing.  Near pairs (b2 = b or b - 1) may touch a diagonal tile: lower tiles get
-        // (gi, gj) and an element inside a diagonal tile is mirrored so the tile holds both triangles.
+        // separable addressing.  Near pairs (b2 = b or b - 1) may touch a diagonal tile: only its lower triangle is
+        // ever read (potrf4; the tensor-core update carries the upper one along without looking at it).
         // The two kinds run in separate loops so that no warp executes both store paths.
         auto do_pair = [&](int b, int b2, auto far_tag) {
           constexpr bool FAR = decltype(far_tag)::value;
@@ -549,7 +517,6 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
                 const int gi = g0 + aa, gj = h0 + bb;
                 const double v = 2.0 * blk[aa][bb];
                 if ((gi >> 2) >= (gj >> 2)) Mm[Rof(gi) + Cof(gj)] = v;
-                if (b != b2 && (gi >> 2) == (gj >> 2)) Mm[Rof(gj) + Cof(gi)] = v;
               }
           }
         };
@@ -570,43 +537,85 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
         for (int e = gtid; e < (n4 - n) * n4; e += GT) {
           const int gi = n + e / n4, gj = e % n4;
           if ((gi >> 2) >= (gj >> 2)) Mm[Rof(gi) + Cof(gj)] = gi == gj ? 1.0 : 0.0;
-          if ((gi >> 2) == (gj >> 2) && gj < n) Mm[Rof(gj) + Cof(gi)] = 0.0;
         }
       }
       G.sync();
-      // the verification below needs H again: keep a copy in the group's L2-resident slab
-      {
-        const int nd2 = 8 * cm.T();
-        double2* dst = reinterpret_cast<double2*>(Hm);
-        for (int t = gtid; t < nd2; t += GT) __stcg(dst + t, M2[t]);
-        G.sync();  // the factorisation overwrites M2 from its first panel on
-      }
       bool ok;
       if constexpr (W == 1) ok = chol_cm_mma<TT>(G, cm, M2, nblk, xr, s_x, s_exch);
       else ok = chol_cm<W, TT>(G, cm, M2, nblk, s_tb, xr, s_x, s_exch);
       if (ok) {
         bwd_cm<W, TT>(G, cm, M2, nblk, s_x, s_exch);
-        const int nd2 = 8 * cm.T();
-        const double2* src = reinterpret_cast<const double2*>(Hm);
-        for (int t = gtid; t < nd2; t += GT) M2[t] = __ldcg(src + t);
-        G.sync();
       }
       defer = !ok;
     }
     double gs = 1.0, usf = 1.0, stat = 0.0, prim = 0.0;
     if (!defer) {
-      double hx[2];
-      symv_cm<W, TT>(G, cm, M2, n4, nblk, s_x, hx);
+      // Stationarity H u + g on the problem itself, not on the factored matrix: H u = 2 (B' L B u + K u) by one roll-out of
+      // the forces through the dynamics (CentroidalMPC.cpp:85-92, frozen arms), the stage weights (:203-221), and the
+      // adjoint sums the gradient g was built with -- O(N) work on data that is still on chip, where a product with H
+      // needs H a second time (it used to be parked in L2 across the factorisation: 13 % of the kernel's time with the
+      // copy back).  Scratch: the matrix region, dead after the back substitution.
+      double* vC = Mm;                // [nb][6]  wrench of block b: ce u, ce arm x u
+      double* vW = vC + 6 * nbmax;    // [N][6]   wrench of step k
+      double* vE = vW + 6 * N;        // [N][9]   weighted state deviation at node k + 1, then its suffix sums
+      double ub[3] = {0.0, 0.0, 0.0};
+      if (gtid < nb) {
+        const int b = gtid;
+        const double ce = s_ce[b];
+        for (int q = 0; q < 3; ++q) ub[q] = s_x[3 * b + q];
+        vC[6 * b] = ce * ub[0]; vC[6 * b + 1] = ce * ub[1]; vC[6 * b + 2] = ce * ub[2];
+        vC[6 * b + 3] = ce * (arm[1] * ub[2] - arm[2] * ub[1]);
+        vC[6 * b + 4] = ce * (arm[2] * ub[0] - arm[0] * ub[2]);
+        vC[6 * b + 5] = ce * (arm[0] * ub[1] - arm[1] * ub[0]);
+      }
+      G.sync();
+      if (gtid < N) {
+        double a6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int i = 0; i < L; ++i) {
+          const int b = s_blk_of[gtid * L + i];
+          if (b >= 0)
+            for (int q = 0; q < 6; ++q) a6[q] += vC[6 * b + q];
+        }
+        for (int q = 0; q < 6; ++q) vW[6 * gtid + q] = a6[q];
+      }
+      G.sync();
+      if (gtid < 9) {  // one state row per lane: roll-out, weights, suffix sums (position rows carry their own velocity)
+        const int grp = gtid / 3, q = gtid - 3 * grp;
+        const double kb = grp == 2 ? dt : dt / mass, zc = zeta * dt * dt / mass;
+        const double wr9 = cfg.w[gtid];
+        const double* src = vW + (grp == 2 ? 3 + q : q);
+        double a = 0.0, bq = 0.0;
+        for (int k = 0; k < N; ++k) {
+          const double X = src[6 * k];
+          a = fma(dt, bq, a) + zc * X;
+          bq = fma(kb, X, bq);
+          vE[9 * k + gtid] = (gtid == 2 ? c_qz[k] : wr9) * (grp == 0 ? a : bq);
+        }
+        double S = 0.0, Pw = 0.0;
+        for (int k = N - 1; k >= 0; --k) {
+          const double e = vE[9 * k + gtid];
+          Pw += S + zeta * e; S += e;
+          vE[9 * k + gtid] = grp == 0 ? Pw : S;
+        }
+      }
+      G.sync();
       double gmax = 0.0, umax = 0.0;
       bool fin = true;
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int r = gtid + s * GT;
-        if (r < n) {
-          const double xv = s_x[r];
-          gmax = fmax(gmax, fabs(gr[s])); umax = fmax(umax, fabs(xv));
-          stat = fmax(stat, fabs(hx[s] + gr[s]));
-          fin = fin && isfinite(xv) && isfinite(hx[s]);
+      if (gtid < nb) {
+        const int b = gtid, j = s_blk_j[b], i = s_blk_i[b];
+        const double ce = s_ce[b], cmass = ce / mass;
+        const double* e9 = vE + 9 * j;
+        const double sl3[3] = {e9[6], e9[7], e9[8]};
+        const double cr[3] = {sl3[1] * arm[2] - sl3[2] * arm[1], sl3[2] * arm[0] - sl3[0] * arm[2], sl3[0] * arm[1] - sl3[1] * arm[0]};
+        const int bp = j > 0 ? s_blk_of[(j - 1) * L + i] : -1, bn = j + 1 < N ? s_blk_of[(j + 1) * L + i] : -1;
+        const double nn = (j > 0 ? 1.0 : 0.0) + (j + 1 < N ? 1.0 : 0.0);
+        for (int q = 0; q < 3; ++q) {
+          const double up = bp >= 0 ? s_x[3 * bp + q] : 0.0, un = bn >= 0 ? s_x[3 * bn + q] : 0.0;
+          const double ku = c_wf[3 * i + q] * ub[q] + c_wr[3 * i + q] * (nn * ub[q] - up - un);
+          const double hu = 2.0 * (cmass * (dt * dt * e9[q] + dt * e9[3 + q]) + dt * ce * cr[q] + ku);
+          gmax = fmax(gmax, fabs(gb[q])); umax = fmax(umax, fabs(ub[q]));
+          stat = fmax(stat, fabs(hu + gb[q]));
+          fin = fin && isfinite(ub[q]) && isfinite(hu);
         }
       }
       if (gtid < nb) {
