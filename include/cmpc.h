@@ -122,7 +122,11 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
                      cmpc_stats* stats);
 
 /* Same with DEVICE pointers (inputs already resident in HBM, outputs left in HBM);
- * asynchronous on the handle's stream unless stats != NULL (then it synchronises). */
+ * asynchronous on the handle's stream unless stats != NULL (then it synchronises).  The call only enqueues work
+ * (a memset, kernels, and -- when a batch has work for both interior-point kernels -- a fork to an auxiliary stream of
+ * the handle that is joined again before the call returns control of the stream), so with stats == NULL it can be
+ * captured into a CUDA graph on the handle's stream and replayed (tests/test_gpu_parity.py).  The launch plan follows
+ * the list counts of the handle's previous call; it changes the time a call takes, never a bit of its results. */
 int cmpc_solve_batch_device(cmpc_handle* h, int B, const double* d_state,
                             const double* d_des_state, const double* d_des_inputs,
                             double* d_forces, int32_t* d_status, int32_t* d_iters,
@@ -228,7 +232,9 @@ int cmpc_fill_contact_tables_switch_device(cmpc_handle* h, int B, const cmpc_gai
                                            const double* d_t_switch, double stance_time, const double* d_t0,
                                            double* d_des_inputs);
 
-/* Use an externally owned CUDA stream (cudaStream_t as void*) for all device work.  The stream must belong to the
+/* Use an externally owned CUDA stream (cudaStream_t as void*) for all device work: everything a call does is ordered
+ * behind what is already on that stream, and whatever is enqueued on it afterwards is ordered behind the call (the
+ * library's own copy / auxiliary streams fork from and join back into it by events).  The stream must belong to the
  * handle's device (checked once the handle is set up).  NULL before cmpc_setup means "let the library create its own
  * non-blocking stream"; NULL after cmpc_setup selects the legacy default stream. */
 int cmpc_set_stream(cmpc_handle* h, void* cuda_stream);
