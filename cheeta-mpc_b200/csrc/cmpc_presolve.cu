@@ -122,8 +122,8 @@ __device__ __forceinline__ bool chol_cm(const Group<W>& G, const CM<TT>& cm, dou
 // with T = 1 (mod 8) the 32 addresses fall into distinct banks.  A tile row past the end of the matrix reads
 // whatever follows in the chunk (T > number of tiles keeps it inside the matrix region) and only feeds output rows /
 // columns that are not stored.
-template <int NI, bool TWO, int TT>
-__device__ __forceinline__ void mma_update(const CM<TT>& cm, double2* M2, int nblk, int lane, int r0, int c0, int k0, int k1) {
+template <int NI, int TT>
+__device__ __forceinline__ void mma_update(const CM<TT>& cm, double2* M2, int nblk, int lane, bool TWO, int r0, int c0, int k0, int k1) {
   const int T = cm.T();
   const int fa = (lane >> 2) & 3, fhi = lane >> 4, ctc = (lane & 3) >> 1;
   // C fragment: row lane >> 2 of the 8, columns 2 (lane & 3) + {0, 1}: tile (row fhi, column ctc), chunk 2 fa + (lane & 1)
@@ -157,17 +157,17 @@ __device__ __forceinline__ void mma_update(const CM<TT>& cm, double2* M2, int nb
   }
 }
 
-template <bool TWO, int TT>
-__device__ __forceinline__ void mma_update_n(int ni, const CM<TT>& cm, double2* M2, int nblk, int lane, int r0, int c0, int k0, int k1) {
+template <int TT>
+__device__ __forceinline__ void mma_update_n(int ni, const CM<TT>& cm, double2* M2, int nblk, int lane, bool TWO, int r0, int c0, int k0, int k1) {
   switch (ni) {
-    case 1: mma_update<1, TWO, TT>(cm, M2, nblk, lane, r0, c0, k0, k1); break;
-    case 2: mma_update<2, TWO, TT>(cm, M2, nblk, lane, r0, c0, k0, k1); break;
-    case 3: mma_update<3, TWO, TT>(cm, M2, nblk, lane, r0, c0, k0, k1); break;
-    case 4: mma_update<4, TWO, TT>(cm, M2, nblk, lane, r0, c0, k0, k1); break;
-    case 5: mma_update<5, TWO, TT>(cm, M2, nblk, lane, r0, c0, k0, k1); break;
-    case 6: mma_update<6, TWO, TT>(cm, M2, nblk, lane, r0, c0, k0, k1); break;
-    case 7: mma_update<7, TWO, TT>(cm, M2, nblk, lane, r0, c0, k0, k1); break;
-    case 8: mma_update<8, TWO, TT>(cm, M2, nblk, lane, r0, c0, k0, k1); break;
+    case 1: mma_update<1, TT>(cm, M2, nblk, lane, TWO, r0, c0, k0, k1); break;
+    case 2: mma_update<2, TT>(cm, M2, nblk, lane, TWO, r0, c0, k0, k1); break;
+    case 3: mma_update<3, TT>(cm, M2, nblk, lane, TWO, r0, c0, k0, k1); break;
+    case 4: mma_update<4, TT>(cm, M2, nblk, lane, TWO, r0, c0, k0, k1); break;
+    case 5: mma_update<5, TT>(cm, M2, nblk, lane, TWO, r0, c0, k0, k1); break;
+    case 6: mma_update<6, TT>(cm, M2, nblk, lane, TWO, r0, c0, k0, k1); break;
+    case 7: mma_update<7, TT>(cm, M2, nblk, lane, TWO, r0, c0, k0, k1); break;
+    case 8: mma_update<8, TT>(cm, M2, nblk, lane, TWO, r0, c0, k0, k1); break;
     default: break;
   }
 }
@@ -188,8 +188,7 @@ __device__ __forceinline__ bool chol_cm_mma(const Group<1>& G, const CM<TT>& cm,
   for (int kb = 0; kb < nblk; ++kb) {
     const int nrows = nblk - kb;
     if (kb > 0) {
-      if (kb & 1) mma_update_n<false, TT>((nrows + 1) >> 1, cm, M2, nblk, lane, kb, kb, kb - 1, kb);
-      else mma_update_n<true, TT>((nrows + 1) >> 1, cm, M2, nblk, lane, kb, kb, 0, kb);
+      mma_update_n<TT>((nrows + 1) >> 1, cm, M2, nblk, lane, !(kb & 1), kb, kb, (kb & 1) ? kb - 1 : 0, kb);
       G.sync();
     }
     double d[16], a[16];
