@@ -140,6 +140,7 @@ __device__ __forceinline__ void mma_update(const CM<TT>& cm, double2* M2, int nb
   // fragment element inside the tile pair (t, t + 1)
   const double* pb = reinterpret_cast<const double*>(M2) + 2 * ((2 * fa + ctc) * T + fhi) + (lane & 1)
                      + 2 * (k0 * nblk - ((k0 * (k0 - 1)) >> 1) - k0);  // + 2 (tile row): column k0
+#pragma unroll 1
   for (int kk = k0; kk < k1; ++kk) {
     const double b = pb[2 * c0];
     const double bn = -b;
