@@ -471,9 +471,9 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
         // One block pair.  FAR (b2 <= b - 2): all nine elements lie strictly below the diagonal tiles,
         // separable addressing.  Near pairs (b2 = b or b - 1) may touch a diagonal tile: only its lower triangle is
         // ever read (potrf4; the tensor-core update carries the upper one along without looking at it).
-        // The two kinds run in separate loops so that no warp executes both store paths.
-        auto do_pair = [&](int b, int b2, auto far_tag) {
-          constexpr bool FAR = decltype(far_tag)::value;
+        // One loop over all pairs, far ones first (one copy of the block arithmetic: the kernel's working set of
+        // instructions matters more than the one round in which a warp runs both store paths).
+        auto do_pair = [&](int b, int b2, bool FAR) {
           const int j = s_blk_j[b], i = s_blk_i[b], j2 = s_blk_j[b2], i2 = s_blk_i[b2];
           const double ce = s_ce[b], ce2 = s_ce[b2];
           const double r0 = s_x[3 * b], r1 = s_x[3 * b + 1], r2 = s_x[3 * b + 2];
@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
             }
           }
           const int g0 = 3 * b, h0 = 3 * b2;
-          if constexpr (FAR) {
+          if (FAR) {
             int R[3], C[3];
 #pragma unroll
             for (int aa = 0; aa < 3; ++aa) { R[aa] = Rof(g0 + aa); C[aa] = Cof(h0 + aa); }
@@ -521,17 +521,23 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
           }
         };
         const int nfar = nb >= 3 ? ((nb - 1) * (nb - 2)) >> 1 : 0;
-        {  // pair idx = a (a + 1) / 2 + rem, 0 <= rem <= a: block row a + 2, block column rem; decoded incrementally
+        {  // far pair idx = a (a + 1) / 2 + rem, 0 <= rem <= a: block row a + 2, block column rem (decoded incrementally);
+           // then the 2 nb - 1 near pairs
           int a = 0, rem = gtid;
-          for (int idx = gtid; idx < nfar; idx += GT) {
-            while (rem > a) { rem -= a + 1; ++a; }
-            do_pair(a + 2, rem, std::true_type{});
-            rem += GT;
+          const int npairs = nfar + 2 * nb - 1;
+          for (int idx = gtid; idx < npairs; idx += GT) {
+            int b, b2;
+            const bool far = idx < nfar;
+            if (far) {
+              while (rem > a) { rem -= a + 1; ++a; }
+              b = a + 2; b2 = rem;
+              rem += GT;
+            } else {
+              const int e = idx - nfar;
+              b = (e + 1) >> 1; b2 = b - (e & 1);
+            }
+            do_pair(b, b2, far);
           }
-        }
-        for (int idx = gtid; idx < 2 * nb - 1; idx += GT) {
-          const int b = (idx + 1) >> 1;
-          do_pair(b, b - (idx & 1), std::false_type{});
         }
         // padding rows (n .. n4-1): identity
         for (int e = gtid; e < (n4 - n) * n4; e += GT) {
