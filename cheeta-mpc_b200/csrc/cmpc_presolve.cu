@@ -318,6 +318,7 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
   V.Mm = Mm; V.ce = s_ce; V.eq = Mm + nin; V.qz = V.eq + 9 * N; V.fz = V.qz + N; V.arm = s_x; V.g = s_x;
   V.misc = s_misc; V.tb = s_tb; V.blk_j = s_blk_j; V.blk_i = s_blk_i; V.blk_of = s_blk_of;
   const double mass = cfg.mass, dt = cfg.dt;
+  const double imass = 1.0 / mass;  // (once per thread: every per-instance use multiplies)
   const double zeta = cfg.zoh ? 0.5 : 0.0;
   const int count = args.count ? *args.count : args.count_imm;
   if (count <= 0) return;  // empty list (uniform over the grid): nothing to set up
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
         for (int q = 0; q < 3; ++q) arm[q] = Mm[ns + nds + i * (4 * N + 3) + N + 3 * j + q] - Mm[ns + 3 * j + q];
         const double* e9 = V.eq + 9 * j;
         const double sl3[3] = {e9[6], e9[7], e9[8]};
-        const double cmass = ce / mass;
+        const double cmass = ce * imass;
         const double cr[3] = {sl3[1] * arm[2] - sl3[2] * arm[1], sl3[2] * arm[0] - sl3[0] * arm[2], sl3[0] * arm[1] - sl3[1] * arm[0]};
         for (int q = 0; q < 3; ++q) {
           double gq = 2.0 * (cmass * (dt * dt * e9[q] + dt * e9[3 + q]) + dt * ce * cr[q]);
@@ -587,7 +588,7 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
       G.sync();
       if (gtid < 9) {  // one state row per lane: roll-out, weights, suffix sums (position rows carry their own velocity)
         const int grp = gtid / 3, q = gtid - 3 * grp;
-        const double kb = grp == 2 ? dt : dt / mass, zc = zeta * dt * dt / mass;
+        const double kb = grp == 2 ? dt : dt * imass, zc = zeta * dt * dt * imass;
         const double wr9 = cfg.w[gtid];
         const double* src = vW + (grp == 2 ? 3 + q : q);
         double a = 0.0, bq = 0.0;
@@ -609,7 +610,7 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
       bool fin = true;
       if (gtid < nb) {
         const int b = gtid, j = s_blk_j[b], i = s_blk_i[b];
-        const double ce = s_ce[b], cmass = ce / mass;
+        const double ce = s_ce[b], cmass = ce * imass;
         const double* e9 = vE + 9 * j;
         const double sl3[3] = {e9[6], e9[7], e9[8]};
         const double cr[3] = {sl3[1] * arm[2] - sl3[2] * arm[1], sl3[2] * arm[0] - sl3[0] * arm[2], sl3[0] * arm[1] - sl3[1] * arm[0]};
@@ -677,7 +678,7 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
     if (gtid == 0) {
       args.status[inst] = CMPC_STATUS_OK;
       if (args.iters) args.iters[inst] = 0;
-      if (args.kkt) args.kkt[inst] = fmax(stat / gs, fmax(prim, 0.0) / usf);
+      if (args.kkt) args.kkt[inst] = fmax(stat * fast_rcp(gs), fmax(prim, 0.0) * fast_rcp(usf));
     }
     G.sync();
   }
