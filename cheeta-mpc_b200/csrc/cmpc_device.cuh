@@ -820,7 +820,7 @@ __host__ __device__ inline SmemPlan make_plan(int N, int L, int W, int nbmax, in
   p.Mm = o;
   if (m_in_smem) o += mat_region_doubles(N, L, n4max);
   p.total = (o + 1) & ~1;
-  p.cta = (2 * N + 1) & ~1;
+  p.cta = (3 * N + 1) & ~1;
   return p;
 }
 
@@ -829,6 +829,7 @@ __host__ __device__ inline SmemPlan make_plan(int N, int L, int W, int nbmax, in
 struct BuildView {
   double* Mm;   // the matrix buffer; stages the raw inputs [state | des_state | des_inputs] first
   double *ce, *fz, *arm, *eq, *qz, *g;
+  const double* qzt;  // CTA-shared table: z-position weight of node k + 1 (an exp() per node and instance otherwise)
   int* misc;    // [0] = nb (clamped to the class bound), [1] = invalid table, [3] = nb unclamped
   uint16_t* tb;
   uint8_t *blk_j, *blk_i;
@@ -883,12 +884,13 @@ __device__ __forceinline__ bool stage_inputs(const Group<W>& G, const DevConfig&
     const int total = __shfl_sync(0xffffffffu, incl, N - 1);
     if (j < N) {
       int b = incl - cnt;
+      const double fzj = (colsum > 0.0) ? mass * kGrav / colsum : 0.0;  // desired fz, :331-333 (one division per step)
       for (int i = 0; i < L; ++i) {
         const double ce = g_di[i * (4 * N + 3) + j];
         if (ce > 0.0 && b < args.nbmax) {
           V.blk_j[b] = j; V.blk_i[b] = i; V.blk_of[j * L + i] = b;
           V.ce[b] = ce;
-          V.fz[b] = (colsum > 0.0) ? mass * kGrav / colsum : 0.0;  // desired fz, :331-333
+          V.fz[b] = fzj;
           ++b;
         } else {
           V.blk_of[j * L + i] = -1;
@@ -906,8 +908,7 @@ __device__ __forceinline__ bool stage_inputs(const Group<W>& G, const DevConfig&
     for (int a = 0; a < 3; ++a) { c[a] = g_state[a] + kk * dt * g_state[3 + a]; v[a] = g_state[3 + a]; }
     c[2] += gpos * dt * dt * (-kGrav);
     v[2] += kk * dt * (-kGrav);
-    const double om = (cfg.w[2] * 0.5) * exp(-kk) + cfg.w[2] * 0.5;  // :205
-    const double qz = om * om;                                        // :210 (inside the square)
+    const double qz = V.qzt[k];  // omega_{k+1}^2, omega = w2/2 exp(-(k+1)) + w2/2 (:205, :210: inside the square)
     V.qz[k] = qz;
     V.eq[9 * k + 0] = cfg.w[0] * (c[0] - g_dpos[3 * node + 0]);
     V.eq[9 * k + 1] = cfg.w[1] * (c[1] - g_dpos[3 * node + 1]);

@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
   const int nin = (ns + nds + ndi + 1) & ~1;
   BuildView V;
   V.Mm = Mm; V.ce = s_ce; V.eq = Mm + nin; V.qz = V.eq + 9 * N; V.fz = V.qz + N; V.arm = s_x; V.g = s_x;
+  V.qzt = c_qz;
   V.misc = s_misc; V.tb = s_tb; V.blk_j = s_blk_j; V.blk_i = s_blk_i; V.blk_of = s_blk_of;
   const double mass = cfg.mass, dt = cfg.dt;
   const double imass = 1.0 / mass;  // (once per thread: every per-instance use multiplies)

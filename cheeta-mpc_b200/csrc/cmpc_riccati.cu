@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
   int8_t* s_blk_of = reinterpret_cast<int8_t*>(s_blk_i + nbfull);
   BuildView V;
   V.Mm = base + P.in;
+  V.qzt = c_qz + 1;  // the table is indexed by node
   V.eq = base + P.P; V.qz = V.eq + 9 * N; V.fz = V.qz + N + (N & 1); V.ce = V.fz + nbfull;  // scratch of the shared prologue, dead after it
   V.arm = nullptr; V.g = nullptr; V.tb = nullptr;
   V.misc = s_misc; V.blk_j = s_blk_j; V.blk_i = s_blk_i; V.blk_of = s_blk_of;

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256), 1) cmpc_s
   const int gtid = G.gtid;
   double* c_z1 = smem;      // CTA-shared z-weighted sums for the build (fill_z_tables)
   double* c_z2 = smem + N;
+  double* c_qz = smem + 2 * N;  // z-position weight per node (stage_inputs)
   double* base = smem + P.cta + (size_t)G.gid * P.total;
   G.red = base + P.red;
   double* s_exch = base + P.exch;
@@ -78,7 +79,11 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256), 1) cmpc_s
   // shadow tells): in steady state no launch touches the bus for it
   if (args.hint_out && blockIdx.x == 0 && threadIdx.x == 0 && *args.hint_shadow != total) { *args.hint_shadow = total; *args.hint_out = total; }
   if (total <= 0) return;  // empty lists (uniform over the grid): nothing to set up
-  if ((int)threadIdx.x < N) fill_z_tables(cfg, c_z1, c_z2, threadIdx.x);
+  if ((int)threadIdx.x < N) {
+    fill_z_tables(cfg, c_z1, c_z2, threadIdx.x);
+    const double om = (cfg.w[2] * 0.5) * exp(-(double)(threadIdx.x + 1)) + cfg.w[2] * 0.5;  // node k + 1, CentroidalMPC.cpp:205
+    c_qz[threadIdx.x] = om * om;
+  }
   __syncthreads();
   int li = 0;
 
@@ -94,7 +99,7 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256), 1) cmpc_s
     const int32_t* lperm = args.nlists > 0 ? args.lperm[li] : args.perm;
     const int inst = lperm ? lperm[slot] : slot;
     BuildView V;
-    V.Mm = Mm; V.ce = s_ce; V.fz = s_fz; V.arm = s_arm; V.eq = s_eq; V.qz = s_qz; V.g = s_g;
+    V.Mm = Mm; V.ce = s_ce; V.fz = s_fz; V.arm = s_arm; V.eq = s_eq; V.qz = s_qz; V.g = s_g; V.qzt = c_qz;
     V.misc = s_misc; V.tb = s_tb; V.blk_j = s_blk_j; V.blk_i = s_blk_i; V.blk_of = s_blk_of;
     const bool finite = stage_inputs<W>(G, cfg, args, inst, V);
     const int nb = s_misc[0];
