@@ -82,6 +82,9 @@ __host__ __device__ __forceinline__ Lay make_lay(int N, int L, int gb) {
   return y;
 }
 
+// leg-step index -> stage: a shift for four legs (a division by a run-time value is ~20 instructions, and every per-leg-step
+// loop of the iteration has one)
+__device__ __forceinline__ int div_legs(int tb, int L) { return L == 4 ? tb >> 2 : tb / L; }
 struct Leg { double a0, a1, a2, bp, bv, s; };
 __device__ __forceinline__ Leg leg_at(const double* tk, int i, double kp, double kv, double ks) {
   const double2 p = *reinterpret_cast<const double2*>(tk + 4 * i), q = *reinterpret_cast<const double2*>(tk + 4 * i + 2);
@@ -710,7 +713,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
     for (int t = lane; t < nfN; t += 32) gmax = fmax(gmax, fabs(s_rd[t]));
 #pragma unroll 1
     for (int tb = lane; tb < nbfull; tb += 32) {
-      const int k = tb / L, i = tb - k * L;
+      const int k = div_legs(tb, L), i = tb - k * L;
       const double ce = s_tab[16 * k + 4 * i + 3];
       double fz = 0.0;
       if (ce > 0.0) {
@@ -732,7 +735,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
     const double mu0 = fmax(1e-2, r0max);
 #pragma unroll 1
     for (int tb = lane; tb < nbfull; tb += 32) {
-      const int k = tb / L, i = tb - k * L;
+      const int k = div_legs(tb, L), i = tb - k * L;
       const double ce = s_tab[16 * k + 4 * i + 3];
       double y[5] = {1.0, 1.0, 1.0, 1.0, 1.0};
       const double ubxy = kFricUb * ce, ubz = mass * kGrav * (double)L * ce;  // :183,199
@@ -764,7 +767,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
       rmax = 0.0; umax = 0.0; gap = 0.0;
 #pragma unroll 1
       for (int tb = lane; tb < nbfull; tb += 32) {
-        const int k = tb / L, i = tb - k * L;
+        const int k = div_legs(tb, L), i = tb - k * L;
         const double ce = s_tab[16 * k + 4 * i + 3];
         if (!(ce > 0.0)) continue;
         const double ubxy = kFricUb * ce, ubz = mass * kGrav * (double)L * ce;
@@ -805,7 +808,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
         // ---- active-set guess from the interior-point iterate
 #pragma unroll 1
         for (int tb = lane; tb < nbfull; tb += 32) {
-          const int k = tb / L, i = tb - k * L;
+          const int k = div_legs(tb, L), i = tb - k * L;
           const double ce = s_tab[16 * k + 4 * i + 3];
           uint16_t a = 0;
           if (ce > 0.0) {
@@ -829,7 +832,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
           bool ok_all = true;
 #pragma unroll 1
           for (int tb = lane; tb < nbfull; tb += 32) {
-            const int k = tb / L, i = tb - k * L;
+            const int k = div_legs(tb, L), i = tb - k * L;
             const double ce = s_tab[16 * k + 4 * i + 3];
             double f0[3] = {0.0, 0.0, 0.0};
             if (ce > 0.0) {
@@ -872,7 +875,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
             bool okm = true, changed = false;
 #pragma unroll 1
             for (int tb = lane; tb < nbfull; tb += 32) {
-              const int k = tb / L, i = tb - k * L;
+              const int k = div_legs(tb, L), i = tb - k * L;
               const double ce = s_tab[16 * k + 4 * i + 3];
               if (!(ce > 0.0)) continue;
               const double mub = cfg.mu[i];
@@ -929,7 +932,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
         stage_gradient(N, L, gb, lane, y_.u, s_rd);
 #pragma unroll 1
         for (int tb = lane; tb < nbfull; tb += 32) {
-          const int k = tb / L, i = tb - k * L;
+          const int k = div_legs(tb, L), i = tb - k * L;
           if (!(s_tab[16 * k + 4 * i + 3] > 0.0)) continue;
           double w[5], o[3];
           for (int q = 0; q < 5; ++q) w[q] = g_zl[5 * tb + q] - g_zu[5 * tb + q];
@@ -945,7 +948,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
       // ---- 1/2 C' diag(zl/sl + zu/su) C per leg-step -> Rs;  affine right-hand side -rd + C'(zu - zl) -> du
 #pragma unroll 1
       for (int tb = lane; tb < nbfull; tb += 32) {
-        const int k = tb / L, i = tb - k * L;
+        const int k = div_legs(tb, L), i = tb - k * L;
         const double ce = s_tab[16 * k + 4 * i + 3];
         if (!(ce > 0.0)) { s_du[3 * tb] = 0.0; s_du[3 * tb + 1] = 0.0; s_du[3 * tb + 2] = 0.0; continue; }
         const double ubxy = kFricUb * ce, ubz = mass * kGrav * (double)L * ce;
@@ -978,7 +981,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
           __syncwarp();
 #pragma unroll 1
           for (int tb = lane; tb < nbfull; tb += 32) {
-            const int k = tb / L, i = tb - k * L;
+            const int k = div_legs(tb, L), i = tb - k * L;
             const double ce = s_tab[16 * k + 4 * i + 3];
             if (!(ce > 0.0)) continue;  // du = dua = 0 there
             const double mub = cfg.mu[i];
@@ -1006,7 +1009,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
         double tloc = 0.0;
 #pragma unroll 1
         for (int tb = lane; tb < nbfull; tb += 32) {
-          const int k = tb / L, i = tb - k * L;
+          const int k = div_legs(tb, L), i = tb - k * L;
           const double ce = s_tab[16 * k + 4 * i + 3];
           if (!(ce > 0.0)) continue;
           const double mub = cfg.mu[i];
@@ -1039,7 +1042,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
           double ga = 0.0;
 #pragma unroll 1
           for (int tb = lane; tb < nbfull; tb += 32) {
-            const int k = tb / L, i = tb - k * L;
+            const int k = div_legs(tb, L), i = tb - k * L;
             const double ce = s_tab[16 * k + 4 * i + 3];
             if (!(ce > 0.0)) continue;
             const double mub = cfg.mu[i];
@@ -1067,7 +1070,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
       bool fin = true;
 #pragma unroll 1
       for (int tb = lane; tb < nbfull; tb += 32) {
-        const int k = tb / L, i = tb - k * L;
+        const int k = div_legs(tb, L), i = tb - k * L;
         const double ce = s_tab[16 * k + 4 * i + 3];
         if (!(ce > 0.0)) continue;
         const double mub = cfg.mu[i];
@@ -1112,7 +1115,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
       double stat = 0.0, umax = 0.0, prim = 0.0, dual = 0.0, comp = 0.0;
 #pragma unroll 1
       for (int tb = lane; tb < nbfull; tb += 32) {
-        const int k = tb / L, i = tb - k * L;
+        const int k = div_legs(tb, L), i = tb - k * L;
         const double ce = s_tab[16 * k + 4 * i + 3];
         if (!(ce > 0.0)) continue;
         const double mub = cfg.mu[i];
@@ -1144,7 +1147,7 @@ __global__ void __launch_bounds__(384, 1) cmpc_ripm_kernel(const __grid_constant
       // reported active set: polished -> rows with zero slack at the KKT point; otherwise the interior-point guess
 #pragma unroll 1
       for (int tb = lane; tb < nbfull; tb += 32) {
-        const int k = tb / L, i = tb - k * L;
+        const int k = div_legs(tb, L), i = tb - k * L;
         const double ce = s_tab[16 * k + 4 * i + 3];
         uint16_t a = 0x8000;
         if (ce > 0.0) {
