@@ -399,6 +399,7 @@ __device__ __forceinline__ void mma_update_bc4(double* M, int nblk, int lane, bo
     if (colok && trow < nblk && trow >= tcol) { const double2 c = *reinterpret_cast<const double2*>(cbase + trow * kTS); acc[i][0] = c.x; acc[i][1] = c.y; }
   }
   const double* pb = M + fhi * kTS + 4 * fa + (lane & 3) + (k0 * nblk - ((k0 * (k0 - 1)) >> 1) - k0) * kTS;  // + kTS (tile row): column k0
+#pragma unroll 1
   for (int kk = k0; kk < k1; ++kk) {
     const double b = pb[kTS * c0];
     const double bn = -b;
