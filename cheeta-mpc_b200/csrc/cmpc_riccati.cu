@@ -47,7 +47,7 @@ __device__ __forceinline__ int stage_setup(const RicView& R, const DevConfig& cf
   __syncwarp();
   if (lane < m) {  // only the nine state rows of B-bar are ever read: the selection rows are applied through cmp[]
     const int a = lane, c = R.cmp[a], i = c / 3, q = c - 3 * i;
-    const double ce = contact_of(R, i, k), cm = ce / cfg.mass, dt = cfg.dt;
+    const double ce = contact_of(R, i, k), cm = ce * fast_rcp(cfg.mass), dt = cfg.dt;  // (a division is ~30 dependent instructions)
     const double* foot = R.in + R.ns + R.nds + i * (4 * R.N + 3) + R.N + 3 * k;
     const double* com = R.in + R.ns + 3 * k;
     const double r0 = foot[0] - com[0], r1 = foot[1] - com[1], r2 = foot[2] - com[2];  // frozen lever arm
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
         const double rate = k >= 1 ? 1.0 : 0.0;
         double colsum = 0.0;
         for (int i = 0; i < L; ++i) colsum += contact_of(R, i, k);
-        const double fz = mass * kGrav / colsum;  // desired fz of the stance legs (:331-333)
+        const double fz = mass * kGrav * fast_rcp(colsum);  // desired fz of the stance legs (:331-333)
         // t = P dbar + p
         if (lane < nz) R.t[lane] = R.P[lane * nz + 2] * dpz + R.P[lane * nz + 5] * dvz + R.p[lane];
         // T1 = P Bbar : rows of Bbar below the state block are a selection
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
         __syncwarp();
         double colsum = 0.0;
         for (int i = 0; i < L; ++i) colsum += contact_of(R, i, k);
-        const double fz = mass * kGrav / colsum;
+        const double fz = mass * kGrav * fast_rcp(colsum);
         if (lane < m) {
           const int a = lane, c = R.cmp[a];
           const double wf = cfg.w[9 + 3 * L + c], wr = cfg.w[9 + 6 * L + c];
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(448) cmpc_riccati_kernel(const DevConfig cfg, 
     if (lane == 0) {
       args.status[inst] = CMPC_STATUS_OK;
       if (args.iters) args.iters[inst] = 0;
-      if (args.kkt) args.kkt[inst] = fmax(stat / gs, fmax(prim, 0.0) / usf);
+      if (args.kkt) args.kkt[inst] = fmax(stat * fast_rcp(gs), fmax(prim, 0.0) * fast_rcp(usf));
     }
     __syncwarp();
   }
