@@ -637,6 +637,16 @@ template <int W>
 __device__ __forceinline__ void copy_mat_impl(const Group<W> G, double* dst, const double* src, int ndoubles) {
   const double2* s2 = reinterpret_cast<const double2*>(src);
   double2* d2 = reinterpret_cast<double2*>(dst);
+  if (__isShared(dst)) {
+    // global -> shared without a register round trip: every 16-byte piece of the thread is in flight at once (as plain
+    // loads the compiler batches four at a time: eight dependent trips to L2 for a 15 KB matrix, every iteration)
+    const unsigned da = (unsigned)__cvta_generic_to_shared(d2);
+    for (int t = G.gtid; t < (ndoubles >> 1); t += Group<W>::GT)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da + 16u * (unsigned)t), "l"(s2 + t) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    return;
+  }
   for (int t = G.gtid; t < (ndoubles >> 1); t += Group<W>::GT) d2[t] = __ldcg(s2 + t);
 }
 template <int W>
