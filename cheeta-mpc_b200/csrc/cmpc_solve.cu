@@ -420,15 +420,19 @@ __global__ void __launch_bounds__(W == 2 ? 512 : (W == 1 ? 320 : 256), 1) cmpc_s
                 okm = okm && fmax(fabs(rb[0]), fmax(fabs(rb[1]), fabs(rb[2]))) <= 1e-9 * gs;
               } else {
                 double Nrm[10][3], lam[10];
-                int idx[10], k = 0;
-                for (int q = 0; q < 5; ++q) if (s_actl[5 * b + q]) { row_vec(mub, q, Nrm[k]); idx[k++] = q; }
+                int k = 0;
+                for (int q = 0; q < 5; ++q) if (s_actl[5 * b + q]) { row_vec(mub, q, Nrm[k]); ++k; }
                 for (int q = 0; q < 5; ++q) if (s_actu[5 * b + q]) {
                   row_vec(mub, q, Nrm[k]);
                   Nrm[k][0] = -Nrm[k][0]; Nrm[k][1] = -Nrm[k][1]; Nrm[k][2] = -Nrm[k][2];
-                  idx[k++] = 5 + q;
+                  ++k;
                 }
                 okm = block_multipliers(k, Nrm, rb, 1e-9 * gs, lam) && okm;
-                for (int sI = 0; sI < k; ++sI) { if (idx[sI] < 5) ll[idx[sI]] = lam[sI]; else lu[idx[sI] - 5] = lam[sI]; }
+                // scatter back in the order the rows were collected (statically indexed targets: a dynamically indexed
+                // register array becomes a select chain per element -- 1.7 k instructions of this kernel were that)
+                int kk = 0;
+                for (int q = 0; q < 5; ++q) if (s_actl[5 * b + q]) ll[q] = lam[kk++];
+                for (int q = 0; q < 5; ++q) if (s_actu[5 * b + q]) lu[q] = lam[kk++];
               }
               if (commit) {
                 for (int q = 0; q < 5; ++q) { s_zl[5 * b + q] = ll[q]; s_zu[5 * b + q] = lu[q]; }
