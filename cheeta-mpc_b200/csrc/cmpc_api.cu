@@ -83,6 +83,10 @@ struct cmpc_handle {
   int tune_calls = 0, tune_batch = 0;
   float tune_best[3] = {1e30f, 1e30f, 1e30f};  // [0] zero-copy, [1] pipelined, [2] full duplex: best span in ms
   char route[96] = "none";           // what the last cmpc_solve_batch call did (cmpc_last_route)
+  // the counts / work block is double-buffered: a call uses copy counts_cur; the router presolve kernel of that call zeroes the
+  // other copy for the next call, so that a call does not start with a memset node (2 us of a 97 us headline step)
+  int counts_cur = 0;
+  bool counts_zero[2] = {false, false};  // copy i is (or will be, in stream order) all zero
   int32_t *d_counts = nullptr, *d_perm = nullptr;  // counts / work of: class lists, deferred lists, polish lists, fall-back lists (4 each); perm [4][4][B]
   int32_t* h_hint = nullptr;      // pinned + mapped [4]: instances the last call's interior-point launch of each class found (0 = skip the split kernels)
   int32_t* h_hint_dev = nullptr;
@@ -574,9 +578,21 @@ int presolve_kind(const cmpc_handle* h, int c) {
 //    ready != nullptr: the inputs are still arriving (copy stream bumps *ready per chunk of
 //    ready_chunk instances) and the router waits per instance for its chunk.
 //  * presolve off: classify kernel, then one interior-point kernel per class.
+constexpr int kCounts = 8 * kNumClasses;  // counts and work counters of one call: class, deferred, polish and fall-back lists
+
 int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = nullptr, int ready_chunk = 0) {
-  if (cudaMemsetAsync(h->d_counts, 0, 8 * kNumClasses * sizeof(int32_t), h->stream) != cudaSuccess)
-    return fail(h, CMPC_ERR_CUDA, "memset counts");
+  // Counts / work block of this call.  Under stream capture the captured sequence is replayed at times the handle does not
+  // see: it zeroes its copy itself, before and after, and the handle's bookkeeping is left alone.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(h->stream, &cap) != cudaSuccess) return fail(h, CMPC_ERR_CUDA, "stream capture status");
+  const bool capturing = cap != cudaStreamCaptureStatusNone;
+  const int cur = h->counts_cur;
+  int32_t* const cnt = h->d_counts + cur * kCounts;
+  int32_t* const cnt_next = h->d_counts + (cur ^ 1) * kCounts;
+  if (capturing || !h->counts_zero[cur]) {
+    if (cudaMemsetAsync(cnt, 0, kCounts * sizeof(int32_t), h->stream) != cudaSuccess) return fail(h, CMPC_ERR_CUDA, "memset counts");
+  }
+  if (!capturing) { h->counts_zero[cur] = false; h->counts_cur = cur ^ 1; }
   int launches = 0;
   const bool presolve = h->cfg.presolve && h->cfg.polish;
   const bool router = presolve && h->cls[0].used && presolve_kind(h, 0) == 1;
@@ -588,7 +604,7 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
   auto chained = [&](SolveArgs& x) { x.pdl = (h->pdl && launches > 0) ? 1 : 0; };
   if (!router) {
     if (ready) return fail(h, CMPC_ERR_STATE, "progressive inputs need the presolve router");
-    classify_kernel<<<(B + 31) / 32, 1024, 0, h->stream>>>(h->dev, B, a.des_inputs, h->bounds, h->d_counts, h->d_perm);
+    classify_kernel<<<(B + 31) / 32, 1024, 0, h->stream>>>(h->dev, B, a.des_inputs, h->bounds, cnt, h->d_perm);
     ++launches;
   }
   a.nlists = 0;
@@ -596,8 +612,8 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
   const int32_t* in_perm[kNumClasses]; const int32_t* in_count[kNumClasses]; int32_t* in_work[kNumClasses];
   for (int c = 0; c < kNumClasses; ++c) {
     in_perm[c] = h->d_perm + (size_t)c * B;
-    in_count[c] = h->d_counts + c;
-    in_work[c] = h->d_counts + kNumClasses + c;
+    in_count[c] = cnt + c;
+    in_work[c] = cnt + kNumClasses + c;
   }
   // ---- presolves: the dense kernel per class (class 0 = the batch's router), then ONE stage-wise launch over the other classes
   SolveArgs ric = a;
@@ -606,7 +622,7 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
     const int kind = presolve_kind(h, c);
     if (!kind) continue;
     int32_t* fperm = h->d_perm + (size_t)(kNumClasses + c) * h->max_batch;
-    int32_t* fcount = h->d_counts + 2 * kNumClasses + c;
+    int32_t* fcount = cnt + 2 * kNumClasses + c;
     if (kind == 1) {
       SolveArgs p = a;
       p.perm = in_perm[c]; p.count = in_count[c]; p.work = in_work[c];
@@ -615,12 +631,14 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
       if (router && c == 0) {
         p.perm = nullptr; p.count = nullptr; p.count_imm = B;
         p.route = 1; p.route_b1 = h->bounds.y; p.route_b2 = h->bounds.z;
-        p.route_perm = h->d_perm; p.route_counts = h->d_counts; p.route_stride = B;
+        p.route_perm = h->d_perm; p.route_counts = cnt; p.route_stride = B;
         p.ready = ready; p.ready_chunk = ready_chunk; p.error_flag = h->h_error_dev;
+        if (launches == 0 && !capturing) { p.zero_next = cnt_next; p.zero_n = kCounts; }  // (first kernel of the call, not PDL-chained)
       }
       chained(p);
       int rc = launch_presolve(h, h->cls[c], p);
       if (rc) return rc;
+      if (p.zero_next) h->counts_zero[cur ^ 1] = true;
       ++launches;
     } else {  // stage-wise presolve: collected, largest class first
       for (int q = ric.nlists; q > 0; --q) {
@@ -631,7 +649,7 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
       ric.lfail_perm[0] = fperm; ric.lfail_count[0] = fcount;
       ++ric.nlists;
     }
-    in_perm[c] = fperm; in_count[c] = fcount; in_work[c] = h->d_counts + 3 * kNumClasses + c;
+    in_perm[c] = fperm; in_count[c] = fcount; in_work[c] = cnt + 3 * kNumClasses + c;
   }
   if (ric.nlists > 0) {
     ric.route = 0; ric.ready = nullptr;
@@ -687,8 +705,8 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
       p.fail_perm = nullptr; p.fail_count = nullptr; p.route = 0; p.ready = nullptr;
       int32_t* pol_perm = h->d_perm + (size_t)(2 * kNumClasses + c) * h->max_batch;
       int32_t* fb_perm = h->d_perm + (size_t)(3 * kNumClasses + c) * h->max_batch;
-      int32_t* pol_count = h->d_counts + 4 * kNumClasses + c; int32_t* pol_work = h->d_counts + 5 * kNumClasses + c;
-      int32_t* fb_count = h->d_counts + 6 * kNumClasses + c; int32_t* fb_work = h->d_counts + 7 * kNumClasses + c;
+      int32_t* pol_count = cnt + 4 * kNumClasses + c; int32_t* pol_work = cnt + 5 * kNumClasses + c;
+      int32_t* fb_count = cnt + 6 * kNumClasses + c; int32_t* fb_work = cnt + 7 * kNumClasses + c;
       const cmpc_handle::ClassPlan& cp = h->cls[c];
       // (next to the stage-wise kernel no early trigger: the resident-but-waiting CTAs of the next kernel would take the SMs
       // the stage-wise kernel is meant to get -- whichever arrived first won, and the routes ran one after the other)
@@ -726,6 +744,7 @@ int launch_solve(cmpc_handle* h, SolveArgs a, int B, const int32_t* ready = null
     if (rc) return rc;
     ++launches;
   }
+  if (capturing && cudaMemsetAsync(cnt, 0, kCounts * sizeof(int32_t), h->stream) != cudaSuccess) return fail(h, CMPC_ERR_CUDA, "memset counts");
   return launches;
 }
 
@@ -903,7 +922,8 @@ static int setup_impl(cmpc_handle* h, int max_batch, int device) {
   h->debug_tune = getenv("CMPC_DEBUG_TUNE") != nullptr;
   h->debug_timeline = getenv("CMPC_DEBUG_TIMELINE") != nullptr;
   h->debug_plan = getenv("CMPC_DEBUG_PLAN") != nullptr;
-  CUDA_TRY(h, cudaMalloc(&h->d_counts, 8 * kNumClasses * sizeof(int32_t)));
+  CUDA_TRY(h, cudaMalloc(&h->d_counts, 2 * kCounts * sizeof(int32_t)));
+  h->counts_cur = 0; h->counts_zero[0] = h->counts_zero[1] = false;
   CUDA_TRY(h, cudaMalloc(&h->d_perm, (size_t)4 * kNumClasses * B * sizeof(int32_t)));
   CUDA_TRY(h, cudaHostAlloc(&h->h_hint, (kNumClasses + 1) * sizeof(int32_t), cudaHostAllocMapped));  // [kNumClasses]: the stage-wise interior point's lists
   for (int c = 0; c <= kNumClasses; ++c) h->h_hint[c] = 0;
@@ -1027,6 +1047,7 @@ int cmpc_set_stream(cmpc_handle* h, void* s) {
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   h->stream = (cudaStream_t)s;
   h->own_stream = false;
+  h->counts_zero[0] = h->counts_zero[1] = false;  // (zeroed in the old stream's order: the next call does it again)
   return CMPC_OK;
 }
 
@@ -1282,6 +1303,7 @@ int cmpc_build_batch(cmpc_handle* h, int B, const double* state, const double* d
   a.status = h->d_status; a.Hout = dH; a.gout = dg; a.forces = h->d_forces;
   a.count = nullptr; a.count_imm = B; a.perm = nullptr; a.work = h->d_counts + kNumClasses;
   cudaMemsetAsync(h->d_counts, 0, 2 * kNumClasses * sizeof(int32_t), s);
+  h->counts_zero[0] = false;
   int rc = launch_class<1>(h, h->exp_plan, a);
   if (rc == CMPC_OK) {
     cudaMemcpyAsync(H, dH, (size_t)B * p * p * 8, cudaMemcpyDeviceToHost, s);

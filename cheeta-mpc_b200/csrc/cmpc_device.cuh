@@ -126,6 +126,8 @@ struct SolveArgs {
   int32_t* pol_count;
   int32_t* fb_perm;          // phase 1 / 2 -> fused kernel: everything the split does not finish itself
   int32_t* fb_count;
+  int32_t* zero_next;        // router presolve kernel only: the OTHER copy of the counts / work block, zeroed here for the next call
+  int zero_n;                //  (the counts are double-buffered so that a call does not start with a memset node; cmpc_api.cu launch_solve)
   int32_t* hint_shadow;      // device copy of *hint_out (the host word is only written when the value changes)
   int32_t* hint_out;         // mapped host word: how many instances this launch found on its lists (next call's launch plan)
 };

@@ -321,6 +321,9 @@ __global__ void __launch_bounds__(W == 1 ? 448 : 256) cmpc_presolve_kernel(const
   const double mass = cfg.mass, dt = cfg.dt;
   const double imass = 1.0 / mass;  // (once per thread: every per-instance use multiplies)
   const double zeta = cfg.zoh ? 0.5 : 0.0;
+  // (first kernel of a call, launched without PDL: every kernel of the call before this one has completed, so its counts
+  // block -- the one the NEXT call will use -- is free)
+  if (args.zero_next && blockIdx.x == 0 && (int)threadIdx.x < args.zero_n) args.zero_next[threadIdx.x] = 0;
   const int count = args.count ? *args.count : args.count_imm;
   if (count <= 0) return;  // empty list (uniform over the grid): nothing to set up
 
