@@ -123,7 +123,7 @@ int cmpc_solve_batch(cmpc_handle* h, int B, const double* state, const double* d
 
 /* Same with DEVICE pointers (inputs already resident in HBM, outputs left in HBM);
  * asynchronous on the handle's stream unless stats != NULL (then it synchronises).  The call only enqueues work
- * (a memset, kernels, and -- when a batch has work for both interior-point kernels -- a fork to an auxiliary stream of
+ * (kernels -- under stream capture also two memsets --, and -- when a batch has work for both interior-point kernels -- a fork to an auxiliary stream of
  * the handle that is joined again before the call returns control of the stream), so with stats == NULL it can be
  * captured into a CUDA graph on the handle's stream and replayed (tests/test_gpu_parity.py).  The launch plan follows
  * the list counts of the handle's previous call; it changes the time a call takes, never a bit of its results. */
