@@ -1,5 +1,6 @@
-import sys, json
-for line in sys.stdin:
+import sys, json, fileinput
+# one-line view of bench.py JSON lines: files given as arguments, or stdin ('-' / no argument)
+for line in fileinput.input():
     line=line.strip()
     if not line.startswith('{'): continue
     d=json.loads(line)
