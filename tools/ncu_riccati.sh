@@ -19,5 +19,5 @@ for _ in range(3):
 print(stats.as_dict())
 PY
 python /tmp/ncu_ric.py > gpurun_out/ncu_ric_plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:cmpc_riccati_kernel -s 5 -c 1 -f -o gpurun_out/prof_riccati python /tmp/ncu_ric.py > gpurun_out/ncu_ric.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:cmpc_riccati_kernel -s 2 -c 1 -f -o gpurun_out/prof_riccati python /tmp/ncu_ric.py > gpurun_out/ncu_ric.log 2>&1
 tail -n 2 gpurun_out/ncu_ric_plain.log gpurun_out/ncu_ric.log
